@@ -1,0 +1,28 @@
+/* kml_host.h - C entry points of the host driver (libkml_host.so): the Karamelo
+ * input-script front end + scheme orchestration that drives libkml.so.
+ * Replaces the reference's `karamelo -i file` process entry (reference src/main.cpp:21-32,
+ * src/mpm.cpp:31-135, src/input.cpp:101-142) for embedding; the CLI `kml` wraps it. */
+#ifndef KML_HOST_H
+#define KML_HOST_H
+#include "kml.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct kmlh_sim kmlh_sim;
+const char *kmlh_last_error(void);
+int kmlh_create(kmlh_sim **out);
+int kmlh_destroy(kmlh_sim *s);
+int kmlh_set_quiet(kmlh_sim *s, int quiet);
+int kmlh_set_device(kmlh_sim *s, int device);
+int kmlh_run_file(kmlh_sim *s, const char *path);   /* Input::file */
+int kmlh_run_line(kmlh_sim *s, const char *line);   /* one script line through Input::parsev */
+int kmlh_get_var(kmlh_sim *s, const char *name, double *value);
+int kmlh_nsolids(kmlh_sim *s, int *n);
+/* np, device solid id, device grid id and node counts of solid i */
+int kmlh_solid_info(kmlh_sim *s, int i, int64_t *np, int *solid_id, int *grid_id, int n[3]);
+int kmlh_state(kmlh_sim *s, int64_t *ntimestep, double *time, double *dt);
+kml_ctx *kmlh_ctx(kmlh_sim *s);
+#ifdef __cplusplus
+}
+#endif
+#endif

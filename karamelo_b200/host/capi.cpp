@@ -1,0 +1,32 @@
+// capi.cpp - C entry points of the host driver (include/kml_host.h).
+#include "../../include/kml_host.h"
+#include "sim.h"
+#include <stdexcept>
+
+using namespace kmlh;
+struct kmlh_sim { Sim sim; };
+static std::string g_herr;
+#define GUARD(body) try { body; return 0; } catch (const std::exception &e) { g_herr = e.what(); return 1; }
+
+extern "C" {
+const char *kmlh_last_error(void) { return g_herr.c_str(); }
+int kmlh_create(kmlh_sim **out) { GUARD(*out = new kmlh_sim()) }
+int kmlh_destroy(kmlh_sim *s) { delete s; return 0; }
+int kmlh_set_quiet(kmlh_sim *s, int q) { s->sim.quiet = q != 0; s->sim.input.echo = !q; return 0; }
+int kmlh_set_device(kmlh_sim *s, int d) { s->sim.device = d; return 0; }
+int kmlh_run_file(kmlh_sim *s, const char *path) { GUARD(s->sim.input.file(path)) }
+int kmlh_run_line(kmlh_sim *s, const char *line) { GUARD(s->sim.input.line(line)) }
+int kmlh_get_var(kmlh_sim *s, const char *name, double *value) {
+  GUARD(auto it = s->sim.input.vars.find(name); if (it == s->sim.input.vars.end()) fatal(std::string("unknown variable ") + name); *value = it->second.result(&s->sim.input))
+}
+int kmlh_nsolids(kmlh_sim *s, int *n) { *n = (int)s->sim.solids.size(); return 0; }
+int kmlh_solid_info(kmlh_sim *s, int i, int64_t *np, int *solid_id, int *grid_id, int n[3]) {
+  if (i < 0 || i >= (int)s->sim.solids.size()) { g_herr = "bad solid index"; return 1; }
+  SolidH &S = *s->sim.solids[i];
+  *np = S.np; *solid_id = S.dev; *grid_id = S.grid->id;
+  for (int d = 0; d < 3; d++) n[d] = S.grid->desc.n[d];
+  return 0;
+}
+int kmlh_state(kmlh_sim *s, int64_t *nt, double *t, double *dt) { *nt = s->sim.ntimestep; *t = s->sim.atime; *dt = s->sim.dt; return 0; }
+kml_ctx *kmlh_ctx(kmlh_sim *s) { return s->sim.ctx; }
+}

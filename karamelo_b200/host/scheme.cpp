@@ -1,0 +1,336 @@
+// scheme.cpp - the per-step stage order (host-side orchestration, as in the reference),
+// the fix / compute commands that sit between stages, run commands and log/dump output.
+#include "sim.h"
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+namespace kmlh {
+
+// ------------------------------------------------------------------ fixes -------------------
+namespace {
+
+// FixInitialVelocityParticles, reference src/fix_initial_velocity_particles.cpp:36-161.
+// Per-particle expressions are evaluated by the script interpreter exactly as the reference
+// does (vars x,y,z,x0,y0,z0 set per particle, expression re-parsed), once, at step 1.
+struct FixInitialVelocityParticles : Fix {
+  bool set[3] = {false, false, false}; Var val[3];
+  void initial_integrate(Sim &s) override {
+    if (s.ntimestep != 1) return;
+    const int solid = s.gsolid[igroup];
+    for (size_t is = 0; is < s.solids.size(); is++) {
+      if (solid != -1 && (int)is != solid) continue;
+      SolidH &S = *s.solids[is];
+      std::vector<std::array<double, 3>> x(S.np), v(S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
+      bool fast = true; // constant expressions need no per-particle re-parse
+      for (int d = 0; d < 3; d++) if (set[d] && !val[d].is_constant()) fast = false;
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        if (!fast) {
+          s.input.vars["x"] = Var("x", x[ip][0]); s.input.vars["y"] = Var("y", x[ip][1]); s.input.vars["z"] = Var("z", x[ip][2]);
+          s.input.vars["x0"] = Var("x0", S.x0[ip][0]); s.input.vars["y0"] = Var("y0", S.x0[ip][1]); s.input.vars["z0"] = Var("z0", S.x0[ip][2]);
+        }
+        for (int d = 0; d < 3; d++) if (set[d]) v[ip][d] = val[d].result(&s.input);
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_V, v.data()));
+    }
+  }
+};
+
+// FixVelocityNodes, reference src/fix_velocity_nodes.cpp:36-268
+struct FixVelocityNodes : Fix {
+  bool set[3] = {false, false, false}; Var val[3], prev[3];
+  void apply(Sim &s, int which) {
+    double v[3] = {0, 0, 0}, vp[3] = {0, 0, 0}, ftot[3]; int m = 0;
+    for (int d = 0; d < 3; d++) if (set[d]) { m |= 1 << d; v[d] = val[d].result(&s.input); if (which == 0) vp[d] = prev[d].result(&s.input); }
+    s.check(kml_fix_velocity_nodes(s.ctx, s.gsolid[igroup], groupbit, m, v, vp, which, which == 0 ? ftot : nullptr));
+    if (which == 0) { s.input.vars[id + "_x"] = Var(id + "_x", ftot[0]); s.input.vars[id + "_y"] = Var(id + "_y", ftot[1]); s.input.vars[id + "_z"] = Var(id + "_z", ftot[2]); }
+  }
+  void post_update_grid_state(Sim &s) override { apply(s, 0); }
+  void post_velocities_to_grid(Sim &s) override { apply(s, 1); }
+};
+
+// FixBodyforce, reference src/fix_body_force.cpp:36-180 (components that do not depend on x0,y0,z0)
+struct FixBodyForce : Fix {
+  bool set[3] = {false, false, false}; Var val[3];
+  void post_particles_to_grid(Sim &s) override {
+    double f[3] = {0, 0, 0}, ftot[3]; int m = 0;
+    for (int d = 0; d < 3; d++) if (set[d]) { m |= 1 << d; f[d] = val[d].result(&s.input); }
+    s.check(kml_fix_body_force(s.ctx, s.gsolid[igroup], groupbit, m, f, ftot));
+    const char *sfx[3] = {"_x", "_y", "_z"};
+    for (int d = 0; d < 3; d++) if (set[d]) s.input.vars[id + sfx[d]] = Var(id + sfx[d], ftot[d]);
+  }
+};
+
+// FixContactHertz / FixContactMinPenetration, reference src/fix_contact_hertz.cpp, src/fix_contact_min_penetration.cpp
+struct FixContact : Fix {
+  int solid1 = -1, solid2 = -1; double mu = 0; bool hertz = true;
+  void initial_integrate(Sim &s) override {
+    double ftot[3];
+    if (hertz) s.check(kml_fix_contact_hertz(s.ctx, s.solids[solid1]->dev, s.solids[solid2]->dev, ftot));
+    else s.check(kml_fix_contact_min_penetration(s.ctx, s.solids[solid1]->dev, s.solids[solid2]->dev, mu, ftot));
+    s.input.vars[id + "_x"] = Var(id + "_x", ftot[0]); s.input.vars[id + "_y"] = Var(id + "_y", ftot[1]); s.input.vars[id + "_z"] = Var(id + "_z", ftot[2]);
+  }
+};
+
+struct ComputeEnergy : Compute {
+  bool kinetic = true;
+  void compute_value(Sim &s) override {
+    double e = 0;
+    if (kinetic) s.check(kml_compute_kinetic_energy(s.ctx, s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev, groupbit, &e));
+    else s.check(kml_compute_strain_energy(s.ctx, s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev, groupbit, &e));
+    s.input.vars[id] = Var(id, e);
+  }
+};
+} // namespace
+
+// Modify::add_fix, reference src/modify.cpp:95-140 (fix(ID, style, group-ID, args...))
+Var Sim::cmd_fix(std::vector<std::string> &a) {
+  if (a.size() < 3) fatal("Error: too few arguments for the fix command.\n");
+  for (auto &f : fixes) if (f->id == a[0]) fatal("Error: reuse of fix ID.\n");
+  const std::string &style = a[1];
+  std::unique_ptr<Fix> fix;
+  auto group_of = [&](Fix &f) {
+    f.igroup = find_group(a[2]);
+    if (f.igroup == -1) fatal("Error: could not find group ID " + a[2] + "\n");
+    f.groupbit = gbitmask[f.igroup];
+  };
+  if (style == "initial_velocity_particles") {
+    auto f = new FixInitialVelocityParticles(); fix.reset(f); group_of(*f);
+    if (a.size() != 6) fatal("Error: fix initial_velocity_particles: wrong number of arguments.\n");
+    if (gpon[f->igroup] != "particles" && gpon[f->igroup] != "all") fatal("fix_initial_velocity_particles needs to be given a group of particles.\n");
+    for (int d = 0; d < 3; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
+    f->mask = INITIAL_INTEGRATE;
+  } else if (style == "velocity_nodes") {
+    auto f = new FixVelocityNodes(); fix.reset(f); group_of(*f);
+    if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_velocity_nodes.\n");
+    if (gpon[f->igroup] != "nodes") fatal("fix_velocity_nodes needs to be given a group of nodes.\n");
+    for (int d = 0; d < dimension; d++) {
+      if (a[3 + d] == "NULL") continue;
+      f->val[d] = input.parsev(a[3 + d]); f->set[d] = true;
+      std::string previous = a[3 + d]; // "time" -> "time - dt", src/fix_velocity_nodes.cpp:66-80
+      size_t pos = 0;
+      while ((pos = previous.find("time", pos)) != std::string::npos) { previous.replace(pos, 4, "time - dt"); pos += 9; }
+      f->prev[d] = input.parsev(previous);
+    }
+    f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
+  } else if (style == "body_force") {
+    auto f = new FixBodyForce(); fix.reset(f); group_of(*f);
+    if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_body_force.\n");
+    for (int d = 0; d < dimension; d++) if (a[3 + d] != "NULL") {
+      f->val[d] = input.parsev(a[3 + d]); f->set[d] = true;
+      const std::string &e = f->val[d].eq();
+      if (!f->val[d].is_constant() && (e.find("x0") != std::string::npos || e.find("y0") != std::string::npos || e.find("z0") != std::string::npos))
+        fatal("fix body_force: position-dependent body forces are not supported by this build.\n");
+    }
+    f->mask = POST_PARTICLES_TO_GRID;
+  } else if (style == "contact/hertz" || style == "contact/minimize_penetration") {
+    auto f = new FixContact(); fix.reset(f);
+    f->hertz = style == "contact/hertz";
+    if (a.size() < (size_t)(f->hertz ? 4 : 5)) fatal("Error: not enough arguments.\n");
+    f->solid1 = find_solid(a[2]); if (f->solid1 < 0) fatal("Error: solid " + a[2] + " unknown.\n");
+    f->solid2 = find_solid(a[3]); if (f->solid2 < 0) fatal("Error: solid " + a[3] + " unknown.\n");
+    if (!f->hertz) f->mu = input.parsev(a[4]);
+    f->mask = INITIAL_INTEGRATE;
+  } else fatal("fix style " + style + " is outside the hot path covered by this build (see DESIGN.md).\n");
+  fix->id = a[0]; fix->style = style;
+  fixes.push_back(std::move(fix));
+  return Var(0);
+}
+
+Var Sim::cmd_compute(std::vector<std::string> &a) { // Modify::add_compute
+  if (a.size() < 3) fatal("Error: too few arguments for the compute command.\n");
+  if (a[1] != "kinetic_energy" && a[1] != "strain_energy") fatal("compute style " + a[1] + " is outside the hot path covered by this build.\n");
+  auto c = new ComputeEnergy(); c->id = a[0]; c->style = a[1]; c->kinetic = a[1] == "kinetic_energy";
+  c->igroup = find_group(a[2]); if (c->igroup == -1) fatal("Error: could not find group ID " + a[2] + "\n");
+  c->groupbit = gbitmask[c->igroup];
+  computes.emplace_back(c);
+  input.vars[c->id] = Var(c->id, 0);
+  return Var(0);
+}
+
+void Sim::hooks(int which) {
+  for (auto &f : fixes) {
+    if (!(f->mask & which)) continue;
+    switch (which) {
+    case INITIAL_INTEGRATE: f->initial_integrate(*this); break;
+    case POST_PARTICLES_TO_GRID: f->post_particles_to_grid(*this); break;
+    case POST_UPDATE_GRID_STATE: f->post_update_grid_state(*this); break;
+    case POST_VELOCITIES_TO_GRID: f->post_velocities_to_grid(*this); break;
+    default: break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ output ------------------
+Var Sim::cmd_dump(std::vector<std::string> &a) { // Output::add_dump: dump(ID, group, style, N, file, fields...)
+  if (a.size() < 5) fatal("Error: too few arguments for dump.\n");
+  Dump d; d.id = a[0]; d.igroup = find_group(a[1]); d.style = a[2]; d.every = (int)(double)input.parsev(a[3]); d.filename = a[4];
+  d.fields.assign(a.begin() + 5, a.end());
+  if (d.every <= 0) fatal("Error every_dump = 0 does not make sense.\n");
+  dumps.push_back(d); return Var(0);
+}
+
+static void write_particle_dump(Sim &s, const Dump &d) { // DumpParticle::write, reference src/dump_particle.cpp:52-161
+  std::string fn = d.filename; size_t star = fn.find('*');
+  if (star != std::string::npos) fn = fn.substr(0, star) + std::to_string(s.ntimestep) + fn.substr(star + 1);
+  std::ofstream os(fn);
+  if (!os) fatal("Error: cannot write in file: " + fn + ".\n");
+  int64_t total = 0; for (auto &S : s.solids) total += S->np;
+  os << "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n" << total << "\nITEM: BOX BOUNDS sm sm sm\n";
+  for (int k = 0; k < 3; k++) os << s.boxlo[k] << " " << s.boxhi[k] << "\n";
+  os << "ITEM: ATOMS id type tag ";
+  for (auto &f : d.fields) os << f << " ";
+  os << "\n";
+  for (size_t is = 0; is < s.solids.size(); is++) {
+    SolidH &S = *s.solids[is]; const int64_t n = S.np;
+    std::vector<int64_t> tag(n); std::vector<double> x(3 * n), v(3 * n), sig(9 * n), R(9 * n), vol(n), mass(n), dmg(n), dmgi(n), ep(n), epdot(n), T(n), ie(n), rho(n);
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_PTAG, tag.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_SIGMA, sig.data()));
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_VOL, vol.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_MASS, mass.data()));
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_DAMAGE, dmg.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_DAMAGE_INIT, dmgi.data()));
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN, ep.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN_RATE, epdot.data()));
+    s.check(kml_solid_download(s.ctx, S.dev, KML_P_IENERGY, ie.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_RHO, rho.data()));
+    if (s.temp) s.check(kml_solid_download(s.ctx, S.dev, KML_P_T, T.data()));
+    if (s.is_TL) s.check(kml_solid_download(s.ctx, S.dev, KML_P_R, R.data()));
+    for (int64_t i = 0; i < n; i++) {
+      double sg[9];
+      if (s.is_TL) { // sigma_ = R sigma R^T
+        const double *r = &R[9 * i], *q = &sig[9 * i]; double t[9];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) t[3 * a + b] = r[3 * a] * q[b] + r[3 * a + 1] * q[3 + b] + r[3 * a + 2] * q[6 + b];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) sg[3 * a + b] = t[3 * a] * r[3 * b] + t[3 * a + 1] * r[3 * b + 1] + t[3 * a + 2] * r[3 * b + 2];
+      } else memcpy(sg, &sig[9 * i], sizeof sg);
+      os << tag[i] << " " << is + 1 << " " << tag[i] << " ";
+      for (auto &f : d.fields) {
+        if (f == "x") os << x[3 * i]; else if (f == "y") os << x[3 * i + 1]; else if (f == "z") os << x[3 * i + 2];
+        else if (f == "x0") os << S.x0[i][0]; else if (f == "y0") os << S.x0[i][1]; else if (f == "z0") os << S.x0[i][2];
+        else if (f == "vx") os << v[3 * i]; else if (f == "vy") os << v[3 * i + 1]; else if (f == "vz") os << v[3 * i + 2];
+        else if (f == "s11") os << sg[0]; else if (f == "s22") os << sg[4]; else if (f == "s33") os << sg[8];
+        else if (f == "s12") os << sg[1]; else if (f == "s13") os << sg[2]; else if (f == "s23") os << sg[5];
+        else if (f == "seq") os << sqrt(3. / 2.) * [&] { double tr = (sg[0] + sg[4] + sg[8]) / 3, q = 0; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { double e = sg[3 * a + b] - (a == b ? tr : 0); q += e * e; } return sqrt(q); }();
+        else if (f == "damage") os << dmg[i]; else if (f == "damage_init") os << dmgi[i]; else if (f == "volume") os << vol[i];
+        else if (f == "mass") os << mass[i]; else if (f == "ep") os << ep[i]; else if (f == "epdot") os << epdot[i];
+        else if (f == "ienergy") os << ie[i]; else if (f == "T") os << T[i]; else if (f == "rho") os << rho[i];
+        else os << 0;
+        os << " ";
+      }
+      os << "\n";
+    }
+  }
+}
+
+void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
+  for (auto &d : dumps) d.next = (ntimestep / d.every) * d.every + d.every;
+  if (!quiet) {
+    std::string hdr;
+    for (auto &f : log_fields) hdr += (f == "step" ? "Step" : (f == "time" ? "Time" : f)) + "\t";
+    std::cout << hdr << "\n";
+    if (logfile.is_open()) logfile << hdr << "\n";
+  }
+  if (every_log) { next_log = (ntimestep / every_log) * every_log + every_log; if (laststep != 0) next_log = std::min(next_log, laststep); }
+  else next_log = laststep;
+}
+
+void Sim::output_write(int64_t step) { // Output::write, src/output.cpp:128-199
+  for (auto &d : dumps)
+    if (d.next == step) { if (d.style == "particle") write_particle_dump(*this, d); d.next += d.every; }
+  if (next_log == step || step == 0) {
+    for (auto &c : computes) c->compute_value(*this); // Modify::run_computes
+    if (!quiet) {
+      std::ostringstream o;
+      for (auto &f : log_fields) {
+        if (f == "step") o << ntimestep; else if (f == "dt") o << dt; else if (f == "time") o << atime;
+        else { auto it = input.vars.find(f); if (it == input.vars.end()) fatal("Error: unknown log keyword " + f + ".\n"); o << it->second.result(&input); }
+        o << "\t";
+      }
+      o << "\n"; std::cout << o.str(); if (logfile.is_open()) logfile << o.str();
+    }
+    if (next_log == step) next_log += every_log ? every_log : 0;
+  }
+}
+
+// ------------------------------------------------------------------ schemes -----------------
+// USL::run src/usl.cpp:34-94, MUSL::run src/musl.cpp:34-95, USF::run src/usf.cpp:34-94
+void Sim::run(Var condition) {
+  const bool usl = scheme_style == "usl", musl = scheme_style == "musl", usf = scheme_style == "usf";
+  output_write(ntimestep);
+  while ((bool)condition.result(&input)) {
+    ntimestep++; input.vars["timestep"] = Var("timestep", (double)ntimestep); // Update::update_timestep
+    check(kml_compute_grid_weight_functions_and_gradients(ctx));
+    check(kml_reset(ctx));
+    hooks(INITIAL_INTEGRATE);
+    if (!usf) {
+      check(kml_particles_to_grid(ctx));
+      hooks(POST_PARTICLES_TO_GRID);
+      check(kml_update_grid_state(ctx));
+      hooks(POST_UPDATE_GRID_STATE);
+      if (usl) check(kml_compute_rate_deformation_gradient(ctx, 0));
+      check(kml_grid_to_points(ctx));
+      hooks(POST_GRID_TO_POINT);
+      check(kml_advance_particles(ctx));
+      hooks(POST_ADVANCE_PARTICLES);
+      if (musl) { check(kml_velocities_to_grid(ctx)); hooks(POST_VELOCITIES_TO_GRID); }
+      check(kml_update_grid_positions(ctx));
+      if (musl) check(kml_compute_rate_deformation_gradient(ctx, 1));
+      check(kml_update_deformation_gradient(ctx));
+      check(kml_update_stress(ctx, musl ? 1 : 0));
+    } else {
+      check(kml_particles_to_grid_USF_1(ctx));
+      hooks(POST_UPDATE_GRID_STATE);
+      check(kml_compute_rate_deformation_gradient(ctx, 1));
+      check(kml_update_deformation_gradient(ctx));
+      check(kml_update_stress(ctx, 1));
+      check(kml_particles_to_grid_USF_2(ctx));
+      hooks(POST_PARTICLES_TO_GRID);
+      check(kml_update_grid_state(ctx));
+      hooks(POST_UPDATE_GRID_STATE);
+      check(kml_grid_to_points(ctx));
+      hooks(POST_GRID_TO_POINT);
+      check(kml_advance_particles(ctx));
+      hooks(POST_ADVANCE_PARTICLES);
+      check(kml_update_grid_positions(ctx));
+    }
+    check(kml_exchange_particles(ctx));
+    atime += (ntimestep - atimestep) * dt; atimestep = ntimestep; input.vars["time"] = Var("time", atime); // Update::update_time
+    if (!dt_constant) { check(kml_adjust_dt(ctx, dt_factor, &dt)); input.vars["dt"] = Var("dt", dt); }       // Method::adjust_dt
+    hooks(FINAL_INTEGRATE);
+    if (maxtime != -1 && atime > maxtime) { nsteps = ntimestep; output_write(ntimestep); break; }
+    bool due = ntimestep == next_log || ntimestep == nsteps;
+    for (auto &d : dumps) due = due || d.next == ntimestep;
+    if (due) output_write(ntimestep);
+  }
+  unsigned flags = 0; check(kml_error_flags(ctx, &flags));
+  if (flags) fatal("device error flags set: " + std::to_string(flags) + " (bit0 particle left the domain, bit1 J<=0, bit2 dtCFL invalid, bit3 polar decomposition failed)\n");
+}
+
+// Run / RunTime / RunUntil / RunWhile ::command, src/run.cpp:32-57, src/run_time.cpp:32-56, src/run_until.cpp, src/run_while.cpp
+Var Sim::cmd_run(std::vector<std::string> &a, int kind) {
+  if (a.size() < 1) fatal("Illegal run command.\n");
+  if (!method_set || !ctx) fatal("Error: no method was defined!\n");
+  check(kml_set_dt(ctx, dt));
+  maxtime = -1;
+  firststep = ntimestep;
+  Var cond;
+  if (kind == 0) {
+    int n = (int)(double)input.parsev(a[0]);
+    nsteps = n; laststep = firststep + n;
+    cond = Var("timestep<" + std::to_string(laststep), ntimestep < laststep);
+  } else if (kind == 1) {
+    double mt = (double)input.parsev(a[0]) + atime;
+    nsteps = INT_MAX; maxtime = mt; laststep = INT_MAX;
+    cond = Var("time<" + std::to_string(mt), atime < mt);
+  } else {
+    nsteps = INT_MAX; laststep = INT_MAX;
+    Var c = input.parsev(a[0]);
+    cond = kind == 2 ? Var("!(" + c.str() + ")", !c.result(), false) : Var(c.str(), c.result(), false);
+  }
+  output_setup();
+  run(cond);
+  return Var(0);
+}
+
+} // namespace kmlh

@@ -1,0 +1,536 @@
+// sim.cpp - script commands that build the simulation (setup path).
+// Integer-deciding arithmetic is restated from the reference, cited inline.
+#include "sim.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+
+namespace kmlh {
+
+#define BIG 1.0e20 /* src/region_block.cpp:24 */
+
+static double dmax(double a, double b) { return a > b ? a : b; } // MAX/MIN macros, src/pointers.h:23-24
+static double dmin(double a, double b) { return a < b ? a : b; }
+
+Sim::Sim() : input(this) {
+  for (int i = 0; i < MAX_GROUP; i++) { gnames[i] = ""; gbitmask[i] = 1 << i; gpon[i] = "all"; gsolid[i] = -1; gregion[i] = -1; }
+  gnames[0] = "all";
+  register_commands();
+}
+Sim::~Sim() { if (ctx) kml_destroy(ctx); }
+
+void Sim::check(int rc) const { if (rc) fatal(std::string("kml: ") + kml_last_error()); }
+
+int Sim::find_region(const std::string &n) const { for (size_t i = 0; i < regions.size(); i++) if (regions[i]->id == n) return (int)i; return -1; }
+int Sim::find_solid(const std::string &n) const { for (size_t i = 0; i < solids.size(); i++) if (solids[i]->id == n) return (int)i; return -1; }
+int Sim::find_material(const std::string &n) const { for (size_t i = 0; i < materials.size(); i++) if (materials[i].id == n) return (int)i; return -1; }
+int Sim::find_group(const std::string &n) const { for (int i = 0; i < MAX_GROUP; i++) if (gnames[i] == n) return i; return -1; }
+
+void Sim::register_commands() {
+  auto &c = input.commands;
+  c["method"] = [this](std::vector<std::string> &a) { return cmd_method(a); };
+  c["scheme"] = [this](std::vector<std::string> &a) { return cmd_scheme(a); };
+  c["dimension"] = [this](std::vector<std::string> &a) { return cmd_dimension(a); };
+  c["axisymmetric"] = [this](std::vector<std::string> &a) { // Domain::set_axisymmetric, src/domain.cpp:557-569
+    if (a.size() != 1) fatal("Error: axisymmetric takes one argument.\n");
+    if (a[0] == "true") axisymmetric = true; else if (a[0] == "false") axisymmetric = false;
+    return Var(0);
+  };
+  c["region"] = [this](std::vector<std::string> &a) { return cmd_region(a); };
+  c["eos"] = [this](std::vector<std::string> &a) { return cmd_eos(a); };
+  c["strength"] = [this](std::vector<std::string> &a) { return cmd_strength(a); };
+  c["damage"] = [this](std::vector<std::string> &a) { return cmd_damage(a); };
+  c["temperature"] = [this](std::vector<std::string> &a) { return cmd_temperature(a); };
+  c["material"] = [this](std::vector<std::string> &a) { return cmd_material(a); };
+  c["solid"] = [this](std::vector<std::string> &a) { return cmd_solid(a); };
+  c["group"] = [this](std::vector<std::string> &a) { return cmd_group(a); };
+  c["fix"] = [this](std::vector<std::string> &a) { return cmd_fix(a); };
+  c["delete_fix"] = [this](std::vector<std::string> &a) {
+    for (size_t i = 0; i < fixes.size(); i++) if (fixes[i]->id == a[0]) { fixes.erase(fixes.begin() + i); return Var(0); }
+    fatal("Error: fix " + a[0] + " not found.\n");
+  };
+  c["compute"] = [this](std::vector<std::string> &a) { return cmd_compute(a); };
+  c["dump"] = [this](std::vector<std::string> &a) { return cmd_dump(a); };
+  c["dt_factor"] = [this](std::vector<std::string> &a) { // Update::set_dt_factor, src/update.cpp:62-67
+    if (a.size() != 1) fatal("Illegal dt_factor command.\n");
+    dt_factor = input.parsev(a[0]); return Var(0);
+  };
+  c["set_dt"] = [this](std::vector<std::string> &a) { // Update::set_dt, src/update.cpp:69-76
+    if (a.size() != 1) fatal("Illegal set_dt command.\n");
+    dt = input.parsev(a[0]); dt_constant = true; input.vars["dt"] = Var("dt", dt);
+    if (ctx) check(kml_set_dt(ctx, dt));
+    return Var(0);
+  };
+  c["set_output"] = [this](std::vector<std::string> &a) { every_log = (int)(double)input.parsev(a[0]); return Var(0); }; // Output::set_log
+  c["log"] = [this](std::vector<std::string> &a) { every_log = (int)(double)input.parsev(a[0]); return Var(0); };
+  c["log_modify"] = [this](std::vector<std::string> &a) { // Log::modify: log_modify(custom, step, dt, time, vars...)
+    if (a.empty() || a[0] != "custom") fatal("Unknown log style.\n");
+    log_fields.assign(a.begin() + 1, a.end()); return Var(0);
+  };
+  c["restart"] = [this](std::vector<std::string> &a) { restart_every = (int)(double)input.parsev(a[0]); if (a.size() > 1) restart_name = a[1]; return Var(0); };
+  c["run"] = [this](std::vector<std::string> &a) { return cmd_run(a, 0); };
+  c["run_time"] = [this](std::vector<std::string> &a) { return cmd_run(a, 1); };
+  c["run_until"] = [this](std::vector<std::string> &a) { return cmd_run(a, 2); };
+  c["run_while"] = [this](std::vector<std::string> &a) { return cmd_run(a, 3); };
+  c["plot"] = [](std::vector<std::string> &) { return Var(0); };
+  c["save_plot"] = [](std::vector<std::string> &) { return Var(0); };
+}
+
+// Update::create_method, src/update.cpp:108-196 (+ ULMPM/TLMPM ctor and setup: src/ulmpm.cpp:32-86, src/tlmpm.cpp:34-86)
+Var Sim::cmd_method(std::vector<std::string> &a) {
+  if (a.size() < 3) fatal("Illegal method command: not enough arguments.\n");
+  size_t n = 0;
+  method_type = a[0];
+  PIC_FLIP = 0.99; temp = false; ge = false; is_TL = is_CPDI = false;
+  if (method_type == "ulmpm") {}
+  else if (method_type == "tlmpm") is_TL = true;
+  else if (method_type == "ulcpdi") is_CPDI = true;
+  else if (method_type == "tlcpdi") { is_TL = true; is_CPDI = true; }
+  else fatal("Illegal method style.\n");
+  bool isFLIP = false;
+  n++;
+  static const std::map<std::string, int> subs{{"PIC", KML_SUB_PIC}, {"FLIP", KML_SUB_FLIP}, {"APIC", KML_SUB_APIC}, {"AFLIP", KML_SUB_AFLIP}, {"ASFLIP", KML_SUB_ASFLIP}, {"MLS", KML_SUB_MLS}};
+  auto si = subs.find(a[n]);
+  if (si == subs.end()) fatal("Error: method type " + a[n] + " not understood. Expect: PIC, FLIP, APIC, AFLIP, or ASFLIP\n");
+  sub_method = si->second;
+  if (sub_method == KML_SUB_PIC) PIC_FLIP = 0;
+  else if (sub_method == KML_SUB_FLIP || sub_method == KML_SUB_AFLIP || sub_method == KML_SUB_ASFLIP) {
+    isFLIP = true;
+    if (a.size() < 4) fatal("Illegal modify_method command: not enough arguments.\n");
+  }
+  n++;
+  static const std::map<std::string, int> shapes{{"linear", KML_SHAPE_LINEAR}, {"cubic-spline", KML_SHAPE_CUBIC_SPLINE}, {"quadratic-spline", KML_SHAPE_QUADRATIC_SPLINE}, {"Bernstein-quadratic", KML_SHAPE_BERNSTEIN}};
+  if (a.size() > n + isFLIP) {
+    auto sh = shapes.find(a[n]);
+    if (sh == shapes.end()) fatal("Illegal method_method argument: form function of type " + a[n] + " is unknown.\n");
+    shape_function = sh->second; n++;
+  }
+  if (isFLIP) { PIC_FLIP = input.parsev(a[n]); n++; }
+  if (a.size() >= n + 1) {
+    if (a[n] == "thermo-mechanical") temp = true;
+    else if (a[n] == "mechanical") temp = false;
+    else fatal("Illegal modify_method command: keyword " + a[n] + " unknown. Expected \"thermo-mechanical\" or \"mechanical\".\n");
+  }
+  n++;
+  if (a.size() >= n + 1 && a[n] == "gradient-enhanced") { ge = true; n++; }
+  std::vector<std::string> extra; if (n < a.size()) extra.assign(a.begin() + n, a.end());
+  if (is_CPDI) { // TLCPDI/ULCPDI::setup: style R4 / Q4
+    if (!extra.empty()) { if (extra[0] == "R4") cpdi_style = 0; else if (extra[0] == "Q4") cpdi_style = 1; else fatal("Unknown CPDI style " + extra[0]); }
+  } else if (!extra.empty()) fatal("Illegal modify_method command: too many arguments.\n");
+  // Method::setup: APIC/MLS force PIC_FLIP = 0 (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
+  if (!is_TL && (sub_method == KML_SUB_APIC || sub_method == KML_SUB_MLS)) PIC_FLIP = 0;
+  if (is_TL && sub_method == KML_SUB_APIC) PIC_FLIP = 0;
+  method_set = true;
+  return Var(0);
+}
+
+Var Sim::cmd_scheme(std::vector<std::string> &a) { // Update::create_scheme, src/update.cpp:83-102
+  if (a.size() < 1) fatal("Illegal scheme command: not enough arguments.\n");
+  if (a[0] != "usl" && a[0] != "musl" && a[0] != "usf") fatal("Illegal scheme style.\n");
+  scheme_style = a[0]; return Var(0);
+}
+
+void Sim::ensure_ctx() {
+  if (ctx) return;
+  kml_config cfg; memset(&cfg, 0, sizeof cfg);
+  cfg.dimension = dimension; cfg.is_TL = is_TL; cfg.is_CPDI = is_CPDI; cfg.cpdi_style = cpdi_style;
+  cfg.shape_function = shape_function; cfg.sub_method = sub_method; cfg.PIC_FLIP = PIC_FLIP;
+  cfg.axisymmetric = axisymmetric; cfg.temp = temp; cfg.ge = ge;
+  for (int d = 0; d < 3; d++) { cfg.boxlo[d] = boxlo[d]; cfg.boxhi[d] = boxhi[d]; }
+  cfg.device = device; cfg.rank = 0; cfg.nranks = 1;
+  check(kml_create(&cfg, &ctx));
+  check(kml_set_dt(ctx, dt));
+}
+
+// Grid::init on one rank, src/grid.cpp:68-264 (node counts) - the device creates the nodes themselves.
+void Sim::init_grid(GridH &g, const double *solidlo, const double *solidhi) {
+  double h = g.cellsize;
+  if (shape_function == KML_SHAPE_BERNSTEIN) h /= 2; // src/grid.cpp:82-85
+  const double *boundlo = is_TL ? solidlo : boxlo, *boundhi = is_TL ? solidhi : boxhi;
+  double Loffsetlo[3], Loffsethi_[3]; int noffsetlo[3], noffsethi_[3];
+  for (int d = 0; d < 3; d++) {
+    Loffsetlo[d] = dmax(0.0, sublo[d] - boundlo[d]);
+    Loffsethi_[d] = dmax(0.0, dmin(subhi[d], boundhi[d]) - boundlo[d]);
+    noffsetlo[d] = (int)ceil(Loffsetlo[d] / h);
+    noffsethi_[d] = (int)ceil(Loffsethi_[d] / h);
+  }
+  double Lx = solidhi[0] - solidlo[0];
+  g.nx_global = ((int)(Lx / h)) + 1;
+  while (g.nx_global * h <= Lx + 0.5 * h) g.nx_global++;
+  if (dimension >= 2) { double Ly = solidhi[1] - solidlo[1]; g.ny_global = ((int)Ly) / h + 1; while (g.ny_global * h <= Ly + 0.5 * h) g.ny_global++; } // cast binds to Ly, src/grid.cpp:158
+  else g.ny_global = 1;
+  if (dimension == 3) { double Lz = solidhi[2] - solidlo[2]; g.nz_global = ((int)Lz) / h + 1; while (g.nz_global * h <= Lz + 0.5 * h) g.nz_global++; }
+  else g.nz_global = 1;
+  int nx = std::max(0, noffsethi_[0] - noffsetlo[0]);
+  int ny = dimension >= 2 ? std::max(0, noffsethi_[1] - noffsetlo[1]) : 1;
+  int nz = dimension >= 3 ? std::max(0, noffsethi_[2] - noffsetlo[2]) : 1;
+  while (boundlo[0] + h * (noffsetlo[0] + nx - 0.5) < dmin(subhi[0], boundhi[0])) nx++;
+  while (boundlo[1] + h * (noffsetlo[1] + ny - 0.5) < dmin(subhi[1], boundhi[1])) ny++;
+  while (boundlo[2] + h * (noffsetlo[2] + nz - 0.5) < dmin(subhi[2], boundhi[2])) nz++;
+  if (nx != g.nx_global || ny != g.ny_global || nz != g.nz_global || noffsetlo[0] || noffsetlo[1] || noffsetlo[2])
+    fatal("Grid::init: local node counts (" + std::to_string(nx) + "," + std::to_string(ny) + "," + std::to_string(nz) + ") differ from the global ones (" +
+          std::to_string(g.nx_global) + "," + std::to_string(g.ny_global) + "," + std::to_string(g.nz_global) + "); the reference indexes out of bounds here.\n");
+  g.desc.lo[0] = boundlo[0]; g.desc.lo[1] = dimension >= 2 ? boundlo[1] : 0; g.desc.lo[2] = dimension == 3 ? boundlo[2] : 0;
+  g.desc.h = h; g.desc.cellsize = g.cellsize; g.desc.n[0] = nx; g.desc.n[1] = ny; g.desc.n[2] = nz;
+  g.nnodes = (int64_t)nx * ny * nz;
+  ensure_ctx();
+  check(kml_grid_create(ctx, &g.desc, &g.id));
+  g.mask.assign(g.nnodes, 1);
+}
+
+// Domain::set_dimension, src/domain.cpp:496-551 (+ set_local_box on a 1x1x1 proc grid, src/domain.cpp:366-394)
+Var Sim::cmd_dimension(std::vector<std::string> &a) {
+  if (!method_set) fatal("Error: a method should be defined before calling dimension()!\n");
+  if (a.empty()) fatal("Error: dimension did not receive enough arguments\n");
+  size_t m = 0;
+  int dim = (int)(double)input.parsev(a[m]);
+  if (dim != 1 && dim != 2 && dim != 3) fatal("Error: dimension argument: " + a[m] + "\n.");
+  dimension = dim;
+  // Nargs_dimension = {1: 4, 2: 6, 3: 8} (src/domain.h:93-94); TL takes the cell size too but ignores it
+  if (a.size() < (size_t)(2 * dim + 2)) fatal("Error: not enough arguments.\n");
+  if (a.size() > (size_t)(2 * dim + 2)) fatal("Error: too many arguments.\n");
+  boxlo[0] = input.parsev(a[++m]); boxhi[0] = input.parsev(a[++m]);
+  if (dim > 1) { boxlo[1] = input.parsev(a[++m]); boxhi[1] = input.parsev(a[++m]); }
+  if (dim == 3) { boxlo[2] = input.parsev(a[++m]); boxhi[2] = input.parsev(a[++m]); }
+  double cs = 0;
+  if (!is_TL) { cs = input.parsev(a[++m]); if (cs < 0) fatal("Error: cellsize negative!\n"); }
+  for (int d = 0; d < 3; d++) {
+    if (d < dim) { double h = (boxhi[d] - boxlo[d]) / 1; sublo[d] = 0 * h + boxlo[d]; subhi[d] = sublo[d] + h; }
+    else sublo[d] = subhi[d] = 0;
+  }
+  if (!is_TL) { grid.reset(new GridH()); grid->cellsize = cs; init_grid(*grid, boxlo, boxhi); }
+  created = true;
+  return Var(0);
+}
+
+namespace {
+struct Block : Region {
+  int inside(double x, double y, double z) const override { return x >= lim[0] && x <= lim[1] && y >= lim[2] && y <= lim[3] && z >= lim[4] && z <= lim[5]; }
+};
+struct Cylinder : Region {
+  char axis = 'z'; double c1 = 0, c2 = 0, R = 0, RSq = 0, lo = 0, hi = 0;
+  int inside(double x, double y, double z) const override { // src/region_cylinder.cpp:140-161
+    double dSq;
+    if (axis == 'x') { dSq = (y - c1) * (y - c1) + (z - c2) * (z - c2); return x >= lo && x <= hi && dSq <= RSq; }
+    if (axis == 'y') { dSq = (x - c1) * (x - c1) + (z - c2) * (z - c2); return y >= lo && y <= hi && dSq <= RSq; }
+    dSq = (x - c1) * (x - c1) + (y - c2) * (y - c2); return z >= lo && z <= hi && dSq <= RSq;
+  }
+};
+struct Sphere : Region {
+  double c1 = 0, c2 = 0, c3 = 0, RSq = 0;
+  int inside(double x, double y, double z) const override { return (x - c1) * (x - c1) + (y - c2) * (y - c2) + (z - c3) * (z - c3) <= RSq; }
+};
+} // namespace
+
+// Domain::add_region + Block_/Cylinder/Sphere constructors (src/domain.cpp:76-98, src/region_block.cpp:28-139,
+// src/region_cylinder.cpp:30-134, src/region_sphere.cpp:30-118)
+Var Sim::cmd_region(std::vector<std::string> &a) {
+  if (a.size() < 3) fatal("Error: not enough arguments.\n");
+  if (find_region(a[0]) >= 0) fatal("Error: reuse of region ID.\n");
+  const int dim = dimension;
+  auto is_inf = [](const std::string &s) { return s == "INF" || s == "-INF" || s == "+INF" || s == "EDGE"; };
+  auto opts = [&](Region &r, size_t from) { for (size_t i = from; i < a.size(); i++) if (a[i] == "exterior") r.interior = 0; }; // src/region.cpp:30-62
+  std::unique_ptr<Region> reg;
+  if (a[1] == "block") {
+    size_t need = dim == 3 ? 8 : (dim == 2 ? 6 : 4);
+    if (a.size() < need) fatal("Error: region command not enough arguments.\n");
+    auto b = new Block(); reg.reset(b); opts(*b, need);
+    for (int d = 0; d < dim; d++) {
+      const std::string &slo = a[2 + 2 * d], &shi = a[3 + 2 * d];
+      if (is_inf(slo)) { if (regions.empty()) fatal("Cannot use region INF or EDGE when box does not exist.\n"); b->lim[2 * d] = -BIG; }
+      else { b->lim[2 * d] = input.parsev(slo); if (boxlo[d] > b->lim[2 * d]) boxlo[d] = b->lim[2 * d]; }
+      if (is_inf(shi)) { if (regions.empty()) fatal("Cannot use region INF or EDGE when box does not exist.\n"); b->lim[2 * d + 1] = BIG; }
+      else { b->lim[2 * d + 1] = input.parsev(shi); if (boxhi[d] < b->lim[2 * d + 1]) boxhi[d] = b->lim[2 * d + 1]; }
+    }
+    if (b->lim[0] > b->lim[1] || b->lim[2] > b->lim[3] || b->lim[4] > b->lim[5]) fatal("Illegal region block command.\n");
+  } else if (a[1] == "cylinder") {
+    auto c = new Cylinder(); reg.reset(c);
+    if (dim == 3) {
+      if (a.size() < 8) fatal("Error: not enough arguments.\n");
+      opts(*c, 8);
+      if (a[2] == "x" || a[2] == "y" || a[2] == "z") c->axis = a[2][0]; else fatal("Error: region cylinder axis not understood, expect x, y, or z, received " + a[2] + ".\n");
+      c->c1 = input.parsev(a[3]); c->c2 = input.parsev(a[4]); c->R = input.parsev(a[5]);
+      if (a[6] == "INF" || a[6] == "EDGE") { if (regions.empty()) fatal("Cannot use region INF or EDGE when box does not exist.\n"); c->lo = -BIG; } else c->lo = input.parsev(a[6]);
+      if (a[7] == "INF" || a[7] == "EDGE") { if (regions.empty()) fatal("Cannot use region INF or EDGE when box does not exist.\n"); c->hi = BIG; } else c->hi = input.parsev(a[7]);
+    } else {
+      if (a.size() < 5) fatal("Error: not enough arguments.\n");
+      opts(*c, 5);
+      c->axis = 'z'; c->c1 = input.parsev(a[2]); c->c2 = input.parsev(a[3]); c->R = input.parsev(a[4]); c->lo = c->hi = 0;
+    }
+    c->RSq = c->R * c->R;
+    if (c->lo > c->hi) fatal("Illegal region cylinder command: low is higher than high.\n");
+    double *l = c->lim;
+    if (c->axis == 'x') { l[0] = c->lo; l[1] = c->hi; l[2] = c->c1 - c->R; l[3] = c->c1 + c->R; l[4] = c->c2 - c->R; l[5] = c->c2 + c->R; }
+    else if (c->axis == 'y') { l[0] = c->c1 - c->R; l[1] = c->c1 + c->R; l[2] = c->lo; l[3] = c->hi; l[4] = c->c2 - c->R; l[5] = c->c2 + c->R; }
+    else { l[0] = c->c1 - c->R; l[1] = c->c1 + c->R; l[2] = c->c2 - c->R; l[3] = c->c2 + c->R; l[4] = c->lo; l[5] = c->hi; }
+  } else if (a[1] == "sphere") {
+    auto s = new Sphere(); reg.reset(s);
+    if (a.size() != (size_t)(dim + 3)) fatal("Error: region sphere: wrong number of arguments.\n");
+    size_t i = 2;
+    s->c1 = input.parsev(a[i++]); if (dim >= 2) s->c2 = input.parsev(a[i++]); if (dim == 3) s->c3 = input.parsev(a[i++]);
+    double R = input.parsev(a[i++]);
+    if (R < 0) fatal("Error: R cannot be negative.\n");
+    s->RSq = R * R;
+    double *l = s->lim; l[0] = s->c1 - R; l[1] = s->c1 + R; l[2] = s->c2 - R; l[3] = s->c2 + R; l[4] = s->c3 - R; l[5] = s->c3 + R;
+    if (method_type == "tlmpm") {
+      for (int d = 0; d < (dim == 3 ? 3 : 2); d++) { if (boxlo[d] > l[2 * d]) boxlo[d] = l[2 * d]; if (boxhi[d] < l[2 * d + 1]) boxhi[d] = l[2 * d + 1]; }
+    } else {
+      for (int d = 0; d < (dim == 3 ? 3 : 2); d++) if (boxlo[d] > l[2 * d]) l[2 * d] = boxlo[d];
+    }
+  } else fatal("Unknown region style " + a[1] + "\n");
+  reg->id = a[0]; reg->style = a[1];
+  regions.push_back(std::move(reg));
+  if (ctx) check(kml_set_domain_box(ctx, boxlo, boxhi));
+  return Var(0);
+}
+
+// Material::add_EOS + EOS ctors (src/material.cpp:94-123, src/eos_linear.cpp, src/eos_shock.cpp:30-82, src/eos_fluid.cpp)
+Var Sim::cmd_eos(std::vector<std::string> &a) {
+  if (a.size() < 3) fatal("Error: not enough arguments.\n");
+  for (auto &e : eoss) if (e.id == a[0]) fatal("Error: reuse of EOS ID.\n");
+  EOSH e{}; e.id = a[0];
+  auto P = [&](size_t i) { return (double)input.parsev(a[i]); };
+  if (a[1] == "linear") { if (a.size() < 4) fatal("Error: not enough arguments.\n"); e.type = KML_EOS_LINEAR; e.rho0 = P(2); e.K = P(3); }
+  else if (a[1] == "shock") {
+    if (a.size() < 11) fatal("Error: not enough arguments.\n");
+    e.type = KML_EOS_SHOCK; e.rho0 = P(2); e.K = P(3); e.c0 = P(4); e.S = P(5); e.Gamma = P(6); e.cv = P(7); e.Tr = P(8); e.Q1 = P(9); e.Q2 = P(10);
+  } else if (a[1] == "fluid") { if (a.size() < 5) fatal("Error: not enough arguments.\n"); e.type = KML_EOS_FLUID; e.rho0 = P(2); e.K = P(3); e.Gamma = P(4); }
+  else fatal("Unknown EOS style " + a[1] + "\n");
+  eoss.push_back(e); return Var(0);
+}
+Var Sim::cmd_strength(std::vector<std::string> &a) {
+  if (a.size() < 3) fatal("Error: too few arguments for the strength command.\n");
+  for (auto &s : strengths) if (s.id == a[0]) fatal("Error: reuse of strength ID.\n");
+  StrengthH s{}; s.id = a[0];
+  auto P = [&](size_t i) { return (double)input.parsev(a[i]); };
+  if (a[1] == "linear") { s.type = KML_STRENGTH_LINEAR; s.G = P(2); }
+  else if (a[1] == "fluid") { s.type = KML_STRENGTH_FLUID; s.G = P(2); }
+  else if (a[1] == "plastic") { if (a.size() < 4) fatal("Error: too few arguments for the strength command.\n"); s.type = KML_STRENGTH_PLASTIC; s.G = P(2); s.A = P(3); }
+  else if (a[1] == "johnson_cook") {
+    if (a.size() < 11) fatal("Error: too few arguments for the strength command.\n");
+    s.type = KML_STRENGTH_JOHNSON_COOK; s.G = P(2); s.A = P(3); s.B = P(4); s.n = P(5); s.epsdot0 = P(6); s.C = P(7); s.m = P(8); s.Tr = P(9); s.Tm = P(10);
+    if (s.Tr == s.Tm) fatal("Error: reference temperature Tr equals melting temperature Tm.\n");
+  } else if (a[1] == "swift") {
+    if (a.size() < 7) fatal("Error: too few arguments for the strength command.\n");
+    s.type = KML_STRENGTH_SWIFT; s.G = P(2); s.A = P(3); s.B = P(4); s.C = P(5); s.n = P(6);
+  } else fatal("Unknown strength style " + a[1] + "\n");
+  strengths.push_back(s); return Var(0);
+}
+Var Sim::cmd_damage(std::vector<std::string> &a) {
+  if (a.size() < 10 || a[1] != "damage_johnson_cook") fatal("Error: damage command: unknown style or too few arguments.\n");
+  DamageH d{}; d.id = a[0]; d.type = KML_DAMAGE_JOHNSON_COOK;
+  auto P = [&](size_t i) { return (double)input.parsev(a[i]); };
+  d.d1 = P(2); d.d2 = P(3); d.d3 = P(4); d.d4 = P(5); d.d5 = P(6); d.epsdot0 = P(7); d.Tr = P(8); d.Tm = P(9);
+  if (d.Tr == d.Tm) fatal("Error: reference temperature Tr equals melting temperature Tm.\n");
+  damages.push_back(d); return Var(0);
+}
+Var Sim::cmd_temperature(std::vector<std::string> &a) {
+  if (a.size() != 8 || a[1] != "plastic_work") fatal("Error: temperature command: unknown style or wrong number of arguments.\n");
+  TemperatureH t{}; t.id = a[0]; t.type = KML_TEMPERATURE_PLASTIC_WORK;
+  auto P = [&](size_t i) { return (double)input.parsev(a[i]); };
+  t.chi = P(2); t.cp = P(3); t.kappa = P(4); t.alpha = P(5); t.T0 = P(6); t.Tm = P(7);
+  temperatures.push_back(t); return Var(0);
+}
+
+// Material::add_material + Mat constructors, src/material.cpp:250-372, :720-778
+Var Sim::cmd_material(std::vector<std::string> &a) {
+  if (a.size() < 2) fatal("Error: material command not enough arguments\n");
+  if (find_material(a[0]) >= 0) fatal("Error: reuse of material ID.\n");
+  MaterialH M; M.id = a[0]; kml_material &m = M.km; memset(&m, 0, sizeof m);
+  auto P = [&](size_t i) { return (double)input.parsev(a[i]); };
+  if (a[1] == "linear" || a[1] == "neo-hookean") {
+    if (a.size() < 5) fatal("Error: not enough arguments.\n");
+    m.type = a[1] == "linear" ? KML_MAT_LINEAR : KML_MAT_NEO_HOOKEAN;
+    double cp = 0, kappa = 0;
+    if (a.size() >= 7) { cp = P(5); kappa = P(6); } // the reference reads args[6] already when 6 are given (src/material.cpp:284-287): UB there, an error here
+    else if (a.size() == 6) fatal("material(linear): cp given without kappa (the reference reads past the argument list here).\n");
+    m.rho0 = P(2); m.E = P(3); m.nu = P(4);
+    m.G = m.E / (2 * (1 + m.nu));
+    m.lambda = m.E * m.nu / ((1 + m.nu) * (1 - 2 * m.nu));
+    m.K = m.E / (3 * (1 - 2 * m.nu));
+    m.signal_velocity = sqrt(m.K / m.rho0);
+    m.cp = cp; m.invcp = cp != 0 ? 1.0 / cp : 0; m.kappa = kappa;
+  } else if (a[1] == "rigid") {
+    if (a.size() < 3) fatal("Error: not enough arguments.\n");
+    m.type = KML_MAT_RIGID; m.rigid = 1; m.rho0 = P(2);
+  } else if (a[1] == "eos-strength") {
+    if (a.size() < 4) fatal("Error: not enough arguments.\n");
+    const EOSH *e = nullptr; for (auto &x : eoss) if (x.id == a[2]) e = &x;
+    if (!e) fatal("Error: could not find EOS named: " + a[2] + ".\n");
+    const StrengthH *s = nullptr; for (auto &x : strengths) if (x.id == a[3]) s = &x;
+    if (!s) fatal("Error: could not find strength named: " + a[3] + ".\n");
+    const DamageH *d = nullptr; const TemperatureH *t = nullptr;
+    if (a.size() > 4) {
+      for (auto &x : damages) if (x.id == a[4]) d = &x;
+      if (!d) {
+        for (auto &x : temperatures) if (x.id == a[4]) t = &x;
+        if (!t) fatal("Error: could not find damage named: " + a[4] + ".\n");
+        if (a.size() > 5) fatal("Error: the last argument of the material command should be the temperature\n");
+      } else if (a.size() == 6) {
+        for (auto &x : temperatures) if (x.id == a[5]) t = &x;
+        if (!t) fatal("Error: could not find temperature named: " + a[5] + ".\n");
+      }
+    }
+    m.type = KML_MAT_EOS_STRENGTH;
+    m.eos_type = e->type; m.eos_K = e->K; m.eos_c0 = e->c0; m.eos_S = e->S; m.eos_Gamma = e->Gamma; m.eos_cv = e->cv; m.eos_Tr = e->Tr; m.eos_Q1 = e->Q1; m.eos_Q2 = e->Q2;
+    m.strength_type = s->type; m.str_G = s->G; m.str_A = s->A; m.str_B = s->B; m.str_n = s->n; m.str_epsdot0 = s->epsdot0; m.str_C = s->C; m.str_m = s->m; m.str_Tr = s->Tr; m.str_Tm = s->Tm;
+    if (d) { m.damage_type = d->type; m.dmg_d1 = d->d1; m.dmg_d2 = d->d2; m.dmg_d3 = d->d3; m.dmg_d4 = d->d4; m.dmg_d5 = d->d5; m.dmg_epsdot0 = d->epsdot0; m.dmg_Tr = d->Tr; m.dmg_Tm = d->Tm; }
+    if (t) { m.temperature_type = t->type; m.tmp_chi = t->chi; m.tmp_cp = t->cp; m.tmp_kappa = t->kappa; m.tmp_alpha = t->alpha; m.tmp_T0 = t->T0; m.tmp_Tm = t->Tm; }
+    // Mat::Mat(eos, strength, damage, temp), src/material.cpp:720-745
+    m.rho0 = e->rho0; m.K = e->K; m.G = s->G;
+    m.E = 9 * m.K * m.G / (3 * m.K + m.G);
+    m.nu = (3 * m.K - 2 * m.G) / (2 * (3 * m.K + m.G));
+    m.lambda = m.K - 2 * m.G / 3;
+    m.signal_velocity = sqrt((m.lambda + 2 * m.G) / m.rho0);
+    if (t) { m.cp = t->cp; m.invcp = 1.0 / m.cp; m.kappa = t->kappa; }
+  } else fatal("Error, keyword " + a[1] + " unknown!\n");
+  materials.push_back(M);
+  if (!quiet) std::cout << "Creating new mat with ID: " << a[0] << " (G=" << m.G << ", K=" << m.K << ", signal velocity=" << m.signal_velocity << ")\n";
+  return Var(0);
+}
+
+// Domain::add_solid -> Solid::Solid / options / populate / init (src/solid.cpp:59-238, :1810-2336)
+Var Sim::cmd_solid(std::vector<std::string> &a) {
+  if (!method_set) fatal("Error: a method should be defined before creating a solid!\n");
+  if (a.size() < 2) fatal("Error: solid command not enough arguments.\n");
+  if (find_solid(a[0]) >= 0) fatal("Error: reuse of solid ID.\n");
+  if (a[1] != "region") fatal("solid(" + a[1] + "): only solid(..., region, ...) is supported by this build.\n");
+  if (a.size() < 7) fatal("Error: not enough arguments.\n");
+  std::unique_ptr<SolidH> s(new SolidH()); s->id = a[0];
+  if (is_TL) { s->own_grid.reset(new GridH()); s->grid = s->own_grid.get(); } else s->grid = grid.get();
+  // Solid::options, src/solid.cpp:197-238
+  s->mat = find_material(a[4]);
+  if (s->mat < 0) fatal("Error: could not find material named " + a[4] + "\n");
+  s->grid->cellsize = input.parsev(a[5]); // Grid::setup, src/grid.cpp:415-420
+  if (!is_TL && s->grid->cellsize != s->grid->desc.cellsize) fatal("solid(): cell size differs from the one given to dimension(); the reference silently changes the weight scaling here.\n");
+  s->T0 = input.parsev(a[6]);
+  populate(*s, a);
+  solids.push_back(std::move(s));
+  return Var(0);
+}
+
+void Sim::populate(SolidH &s, std::vector<std::string> &a) {
+  int iregion = find_region(a[2]);
+  if (iregion == -1) fatal("Error: region ID " + a[2] + " not does not exist.\n");
+  if (!created) fatal("The domain must be created before any solids can (create_domain(...)).");
+  const Region &reg = *regions[iregion];
+  for (int d = 0; d < 3; d++) { s.solidlo[d] = reg.lim[2 * d]; s.solidhi[d] = reg.lim[2 * d + 1]; }
+  const double delta = s.grid->cellsize;
+  const double *boundlo, *boundhi;
+  if (is_TL) { init_grid(*s.grid, s.solidlo, s.solidhi); boundlo = s.solidlo; boundhi = s.solidhi; }
+  else { boundlo = boxlo; boundhi = boxhi; }
+  int noffsetlo[3], noffsethi[3];
+  for (int d = 0; d < 3; d++) {
+    double Llo = dmax(0.0, sublo[d] - boundlo[d]);
+    double Lhi = dmax(0.0, dmin(subhi[d], boundhi[d]) - boundlo[d]);
+    noffsetlo[d] = (int)floor(Llo / delta);
+    noffsethi[d] = (int)ceil(Lhi / delta);
+  }
+  int nsub[3];
+  nsub[0] = std::max(0, noffsethi[0] - noffsetlo[0]);
+  nsub[1] = dimension >= 2 ? std::max(0, noffsethi[1] - noffsetlo[1]) : 1;
+  nsub[2] = dimension >= 3 ? std::max(0, noffsethi[2] - noffsetlo[2]) : 1;
+  for (int d = 0; d < 3; d++)
+    while (boundlo[d] + delta * (noffsetlo[d] + nsub[d] - 0.5) < dmin(subhi[d], boundhi[d])) nsub[d]++;
+
+  double vol_ = dimension == 1 ? delta : (dimension == 2 ? delta * delta : delta * delta * delta);
+  const kml_material &mat = materials[s.mat].km;
+  double mass_ = mat.rho0 * vol_;
+  s.np_per_cell = (int)(double)input.parsev(a[3]);
+  const int ppc = s.np_per_cell;
+  double xi; int nip = 1; std::vector<double> ip;
+  const int nc = is_CPDI ? (1 << dimension) : 0;
+  if (ppc == 1) { nip = 1; ip = {0, 0, 0}; }
+  else if (ppc == 2) {
+    nip = dimension == 1 ? 2 : (dimension == 2 ? 4 : 8); xi = 0.25;
+    ip = {-xi, -xi, -xi, -xi, xi, -xi, xi, -xi, -xi, xi, xi, -xi, -xi, -xi, xi, -xi, xi, xi, xi, -xi, xi, xi, xi, xi};
+  } else if (ppc == 3) {
+    xi = nc == 0 ? 0.7746 / 2 : 1.0 / 3.0;
+    nip = dimension == 1 ? 3 : (dimension == 2 ? 9 : 27);
+    const double t[3] = {-xi, 0, xi};
+    for (int c = 0; c < 3; c++) for (int aa = 0; aa < 3; aa++) for (int b = 0; b < 3; b++) { ip.push_back(t[aa]); ip.push_back(t[b]); ip.push_back(t[c]); } // order of src/solid.cpp:2076-2102
+  } else {
+    nip = dimension == 1 ? ppc : (dimension == 2 ? ppc * ppc : ppc * ppc * ppc);
+    double d = 1.0 / ppc;
+    for (int k = 0; k < ppc; k++) for (int i = 0; i < ppc; i++) for (int j = 0; j < ppc; j++) { ip.push_back((i + 0.5) * d - 0.5); ip.push_back((j + 0.5) * d - 0.5); ip.push_back((k + 0.5) * d - 0.5); }
+  }
+  mass_ /= (double)nip; vol_ /= (double)nip;
+
+  s.x0.clear();
+  const int dim = dimension;
+  for (int i = 0; i < nsub[0]; i++) for (int j = 0; j < nsub[1]; j++) for (int k = 0; k < nsub[2]; k++) for (int q = 0; q < nip; q++) {
+    std::array<double, 3> x;
+    x[0] = boundlo[0] + delta * (noffsetlo[0] + i + 0.5 + ip[3 * q + 0]);
+    x[1] = boundlo[1] + delta * (noffsetlo[1] + j + 0.5 + ip[3 * q + 1]);
+    x[2] = dim == 3 ? boundlo[2] + delta * (noffsetlo[2] + k + 0.5 + ip[3 * q + 2]) : 0;
+    bool in_sub = !(x[0] < sublo[0] || x[0] > subhi[0] || x[1] < sublo[1] || x[1] > subhi[1] || x[2] < sublo[2] || x[2] > subhi[2]); // Domain::inside_subdomain
+    if (in_sub && reg.inside(x[0], x[1], x[2]) == 1) s.x0.push_back(x);
+  }
+  s.np = (int64_t)s.x0.size();
+  if (s.np == 0) fatal("Error: solid does not have any particles.\n");
+  s.mask.assign(s.np, 1);
+  s.ptag.resize(s.np);
+  std::vector<double> mass(s.np), vol(s.np), T(s.np, s.T0);
+  for (int64_t i = 0; i < s.np; i++) {
+    if (axisymmetric) { mass[i] = mass_ * s.x0[i][0]; vol[i] = mass[i] / mat.rho0; }
+    else { mass[i] = mass_; vol[i] = vol_; }
+    s.ptag[i] = i + 1 + np_total; // src/solid.cpp:2322
+  }
+  np_total += s.np; // domain->np_total += np, src/solid.cpp:2334
+
+  // upload; everything not set here starts at the values of src/solid.cpp:2283-2321 (F = R = I, J = 1, mask = 1, rest 0)
+  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = s.np; d.grid = s.grid->id; d.mat = mat;
+  check(kml_solid_create(ctx, &d, &s.dev));
+  check(kml_solid_upload(ctx, s.dev, KML_P_PTAG, s.ptag.data()));
+  check(kml_solid_upload(ctx, s.dev, KML_P_X, s.x0.data()));
+  check(kml_solid_upload(ctx, s.dev, KML_P_X0, s.x0.data()));
+  check(kml_solid_upload(ctx, s.dev, KML_P_MASS, mass.data()));
+  check(kml_solid_upload(ctx, s.dev, KML_P_VOL0, vol.data()));
+  check(kml_solid_upload(ctx, s.dev, KML_P_VOL, vol.data()));
+  if (temp) check(kml_solid_upload(ctx, s.dev, KML_P_T, T.data()));
+  // Solid::init totals, src/solid.cpp:170-195
+  s.vtot = s.mtot = 0; for (int64_t i = 0; i < s.np; i++) { s.vtot += vol[i]; s.mtot += mass[i]; }
+  if (!quiet) std::cout << "Solid " << s.id << ": np=" << s.np << " total volume = " << s.vtot << " total mass = " << s.mtot << " grid " << s.grid->desc.n[0] << "x" << s.grid->desc.n[1] << "x" << s.grid->desc.n[2] << std::endl;
+}
+
+// Group::assign, src/group.cpp:65-238
+Var Sim::cmd_group(std::vector<std::string> &a) {
+  if (a.size() < 5) fatal("Error: too few arguments for group: requires at least 4 arguments.\n");
+  int ig = find_group(a[0]);
+  if (ig == -1) {
+    if (ngroup == MAX_GROUP) fatal("Too many groups.\n");
+    for (int i = 0; i < MAX_GROUP; i++) if (gnames[i].empty()) { ig = i; break; }
+    gnames[ig] = a[0]; ngroup++;
+  }
+  const int bit = gbitmask[ig];
+  if (a[1] == "particles") gpon[ig] = "particles"; else if (a[1] == "nodes") gpon[ig] = "nodes";
+  else fatal("Error: do not understand keyword " + a[1] + ", \"particles\" or \"nodes\" expected.\n");
+  if (a[2] != "region") fatal("Error: unknown keyword in group command: " + a[2] + ".\n");
+  gregion[ig] = find_region(a[3]);
+  if (gregion[ig] == -1) fatal("Error: could not find region " + a[3] + ".\n");
+  const Region &reg = *regions[gregion[ig]];
+  std::vector<int> targets;
+  if (a[4] == "all") { gsolid[ig] = -1; for (size_t i = 0; i < solids.size(); i++) targets.push_back((int)i); }
+  else if (a[4] == "solid") {
+    for (size_t i = 5; i < a.size(); i++) { gsolid[ig] = find_solid(a[i]); if (gsolid[ig] == -1) fatal("Error: cannot find solid with ID " + a[i] + ".\n"); targets.push_back(gsolid[ig]); }
+  } else fatal("Error: unknown keyword in group command: " + a[3] + ".\n");
+  for (int is : targets) {
+    SolidH &s = *solids[is]; int n = 0;
+    if (gpon[ig] == "particles") {
+      for (int64_t ip = 0; ip < s.np; ip++) if (reg.match(s.x0[ip][0], s.x0[ip][1], s.x0[ip][2])) { s.mask[ip] |= bit; n++; }
+      check(kml_solid_upload(ctx, s.dev, KML_P_MASK, s.mask.data()));
+    } else {
+      GridH &g = *s.grid; const kml_grid_desc &d = g.desc; int64_t l = 0;
+      for (int i = 0; i < d.n[0]; i++) for (int j = 0; j < d.n[1]; j++) for (int k = 0; k < d.n[2]; k++, l++) {
+        double x = d.lo[0] + i * d.h, y = dimension >= 2 ? d.lo[1] + j * d.h : 0, z = dimension == 3 ? d.lo[2] + k * d.h : 0; // node positions, src/grid.cpp:222-227
+        if (reg.match(x, y, z)) { g.mask[l] |= bit; n++; }
+      }
+      check(kml_grid_upload(ctx, g.id, KML_N_MASK, g.mask.data()));
+    }
+    if (!quiet) std::cout << n << " " << gpon[ig] << " from solid " << s.id << " found" << std::endl;
+  }
+  return Var(0);
+}
+
+} // namespace kmlh
