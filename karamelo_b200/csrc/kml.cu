@@ -1,0 +1,652 @@
+// kml.cu - libkml.so: device state + the C ABI of include/kml.h on top of the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see karamelo_b200/Makefile).
+#include "kml_kernels.cuh"
+#include "kml_p2g_cell.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace kml;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define CUV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); } } while (0)
+
+struct Grid {
+  kml_grid_desc d; GridDev g; double *buf = nullptr; int *ibuf = nullptr;
+  bool v_is_momentum = false, T_is_weighted = false;
+  // cell lists for the cell-centric P2G (UL)
+  CellLists cl;
+};
+struct Solid {
+  kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
+  bool moved = false;     // xn holds the positions after grid_to_points (UL)
+  bool mbp_nonzero = false;
+  double *red = nullptr;  // device: [0] max wave speed, [1] min_h_ratio
+  double dtCFL = 1.0e22;
+};
+
+struct kml_ctx {
+  kml_config c; int dev = 0; cudaStream_t stream = nullptr;
+  std::vector<Grid *> grids; std::vector<Solid *> solids;
+  double dt = 1e-16;
+  unsigned *d_flags = nullptr; double *d_scratch = nullptr; // scratch: small reduction outputs
+  double *h_pinned = nullptr;                                // pinned readback buffer
+  bool tl_mass_done = false;
+  bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
+  bool use_cell_p2g = true;
+  // profiling
+  bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
+};
+
+namespace {
+struct StageTimer {
+  kml_ctx *c; int stage;
+  StageTimer(kml_ctx *c_, int st) : c(c_), stage(st) { if (c->profile) cudaEventRecord(c->ev0, c->stream); }
+  ~StageTimer() {
+    if (c->profile) { cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1); float t = 0; cudaEventElapsedTime(&t, c->ev0, c->ev1); c->ms[stage] += t; }
+  }
+};
+inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+StepParams step_params(kml_ctx *c) {
+  StepParams sp; sp.dt = c->dt; sp.alpha = c->c.PIC_FLIP;
+  for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
+  sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.flags = c->d_flags; return sp;
+}
+
+// kernel dispatch on (dimension, shape function, TL)
+#define KML_DISPATCH_SHAPE(DIMV, TLV, KERNEL, ...)                                                                         \
+  switch (c->c.shape_function) {                                                                                           \
+  case KML_SHAPE_LINEAR: KERNEL<DIMV, KML_SHAPE_LINEAR, TLV> __VA_ARGS__; break;                                           \
+  case KML_SHAPE_CUBIC_SPLINE: KERNEL<DIMV, KML_SHAPE_CUBIC_SPLINE, TLV> __VA_ARGS__; break;                               \
+  case KML_SHAPE_QUADRATIC_SPLINE: KERNEL<DIMV, KML_SHAPE_QUADRATIC_SPLINE, TLV> __VA_ARGS__; break;                       \
+  default: KERNEL<DIMV, KML_SHAPE_BERNSTEIN, TLV> __VA_ARGS__; break;                                                      \
+  }
+#define KML_DISPATCH(KERNEL, ...)                                                                                          \
+  do {                                                                                                                     \
+    if (c->c.is_TL) {                                                                                                      \
+      if (c->c.dimension == 1) { KML_DISPATCH_SHAPE(1, true, KERNEL, __VA_ARGS__) }                                        \
+      else if (c->c.dimension == 2) { KML_DISPATCH_SHAPE(2, true, KERNEL, __VA_ARGS__) }                                   \
+      else { KML_DISPATCH_SHAPE(3, true, KERNEL, __VA_ARGS__) }                                                            \
+    } else {                                                                                                               \
+      if (c->c.dimension == 1) { KML_DISPATCH_SHAPE(1, false, KERNEL, __VA_ARGS__) }                                       \
+      else if (c->c.dimension == 2) { KML_DISPATCH_SHAPE(2, false, KERNEL, __VA_ARGS__) }                                  \
+      else { KML_DISPATCH_SHAPE(3, false, KERNEL, __VA_ARGS__) }                                                           \
+    }                                                                                                                      \
+  } while (0)
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+} // namespace
+
+extern "C" {
+
+const char *kml_last_error(void) { return g_err.c_str(); }
+const char *kml_backend(void) { return "cuda-sm_100a"; }
+
+int kml_create(const kml_config *cfg, kml_ctx **out) {
+  if (cfg->is_CPDI) return fail("kml: CPDI (ulcpdi/tlcpdi) is not implemented in the CUDA engine yet");
+  if (cfg->ge) return fail("kml: gradient-enhanced mapping is not implemented in the CUDA engine yet");
+  if (cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP) return fail("kml: APIC / AFLIP / ASFLIP / MLS are not implemented in the CUDA engine yet");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("kml: no CUDA device available - the engine has no CPU fallback");
+  kml_ctx *c = new kml_ctx(); c->c = *cfg; c->dev = cfg->device;
+  CU(cudaSetDevice(c->dev));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
+  CU(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
+  CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
+  CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+  memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
+  const char *e = getenv("KML_P2G"); if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
+  *out = c; return 0;
+}
+
+int kml_destroy(kml_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
+  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
+  for (auto s : c->solids) { cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
+  cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+  delete c; return 0;
+}
+int kml_synchronize(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+int kml_set_domain_box(kml_ctx *c, const double lo[3], const double hi[3]) { for (int d = 0; d < 3; d++) { c->c.boxlo[d] = lo[d]; c->c.boxhi[d] = hi[d]; } return 0; }
+
+// ---- grids ------------------------------------------------------------------------------------
+static const int GRID_NDBL = 1 + 3 + 3 + 3 + 3 + 4 + 3; // mass v vu f mb T Tu Qext Qint x
+
+int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
+  CU(cudaSetDevice(c->dev));
+  Grid *G = new Grid(); G->d = *d; GridDev &g = G->g;
+  for (int k = 0; k < 3; k++) { g.lo[k] = d->lo[k]; g.n[k] = d->n[k]; }
+  g.h = d->h; g.cellsize = d->cellsize; g.inv_cellsize = 1.0 / d->cellsize;
+  g.nn = (long long)d->n[0] * d->n[1] * d->n[2];
+  const long long nn = g.nn, stride = (nn + 31) / 32 * 32;
+  CU(cudaMalloc(&G->buf, sizeof(double) * stride * GRID_NDBL)); CU(cudaMemsetAsync(G->buf, 0, sizeof(double) * stride * GRID_NDBL, c->stream));
+  CU(cudaMalloc(&G->ibuf, sizeof(int) * stride * 2));
+  double *p = G->buf; auto take = [&]() { double *r = p; p += stride; return r; };
+  g.mass = take(); for (int k = 0; k < 3; k++) g.v[k] = take(); for (int k = 0; k < 3; k++) g.vu[k] = take();
+  for (int k = 0; k < 3; k++) g.f[k] = take(); for (int k = 0; k < 3; k++) g.mb[k] = take();
+  g.T = take(); g.Tu = take(); g.Qext = take(); g.Qint = take(); for (int k = 0; k < 3; k++) g.x[k] = take();
+  g.mask = G->ibuf; g.rigid = G->ibuf + stride;
+  std::vector<int> ones(nn, 1);
+  CU(cudaMemcpyAsync(g.mask, ones.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(g.rigid, 0, sizeof(int) * nn, c->stream));
+  // node positions x = x0 (only TL moves them)
+  std::vector<double> xs(nn);
+  for (int k = 0; k < 3; k++) {
+    long long l = 0;
+    for (int i = 0; i < d->n[0]; i++) for (int j = 0; j < d->n[1]; j++) for (int kk = 0; kk < d->n[2]; kk++, l++) {
+      int idx = k == 0 ? i : (k == 1 ? j : kk);
+      xs[l] = (k < c->c.dimension) ? d->lo[k] + idx * d->h : 0.0;
+    }
+    CU(cudaMemcpyAsync(g.x[k], xs.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->grids.push_back(G); *gid = (int)c->grids.size() - 1; return 0;
+}
+int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.nn; return 0; }
+
+static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
+  if (!G->v_is_momentum && !G->T_is_weighted) return 0;
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted);
+  G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
+  return check_launch("k_grid_update(normalize)");
+}
+
+static int grid_field(kml_ctx *c, Grid *G, int field, double **comp, int *ncomp, int **icomp) {
+  GridDev &g = G->g; *icomp = nullptr; *ncomp = 1;
+  switch (field) {
+  case KML_N_X: for (int k = 0; k < 3; k++) comp[k] = g.x[k]; *ncomp = 3; break;
+  case KML_N_V: for (int k = 0; k < 3; k++) comp[k] = g.v[k]; *ncomp = 3; break;
+  case KML_N_V_UPDATE: for (int k = 0; k < 3; k++) comp[k] = g.vu[k]; *ncomp = 3; break;
+  case KML_N_MB: for (int k = 0; k < 3; k++) comp[k] = g.mb[k]; *ncomp = 3; break;
+  case KML_N_F: for (int k = 0; k < 3; k++) comp[k] = g.f[k]; *ncomp = 3; break;
+  case KML_N_MASS: comp[0] = g.mass; break;
+  case KML_N_T: comp[0] = g.T; break; case KML_N_T_UPDATE: comp[0] = g.Tu; break;
+  case KML_N_QEXT: comp[0] = g.Qext; break; case KML_N_QINT: comp[0] = g.Qint; break;
+  case KML_N_MASK: *icomp = g.mask; break; case KML_N_RIGID: *icomp = g.rigid; break;
+  default: return fail("grid field not supported");
+  }
+  return 0;
+}
+
+int kml_grid_upload(kml_ctx *c, int gid, int field, const void *src) {
+  CU(cudaSetDevice(c->dev));
+  Grid *G = c->grids[gid]; const long long nn = G->g.nn;
+  double *comp[3]; int nc; int *ic;
+  if (grid_field(c, G, field, comp, &nc, &ic)) return 1;
+  if (ic) { CU(cudaMemcpyAsync(ic, src, sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_N_V) G->v_is_momentum = false;
+  if (field == KML_N_T) G->T_is_weighted = false;
+  std::vector<double> tmp(nn); const double *s = (const double *)src;
+  for (int k = 0; k < nc; k++) {
+    for (long long i = 0; i < nn; i++) tmp[i] = s[i * nc + k];
+    CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+int kml_grid_download(kml_ctx *c, int gid, int field, void *dst) {
+  CU(cudaSetDevice(c->dev));
+  Grid *G = c->grids[gid]; const long long nn = G->g.nn; const kml_grid_desc &d = G->d;
+  if (field == KML_N_X0 || field == KML_N_NTYPE) {
+    long long l = 0;
+    for (int i = 0; i < d.n[0]; i++) for (int j = 0; j < d.n[1]; j++) for (int k = 0; k < d.n[2]; k++, l++) {
+      int idx[3] = {i, j, k};
+      for (int a = 0; a < 3; a++) {
+        if (field == KML_N_X0) ((double *)dst)[3 * l + a] = a < c->c.dimension ? d.lo[a] + idx[a] * d.h : 0.0;
+        else {
+          int nt = 0, n = d.n[a], ii = idx[a];
+          if (c->c.shape_function == KML_SHAPE_BERNSTEIN) nt = ii % 2;
+          else if (c->c.shape_function != KML_SHAPE_LINEAR) nt = std::min(2, ii) - std::min(n - 1 - ii, 2);
+          ((int *)dst)[3 * l + a] = nt;
+        }
+      }
+    }
+    return 0;
+  }
+  if (field == KML_N_V || field == KML_N_T) if (grid_normalize_if_needed(c, G)) return 1;
+  double *comp[3]; int nc; int *ic;
+  if (grid_field(c, G, field, comp, &nc, &ic)) return 1;
+  if (ic) { CU(cudaMemcpyAsync(dst, ic, sizeof(int) * nn, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  std::vector<double> tmp(nn); double *o = (double *)dst;
+  for (int k = 0; k < nc; k++) {
+    CU(cudaMemcpyAsync(tmp.data(), comp[k], sizeof(double) * nn, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    for (long long i = 0; i < nn; i++) o[i * nc + k] = tmp[i];
+  }
+  return 0;
+}
+
+// ---- solids -----------------------------------------------------------------------------------
+static const int SOLID_NDBL_UL = 3 * 6 + 6 + 6 + 9 + 11;
+static const int SOLID_NDBL_TL = SOLID_NDBL_UL + 18;
+
+int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
+  CU(cudaSetDevice(c->dev));
+  if (d->mat.rigid || d->mat.type == KML_MAT_RIGID) return fail("kml: rigid materials are not implemented in the CUDA engine yet");
+  Solid *S = new Solid(); S->d = *d; SolidDev &s = S->s;
+  s.np = d->np; S->cap = std::max<long long>(d->capacity, d->np);
+  const long long cap = (S->cap + 31) / 32 * 32; S->cap = cap;
+  const int nd = c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL;
+  CU(cudaMalloc(&S->buf, sizeof(double) * cap * nd)); CU(cudaMemsetAsync(S->buf, 0, sizeof(double) * cap * nd, c->stream));
+  CU(cudaMalloc(&S->lbuf, sizeof(long long) * cap)); CU(cudaMemsetAsync(S->lbuf, 0, sizeof(long long) * cap, c->stream));
+  CU(cudaMalloc(&S->ibuf, sizeof(int) * cap));
+  CU(cudaMalloc(&S->red, sizeof(double) * 2));
+  double *p = S->buf; auto take = [&]() { double *r = p; p += cap; return r; };
+  for (int k = 0; k < 3; k++) s.x[k] = take(); for (int k = 0; k < 3; k++) s.xn[k] = take(); for (int k = 0; k < 3; k++) s.x0[k] = take();
+  for (int k = 0; k < 3; k++) s.v[k] = take(); for (int k = 0; k < 3; k++) s.mbp[k] = take(); for (int k = 0; k < 3; k++) s.q[k] = take();
+  for (int k = 0; k < 6; k++) s.sig[k] = take(); for (int k = 0; k < 6; k++) s.eel[k] = take(); for (int k = 0; k < 9; k++) s.F[k] = take();
+  s.vol0 = take(); s.vol = take(); s.rho0 = take(); s.mass = take(); s.eps = take(); s.epsdot = take(); s.dmg = take(); s.dmgi = take();
+  s.ien = take(); s.T = take(); s.gamma = take();
+  if (c->c.is_TL) { for (int k = 0; k < 9; k++) s.pk1[k] = take(); for (int k = 0; k < 9; k++) s.R[k] = take(); }
+  else { for (int k = 0; k < 9; k++) { s.pk1[k] = nullptr; s.R[k] = nullptr; } }
+  s.ptag = S->lbuf; s.mask = S->ibuf;
+  // initial values of Solid::populate, src/solid.cpp:2283-2321: F = R = I, rho0 = mat.rho0, mask = 1
+  std::vector<double> ones(d->np, 1.0), rho(d->np, d->mat.rho0); std::vector<int> m1(d->np, 1);
+  for (int k : {0, 4, 8}) {
+    CU(cudaMemcpyAsync(s.F[k], ones.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
+    if (c->c.is_TL) CU(cudaMemcpyAsync(s.R[k], ones.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(s.rho0, rho.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(s.mask, m1.data(), sizeof(int) * d->np, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->solids.push_back(S); *sid = (int)c->solids.size() - 1; return 0;
+}
+int kml_solid_np(kml_ctx *c, int sid, int64_t *np) { *np = c->solids[sid]->s.np; return 0; }
+
+// component pointers of a particle field; sym = stored as 6 symmetric components
+static int solid_field(kml_ctx *c, Solid *S, int field, double **comp, int *ncomp, bool *sym) {
+  SolidDev &s = S->s; *sym = false; *ncomp = 1;
+  auto v3 = [&](double *const *a) { for (int k = 0; k < 3; k++) comp[k] = a[k]; *ncomp = 3; };
+  auto m9 = [&](double *const *a) { for (int k = 0; k < 9; k++) comp[k] = a[k]; *ncomp = 9; };
+  switch (field) {
+  case KML_P_X: v3((!c->c.is_TL && S->moved) ? s.xn : s.x); break;
+  case KML_P_X0: v3(s.x0); break; case KML_P_V: v3(s.v); break; case KML_P_MBP: v3(s.mbp); break; case KML_P_Q: v3(s.q); break;
+  case KML_P_SIGMA: for (int k = 0; k < 6; k++) comp[k] = s.sig[k]; *ncomp = 6; *sym = true; break;
+  case KML_P_STRAIN_EL: for (int k = 0; k < 6; k++) comp[k] = s.eel[k]; *ncomp = 6; *sym = true; break;
+  case KML_P_FDEF: m9(s.F); break;
+  case KML_P_VOL0PK1: if (!c->c.is_TL) return fail("vol0PK1 exists only for total-Lagrangian methods"); m9(s.pk1); break;
+  case KML_P_R: if (!c->c.is_TL) return fail("R exists only for total-Lagrangian methods"); m9(s.R); break;
+  case KML_P_VOL0: comp[0] = s.vol0; break; case KML_P_VOL: comp[0] = s.vol; break; case KML_P_RHO0: comp[0] = s.rho0; break;
+  case KML_P_MASS: comp[0] = s.mass; break; case KML_P_EFF_PLASTIC_STRAIN: comp[0] = s.eps; break;
+  case KML_P_EFF_PLASTIC_STRAIN_RATE: comp[0] = s.epsdot; break; case KML_P_DAMAGE: comp[0] = s.dmg; break;
+  case KML_P_DAMAGE_INIT: comp[0] = s.dmgi; break; case KML_P_IENERGY: comp[0] = s.ien; break; case KML_P_T: comp[0] = s.T; break;
+  case KML_P_GAMMA: comp[0] = s.gamma; break;
+  default: return fail("particle field " + std::to_string(field) + " is not materialised by the CUDA engine (derived in-kernel)");
+  }
+  return 0;
+}
+static const int SYM_OF[9] = {0, 3, 4, 3, 1, 5, 4, 5, 2}; // row-major (a,b) -> (xx,yy,zz,xy,xz,yz)
+
+int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid]; const long long np = S->s.np;
+  if (field == KML_P_PTAG) { CU(cudaMemcpyAsync(S->s.ptag, src, sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_P_MASK) { CU(cudaMemcpyAsync(S->s.mask, src, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_P_X && !c->c.is_TL) S->moved = false;
+  if (field == KML_P_MBP) S->mbp_nonzero = true;
+  double *comp[9]; int nc; bool sym;
+  if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
+  std::vector<double> tmp(np); const double *s = (const double *)src;
+  if (sym) {
+    static const int RM_OF_SYM[6] = {0, 4, 8, 1, 2, 5};
+    for (int k = 0; k < 6; k++) {
+      for (long long i = 0; i < np; i++) tmp[i] = s[i * 9 + RM_OF_SYM[k]];
+      CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+  }
+  for (int k = 0; k < nc; k++) {
+    for (long long i = 0; i < np; i++) tmp[i] = s[i * nc + k];
+    CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid]; const long long np = S->s.np;
+  if (field == KML_P_PTAG) { CU(cudaMemcpyAsync(dst, S->s.ptag, sizeof(long long) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_P_MASK) { CU(cudaMemcpyAsync(dst, S->s.mask, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_P_J || field == KML_P_RHO) { // derived: J = det F, rho = rho0 / J (src/solid.cpp:1201-1217)
+    std::vector<double> F(9 * np), r0(np);
+    if (kml_solid_download(c, sid, KML_P_FDEF, F.data()) || kml_solid_download(c, sid, KML_P_RHO0, r0.data())) return 1;
+    for (long long i = 0; i < np; i++) {
+      const double *m = &F[9 * i];
+      double J = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+      ((double *)dst)[i] = field == KML_P_J ? J : r0[i] / J;
+    }
+    return 0;
+  }
+  double *comp[9]; int nc; bool sym;
+  if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
+  std::vector<double> tmp(np); double *o = (double *)dst;
+  if (sym) {
+    std::vector<double> six(6 * np);
+    for (int k = 0; k < 6; k++) { CU(cudaMemcpyAsync(&six[k * np], comp[k], sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream)); }
+    CU(cudaStreamSynchronize(c->stream));
+    for (long long i = 0; i < np; i++) for (int e = 0; e < 9; e++) o[i * 9 + e] = six[SYM_OF[e] * np + i];
+    return 0;
+  }
+  for (int k = 0; k < nc; k++) {
+    CU(cudaMemcpyAsync(tmp.data(), comp[k], sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    for (long long i = 0; i < np; i++) o[i * nc + k] = tmp[i];
+  }
+  return 0;
+}
+
+int kml_solid_device_ptr(kml_ctx *c, int sid, int field, int comp_idx, void **dptr) {
+  Solid *S = c->solids[sid];
+  if (field == KML_P_PTAG) { *dptr = S->s.ptag; return 0; }
+  if (field == KML_P_MASK) { *dptr = S->s.mask; return 0; }
+  double *comp[9]; int nc; bool sym;
+  if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
+  if (comp_idx < 0 || comp_idx >= nc) return fail("component out of range");
+  *dptr = comp[comp_idx]; return 0;
+}
+
+int kml_set_dt(kml_ctx *c, double dt) { c->dt = dt; return 0; }
+int kml_get_dt(kml_ctx *c, double *dt) { *dt = c->dt; return 0; }
+
+// ---- stages -----------------------------------------------------------------------------------
+int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  // Weights are functions of the step-start positions: make the positions advanced by
+  // the previous step current.  UL re-bins the particles by cell for the cell-centric P2G.
+  if (!c->c.is_TL) {
+    for (Solid *S : c->solids) if (S->moved) { for (int k = 0; k < 3; k++) std::swap(S->s.x[k], S->s.xn[k]); S->moved = false; }
+    if (c->use_cell_p2g && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+      StageTimer t(c, KML_STAGE_REBIN);
+      for (Solid *S : c->solids) {
+        Grid *G = c->grids[S->d.grid];
+        int nl = 0;
+        if (G->cl.build(S->s, G->g, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
+        c->launches[KML_STAGE_REBIN] += nl;
+        if (c->solids.size() > 1) break; // cell lists are per grid; several solids on one grid use the atomic path
+      }
+    }
+  }
+  return 0;
+}
+
+int kml_reset(kml_ctx *c) { // ULMPM::reset: mbp = 0, dtCFL = 1e22
+  CU(cudaSetDevice(c->dev));
+  for (Solid *S : c->solids) {
+    S->dtCFL = 1.0e22;
+    if (S->mbp_nonzero) { for (int k = 0; k < 3; k++) CU(cudaMemsetAsync(S->s.mbp[k], 0, sizeof(double) * S->s.np, c->stream)); S->mbp_nonzero = false; }
+    const double init[2] = {0.0, 1.0};
+    CU(cudaMemcpyAsync(S->red, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+  }
+  return 0;
+}
+
+static int p2g_launch(kml_ctx *c, int what_in, int stage) {
+  StageTimer t(c, stage);
+  StepParams sp = step_params(c);
+  const bool TL = c->c.is_TL;
+  // zero the node accumulators touched by this pass (the "reset" branches of src/solid.cpp:317-574)
+  for (size_t is = 0; is < c->solids.size(); is++) {
+    Solid *S = c->solids[is]; Grid *G = c->grids[S->d.grid]; GridDev &g = G->g;
+    const bool reset = TL ? true : (is == 0);
+    int what = what_in;
+    if (TL && (what & P2G_MASS)) { if (c->tl_mass_done) what &= ~P2G_MASS; }
+    if ((what & P2G_MB) && !S->mbp_nonzero) what &= ~P2G_MB;
+    const size_t nb = sizeof(double) * g.nn;
+    if (reset) {
+      if (what & P2G_MASS) CU(cudaMemsetAsync(g.mass, 0, nb, c->stream));
+      if (what & P2G_MOM) for (int k = 0; k < 3; k++) CU(cudaMemsetAsync(g.v[k], 0, nb, c->stream));
+      if (what_in & P2G_FORCE) for (int k = 0; k < 3; k++) { CU(cudaMemsetAsync(g.f[k], 0, nb, c->stream)); CU(cudaMemsetAsync(g.mb[k], 0, nb, c->stream)); }
+      if (what & P2G_TEMP) CU(cudaMemsetAsync(g.T, 0, nb, c->stream));
+      if (what & P2G_HEAT) { CU(cudaMemsetAsync(g.Qext, 0, nb, c->stream)); CU(cudaMemsetAsync(g.Qint, 0, nb, c->stream)); }
+    }
+    if (what == 0) continue;
+    bool done = false;
+    if (!TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
+        !(what & (P2G_TEMP | P2G_HEAT))) {
+      int nl = 0;
+      if (cell_p2g_launch(S->s, g, G->cl, what, c->stream, &nl)) return fail("cell p2g launch failed");
+      c->launches[stage] += nl; done = true;
+    }
+    if (!done) {
+      KML_DISPATCH(k_p2g, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, g, sp, what));
+      c->launches[stage]++;
+    }
+    if (check_launch("k_p2g")) return 1;
+    if (what & P2G_MOM) G->v_is_momentum = true;
+    if (what & P2G_TEMP) G->T_is_weighted = true;
+  }
+  if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
+  return 0;
+}
+
+int kml_particles_to_grid(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  int what = P2G_MASS | P2G_MOM | P2G_FORCE | P2G_MB | (c->c.temp ? (P2G_TEMP | P2G_HEAT) : 0);
+  return p2g_launch(c, what, KML_STAGE_P2G);
+}
+int kml_particles_to_grid_USF_1(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  return p2g_launch(c, P2G_MASS | P2G_MOM | (c->c.temp ? P2G_TEMP : 0), KML_STAGE_P2G);
+}
+int kml_particles_to_grid_USF_2(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  return p2g_launch(c, P2G_FORCE | P2G_MB | (c->c.temp ? P2G_HEAT : 0), KML_STAGE_P2G);
+}
+
+static std::vector<Grid *> active_grids(kml_ctx *c) {
+  std::vector<Grid *> r;
+  for (Solid *S : c->solids) { Grid *G = c->grids[S->d.grid]; if (std::find(r.begin(), r.end(), G) == r.end()) r.push_back(G); }
+  return r;
+}
+
+int kml_update_grid_state(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_GRID);
+  for (Grid *G : active_grids(c)) {
+    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted);
+    G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
+    if (check_launch("k_grid_update")) return 1;
+  }
+  return 0;
+}
+
+int kml_grid_to_points(kml_ctx *c) { c->pending_g2p = true; return 0; }
+
+int kml_advance_particles(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  if (!c->pending_g2p) return fail("advance_particles called without grid_to_points");
+  c->pending_g2p = false;
+  StageTimer t(c, KML_STAGE_G2P);
+  StepParams sp = step_params(c);
+  for (Solid *S : c->solids) {
+    Grid *G = c->grids[S->d.grid];
+    if (grid_normalize_if_needed(c, G)) return 1;
+    KML_DISPATCH(k_g2p, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, sp));
+    c->launches[KML_STAGE_G2P]++;
+    if (check_launch("k_g2p")) return 1;
+    if (!c->c.is_TL) S->moved = true;
+  }
+  return 0;
+}
+
+int kml_velocities_to_grid(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  if (c->pending_g2p) return fail("velocities_to_grid called between grid_to_points and advance_particles");
+  if (p2g_launch(c, P2G_MOM | (c->c.temp ? P2G_TEMP : 0), KML_STAGE_V2G)) return 1;
+  // the reference divides by the node mass inside compute_velocity_nodes; fixes that follow
+  // (post_velocities_to_grid) and the gradient gather need velocities, so normalise now
+  StageTimer t(c, KML_STAGE_V2G);
+  for (Grid *G : active_grids(c)) if (grid_normalize_if_needed(c, G)) return 1;
+  return 0;
+}
+
+int kml_update_grid_positions(kml_ctx *c) {
+  if (!c->c.is_TL) return 0;
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_GRID);
+  for (Grid *G : active_grids(c)) {
+    if (grid_normalize_if_needed(c, G)) return 1;
+    k_grid_positions<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt); c->launches[KML_STAGE_GRID]++;
+  }
+  return check_launch("k_grid_positions");
+}
+
+int kml_compute_rate_deformation_gradient(kml_ctx *c, int doublemapping) {
+  c->pending_grad = doublemapping ? 1 : 0;
+  c->grad_moved = false;
+  for (Solid *S : c->solids) if (S->moved) c->grad_moved = true;
+  return 0;
+}
+int kml_update_deformation_gradient(kml_ctx *c) {
+  if (c->pending_grad < 0) return fail("update_deformation_gradient called without compute_rate_deformation_gradient");
+  c->pending_F = true; return 0;
+}
+
+int kml_update_stress(kml_ctx *c, int doublemapping) {
+  CU(cudaSetDevice(c->dev));
+  if (!c->pending_F || c->pending_grad < 0) return fail("update_stress called without compute_rate_deformation_gradient + update_deformation_gradient");
+  StageTimer t(c, KML_STAGE_STRESS);
+  StepParams sp = step_params(c);
+  for (Solid *S : c->solids) {
+    Grid *G = c->grids[S->d.grid];
+    if (grid_normalize_if_needed(c, G)) return 1;
+    StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
+    (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
+    KML_DISPATCH(k_stress, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, sp, tp, S->d.mat));
+    c->launches[KML_STAGE_STRESS]++;
+    if (check_launch("k_stress")) return 1;
+  }
+  c->pending_F = false; c->pending_grad = -1;
+  return 0;
+}
+
+int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_OTHER);
+  const int ns = (int)c->solids.size();
+  if (ns * 2 + 1 > 64) return fail("too many solids");
+  for (int i = 0; i < ns; i++) CU(cudaMemcpyAsync(c->h_pinned + 2 * i, c->solids[i]->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_pinned + 2 * ns, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  unsigned flags; memcpy(&flags, c->h_pinned + 2 * ns, sizeof flags);
+  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed)");
+  double dtCFL = 1.0e22;
+  for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
+    Solid *S = c->solids[i]; Grid *G = c->grids[S->d.grid];
+    const double wave = c->h_pinned[2 * i], hr = c->c.is_TL ? c->h_pinned[2 * i + 1] : 1.0;
+    S->dtCFL = std::min(S->dtCFL, G->d.cellsize * hr / wave);
+    dtCFL = std::min(dtCFL, S->dtCFL);
+  }
+  if (dtCFL == 0 || std::isnan(dtCFL)) return fail("dtCFL == 0 or NaN");
+  c->dt = dtCFL * dt_factor;
+  if (dt_out) *dt_out = c->dt;
+  return 0;
+}
+
+int kml_exchange_particles(kml_ctx *) { return 0; }
+
+// ---- fixes ------------------------------------------------------------------------------------
+static int read_scratch3(kml_ctx *c, double out[3]) {
+  CU(cudaMemcpyAsync(c->h_pinned + 32, c->d_scratch, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int d = 0; d < 3; d++) out[d] = c->h_pinned[32 + d];
+  return 0;
+}
+
+int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which, double ftot[3]) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_GRID);
+  if (which == 0) CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
+  std::vector<Grid *> gs;
+  if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
+  for (Grid *G : gs) {
+    if (grid_normalize_if_needed(c, G)) return 1;
+    k_fix_velocity_nodes<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, v[0], v[1], v[2], vprev ? vprev[0] : 0, vprev ? vprev[1] : 0,
+                                                                        vprev ? vprev[2] : 0, which, 1.0 / c->dt, c->d_scratch);
+    c->launches[KML_STAGE_GRID]++;
+  }
+  if (check_launch("k_fix_velocity_nodes")) return 1;
+  if (which == 0 && ftot) return read_scratch3(c, ftot);
+  return 0;
+}
+
+int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_GRID);
+  CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
+  std::vector<Grid *> gs;
+  if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
+  for (Grid *G : gs) { k_fix_body_force<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, f[0], f[1], f[2], c->d_scratch); c->launches[KML_STAGE_GRID]++; }
+  if (check_launch("k_fix_body_force")) return 1;
+  if (ftot) return read_scratch3(c, ftot);
+  return 0;
+}
+
+static int contact(kml_ctx *c, int s1, int s2, int hertz, double mu, double ftot[3]) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_CONTACT);
+  Solid *A = c->solids[s1], *B = c->solids[s2];
+  if (c->c.dimension == 1) return 0;
+  ContactParams cp; cp.dim = c->c.dimension; cp.hertz = hertz; cp.axisymmetric = c->c.axisymmetric; cp.temp = c->c.temp; cp.mu = mu; cp.dt = c->dt;
+  const kml_material &m1 = A->d.mat, &m2 = B->d.mat;
+  cp.Estar = 1.0 / ((1 - m1.nu * m1.nu) / m1.E + (1 - m2.nu * m2.nu) / m2.E);
+  cp.max_cellsize = std::max(c->grids[A->d.grid]->d.cellsize, c->grids[B->d.grid]->d.cellsize);
+  cp.alpha = m1.kappa / (m1.kappa + m2.kappa); cp.invcp1 = m1.invcp; cp.invcp2 = m2.invcp;
+  CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
+  // contact uses the current positions: for UL these are the step-start positions (x)
+  SolidDev a = A->s, b = B->s;
+  k_contact<<<nblocks(a.np, 128), 128, 0, c->stream>>>(a, b, cp, c->d_scratch);
+  c->launches[KML_STAGE_CONTACT]++;
+  if (check_launch("k_contact")) return 1;
+  A->mbp_nonzero = B->mbp_nonzero = true;
+  if (ftot) return read_scratch3(c, ftot);
+  return 0;
+}
+int kml_fix_contact_hertz(kml_ctx *c, int s1, int s2, double ftot[3]) { return contact(c, s1, s2, 1, 0.0, ftot); }
+int kml_fix_contact_min_penetration(kml_ctx *c, int s1, int s2, double mu, double ftot[3]) { return contact(c, s1, s2, 0, mu, ftot); }
+
+static int energy(kml_ctx *c, int solid, int groupbit, int kinetic, double *out) {
+  CU(cudaSetDevice(c->dev));
+  CU(cudaMemsetAsync(c->d_scratch + 8, 0, sizeof(double), c->stream));
+  for (size_t i = 0; i < c->solids.size(); i++) {
+    if (solid != -1 && (int)i != solid) continue;
+    Solid *S = c->solids[i];
+    k_energy<<<nblocks(S->s.np, 256), 256, 0, c->stream>>>(S->s, groupbit, kinetic, c->d_scratch + 8);
+    c->launches[KML_STAGE_OTHER]++;
+  }
+  if (check_launch("k_energy")) return 1;
+  CU(cudaMemcpyAsync(c->h_pinned + 40, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c->h_pinned[40]; return 0;
+}
+int kml_compute_kinetic_energy(kml_ctx *c, int solid, int groupbit, double *ek) { return energy(c, solid, groupbit, 1, ek); }
+int kml_compute_strain_energy(kml_ctx *c, int solid, int groupbit, double *es) { return energy(c, solid, groupbit, 0, es); }
+
+int kml_error_flags(kml_ctx *c, unsigned *flags) {
+  CU(cudaSetDevice(c->dev));
+  CU(cudaMemcpyAsync(c->h_pinned + 48, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(flags, c->h_pinned + 48, sizeof(unsigned)); return 0;
+}
+
+int kml_comm_unique_id(void *) { return fail("kml: multi-GPU communicator not built into this library version"); }
+int kml_comm_init(kml_ctx *, const void *) { return fail("kml: multi-GPU communicator not built into this library version"); }
+
+int kml_profile(kml_ctx *c, int enable) { c->profile = enable != 0; return 0; }
+int kml_stage_times(kml_ctx *c, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset) {
+  for (int i = 0; i < KML_STAGE_COUNT; i++) { ms[i] = c->ms[i]; launches[i] = c->launches[i]; }
+  if (reset) { memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches); }
+  return 0;
+}
+
+} // extern "C"

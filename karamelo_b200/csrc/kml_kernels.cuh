@@ -1,0 +1,530 @@
+// kml_kernels.cuh - the per-stage kernels of the MPM step (baseline, all dimensions /
+// shape functions / UL + TL).  Weights are recomputed in registers from the step-start
+// positions by every consumer (no stored neighbour lists; the reference rebuilds
+// vector<vector<>> lists every step, src/ulmpm.cpp:88-337); TL uses the reference
+// configuration x0 (src/tlmpm.cpp:87-340), which is equivalent to its one-time cache.
+#pragma once
+#include "kml_device.cuh"
+
+namespace kml {
+
+struct SolidDev {
+  long long np;
+  double *x[3], *xn[3], *x0[3], *v[3], *mbp[3], *q[3];
+  double *sig[6], *eel[6], *F[9];
+  double *vol0, *vol, *rho0, *mass, *eps, *epsdot, *dmg, *dmgi, *ien, *T, *gamma;
+  double *pk1[9], *R[9]; // TL only
+  long long *ptag; int *mask;
+};
+
+struct StepParams {
+  double dt, alpha;        // alpha = PIC_FLIP
+  double boxlo[3], boxhi[3];
+  int axisymmetric, temp;
+  unsigned *flags;         // device error word
+};
+
+enum { P2G_MASS = 1, P2G_MOM = 2, P2G_FORCE = 4, P2G_MB = 8, P2G_TEMP = 16, P2G_HEAT = 32 };
+
+// symmetric index helper: (xx,yy,zz,xy,xz,yz)
+__device__ __forceinline__ void load_sym(double *const *a, long long i, double *m) {
+  double xx = a[0][i], yy = a[1][i], zz = a[2][i], xy = a[3][i], xz = a[4][i], yz = a[5][i];
+  m[0] = xx; m[1] = xy; m[2] = xz; m[3] = xy; m[4] = yy; m[5] = yz; m[6] = xz; m[7] = yz; m[8] = zz;
+}
+__device__ __forceinline__ void store_sym(double *const *a, long long i, const double *m) {
+  a[0][i] = m[0]; a[1][i] = m[4]; a[2][i] = m[8]; a[3][i] = m[1]; a[4][i] = m[2]; a[5][i] = m[5];
+}
+
+template <int DIM, int SHAPE, bool TL> struct Stencil {
+  static constexpr int SPAN = StencilSpan<SHAPE, TL>::value;
+  int i0[3];
+  double w[3][SPAN], dw[3][SPAN];
+  __device__ __forceinline__ void build(const GridDev &g, double px, double py, double pz) {
+    axis_weights<SHAPE, TL, SPAN>(px, g.lo[0], g.h, g.inv_cellsize, g.n[0], i0[0], w[0], dw[0]);
+    if (DIM >= 2) axis_weights<SHAPE, TL, SPAN>(py, g.lo[1], g.h, g.inv_cellsize, g.n[1], i0[1], w[1], dw[1]);
+    else { i0[1] = 0; w[1][0] = 1; dw[1][0] = 0; }
+    if (DIM == 3) axis_weights<SHAPE, TL, SPAN>(pz, g.lo[2], g.h, g.inv_cellsize, g.n[2], i0[2], w[2], dw[2]);
+    else { i0[2] = 0; w[2][0] = 1; dw[2][0] = 0; }
+  }
+};
+
+// iterate the stencil in the reference's (i,j,k) order; body(node, wf, wfd0, wfd1, wfd2)
+#define KML_FOR_STENCIL(st, g, ...)                                                                    \
+  _Pragma("unroll") for (int sa_ = 0; sa_ < decltype(st)::SPAN; sa_++) {                               \
+    const double wx = st.w[0][sa_], dwx = st.dw[0][sa_];                                               \
+    if (wx == 0.0) continue;                                                                           \
+    const long long ni = (long long)(st.i0[0] + sa_) * g.n[1];                                         \
+    _Pragma("unroll") for (int sb_ = 0; sb_ < (DIM >= 2 ? decltype(st)::SPAN : 1); sb_++) {            \
+      const double wy = st.w[1][sb_], dwy = st.dw[1][sb_];                                             \
+      if (wy == 0.0) continue;                                                                         \
+      const long long nij = (ni + (DIM >= 2 ? st.i0[1] + sb_ : 0)) * g.n[2];                           \
+      _Pragma("unroll") for (int sc_ = 0; sc_ < (DIM == 3 ? decltype(st)::SPAN : 1); sc_++) {          \
+        const double wz = st.w[2][sc_], dwz = st.dw[2][sc_];                                           \
+        if (wz == 0.0) continue;                                                                       \
+        const long long node = nij + (DIM == 3 ? st.i0[2] + sc_ : 0);                                  \
+        const double wf = (DIM == 1) ? wx : ((DIM == 2) ? wx * wy : wx * wy * wz);                     \
+        const double wfd0 = (DIM == 1) ? dwx : ((DIM == 2) ? dwx * wy : dwx * wy * wz);                \
+        const double wfd1 = (DIM == 1) ? 0.0 : ((DIM == 2) ? wx * dwy : wx * dwy * wz);                \
+        const double wfd2 = (DIM == 3) ? wx * wy * dwz : 0.0;                                          \
+        __VA_ARGS__                                                                                    \
+      }                                                                                                \
+    }                                                                                                  \
+  }
+
+// ---- P2G scatter (baseline: one thread per particle, fp64 RED atomics) ----------------------
+// Solid::compute_mass_nodes src/solid.cpp:317-335, compute_velocity_nodes :337-390 (momentum; the
+// division by the node mass happens in the grid kernel), compute_external_and_internal_forces_nodes_UL
+// :482-522, compute_external_forces_nodes :428-450, compute_internal_forces_nodes_TL :452-480,
+// thermal P2G src/solid.cpp:2743-2796.
+template <int DIM, int SHAPE, bool TL>
+__global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams sp, int what) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= s.np) return;
+  const double px = TL ? s.x0[0][ip] : s.x[0][ip], py = TL ? s.x0[1][ip] : s.x[1][ip], pz = TL ? s.x0[2][ip] : s.x[2][ip];
+  Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
+  const double m = s.mass[ip];
+  double mv[3] = {0, 0, 0}, A[9], mbp[3] = {0, 0, 0}, hoop = 0, mT = 0, gam = 0, qv[3] = {0, 0, 0};
+  if (what & P2G_MOM) { mv[0] = s.v[0][ip]; mv[1] = s.v[1][ip]; mv[2] = s.v[2][ip]; }
+  if (what & P2G_FORCE) {
+    if (TL) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) A[i] = s.pk1[i][ip];
+      if (sp.axisymmetric) hoop = A[8] / s.x0[0][ip];
+    } else {
+      load_sym(s.sig, ip, A);
+      const double vol = s.vol[ip];
+      if (sp.axisymmetric) hoop = vol * (A[8] / s.x[0][ip]);
+#pragma unroll
+      for (int i = 0; i < 9; i++) A[i] *= vol;
+    }
+  }
+  if (what & P2G_MB) { mbp[0] = s.mbp[0][ip]; mbp[1] = s.mbp[1][ip]; mbp[2] = s.mbp[2][ip]; }
+  if (what & P2G_TEMP) mT = m * s.T[ip];
+  if (what & P2G_HEAT) { gam = s.gamma[ip]; qv[0] = s.q[0][ip]; qv[1] = s.q[1][ip]; qv[2] = s.q[2][ip]; }
+
+  KML_FOR_STENCIL(st, g, {
+    if (what & P2G_MASS) atomicAdd(&g.mass[node], wf * m);
+    if (what & P2G_MOM) {
+      const double wm = wf * m;
+      atomicAdd(&g.v[0][node], wm * mv[0]);
+      if (DIM >= 2) atomicAdd(&g.v[1][node], wm * mv[1]);
+      if (DIM == 3) atomicAdd(&g.v[2][node], wm * mv[2]);
+    }
+    if (what & P2G_FORCE) {
+      double f0 = -(A[0] * wfd0 + A[1] * wfd1 + A[2] * wfd2);
+      if (sp.axisymmetric) f0 -= hoop * wf;
+      atomicAdd(&g.f[0][node], f0);
+      if (DIM >= 2) atomicAdd(&g.f[1][node], -(A[3] * wfd0 + A[4] * wfd1 + A[5] * wfd2));
+      if (DIM == 3) atomicAdd(&g.f[2][node], -(A[6] * wfd0 + A[7] * wfd1 + A[8] * wfd2));
+    }
+    if (what & P2G_MB) {
+      atomicAdd(&g.mb[0][node], wf * mbp[0]);
+      if (DIM >= 2) atomicAdd(&g.mb[1][node], wf * mbp[1]);
+      if (DIM == 3) atomicAdd(&g.mb[2][node], wf * mbp[2]);
+    }
+    if (what & P2G_TEMP) atomicAdd(&g.T[node], wf * mT);
+    if (what & P2G_HEAT) {
+      atomicAdd(&g.Qext[node], wf * gam);
+      atomicAdd(&g.Qint[node], wfd0 * qv[0] + wfd1 * qv[1] + wfd2 * qv[2]);
+    }
+  })
+}
+
+// ---- grid kernels ----------------------------------------------------------------------------
+// normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
+// Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
+__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nn) return;
+  const double m = g.mass[i];
+  double v[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    v[d] = g.v[d][i];
+    if (normalize) { v[d] = (m > 0) ? v[d] / m : 0.0; g.v[d][i] = v[d]; }
+  }
+  double T = 0;
+  if (temp) { T = g.T[i]; if (normalize_T) { T = (m > 0) ? T / m : 0.0; g.T[i] = T; } }
+  if (update) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) g.vu[d][i] = (m != 0) ? v[d] + dt * (g.f[d][i] + g.mb[d][i]) / m : v[d];
+    if (temp) g.Tu[i] = (m != 0) ? T + dt * (g.Qint[i] + g.Qext[i]) / m : T;
+  }
+}
+
+// Grid::update_grid_positions, src/grid.cpp:468-474 (TL)
+__global__ void k_grid_positions(GridDev g, double dt) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nn) return;
+#pragma unroll
+  for (int d = 0; d < 3; d++) g.x[d][i] += dt * g.v[d][i];
+}
+
+// ---- G2P + advance ---------------------------------------------------------------------------
+// Solid::compute_particle_accelerations_velocities_and_positions src/solid.cpp:576-635 fused with
+// Solid::update_particle_velocities src/solid.cpp:786-796 and update_particle_temperature :2798-2808.
+template <int DIM, int SHAPE, bool TL>
+__global__ void __launch_bounds__(128) k_g2p(SolidDev s, GridDev g, StepParams sp) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= s.np) return;
+  const double px = TL ? s.x0[0][ip] : s.x[0][ip], py = TL ? s.x0[1][ip] : s.x[1][ip], pz = TL ? s.x0[2][ip] : s.x[2][ip];
+  Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
+  double vu[3] = {0, 0, 0}, a[3] = {0, 0, 0}, Tp = 0;
+  KML_FOR_STENCIL(st, g, {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double gvu = g.vu[d][node];
+      vu[d] += wf * gvu;
+      a[d] += wf * (gvu - g.v[d][node]);
+    }
+    if (sp.temp) Tp += wf * g.Tu[node];
+    (void)wfd0; (void)wfd1; (void)wfd2;
+  })
+  const double inv_dt = 1.0 / sp.dt;
+  double xnew[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double ad = a[d] * inv_dt;
+    const double xo = s.x[d][ip];
+    xnew[d] = xo + sp.dt * vu[d];
+    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * (s.v[d][ip] + sp.dt * ad);
+    if (TL) s.x[d][ip] = xnew[d]; else s.xn[d][ip] = xnew[d];
+  }
+  if (sp.temp) s.T[ip] = Tp;
+  if (!TL) { // Domain::inside, src/domain.cpp:176-185 -> error flag instead of abort (src/solid.cpp:617-627)
+    bool in = xnew[0] >= sp.boxlo[0] && xnew[0] <= sp.boxhi[0] && xnew[1] >= sp.boxlo[1] && xnew[1] <= sp.boxhi[1] && xnew[2] >= sp.boxlo[2] && xnew[2] <= sp.boxhi[2];
+    if (!in) atomicOr(sp.flags, 1u);
+  }
+}
+
+// ---- velocity gradient + deformation gradient + stress, fused ---------------------------------
+// Solid::compute_rate_deformation_gradient_UL/_TL src/solid.cpp:798-936, update_deformation_gradient
+// :1155-1244, update_stress :1246-1438 (+ update_heat_flux :2810-2839).  One thread per particle;
+// L, D, Finv, J, rho never touch HBM.
+struct StressParams {
+  int doublemapping;    // gather from grid v (1) or v_update (0)
+  int moved;            // axisymmetric hoop term uses the moved position (MUSL) or the step-start one (USL/USF)
+  double *max_wave;     // device scalar: max_p (c_p + |v|_inf)
+  double *min_h_ratio;  // device scalar (TL)
+};
+
+template <int DIM, int SHAPE, bool TL>
+__global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double wave = 0, hr = 1.0;
+  if (ip < s.np) {
+    const double px = TL ? s.x0[0][ip] : s.x[0][ip], py = TL ? s.x0[1][ip] : s.x[1][ip], pz = TL ? s.x0[2][ip] : s.x[2][ip];
+    Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
+    double *const *gv = tp.doublemapping ? g.v : g.vu;
+    const double *gT = tp.doublemapping ? g.T : g.Tu;
+    double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hoop = 0, qv[3] = {0, 0, 0};
+    KML_FOR_STENCIL(st, g, {
+      const double wfd[3] = {wfd0, wfd1, wfd2};
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        const double va = gv[a][node];
+#pragma unroll
+        for (int b = 0; b < DIM; b++) L[3 * a + b] += va * wfd[b];
+        if (a == 0 && DIM == 2 && sp.axisymmetric) hoop += va * wf;
+      }
+      if (sp.temp) {
+        const double Tn = gT[node];
+#pragma unroll
+        for (int b = 0; b < 3; b++) qv[b] -= wfd[b] * Tn;
+      }
+    })
+    if (DIM == 2 && sp.axisymmetric) {
+      const double xr = TL ? s.x0[0][ip] : (tp.moved ? s.xn[0][ip] : s.x[0][ip]);
+      L[8] += hoop / xr; // the reference divides term by term; same value up to rounding
+    }
+    const double dt = sp.dt;
+    double F[9], Fn[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = s.F[i][ip];
+    if (TL) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) Fn[i] = F[i] + dt * L[i]; // here L holds Fdot
+    } else {
+      double IL[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) IL[i] = dt * L[i];
+      IL[0] += 1; IL[4] += 1; IL[8] += 1;
+      mul3(IL, F, Fn);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
+    double Finv[9]; inv3(Fn, Finv);
+    const double J = det3(Fn);
+    const double vol0 = s.vol0[ip];
+    const double vol = J * vol0;
+    s.vol[ip] = vol;
+    const double damage_old = s.dmg[ip];
+    if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);
+    const double rho = s.rho0[ip] / J;
+    double D[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (mat.type != KML_MAT_NEO_HOOKEAN) {
+      if (TL) {
+        if (!poldec3(Fn, R)) atomicOr(sp.flags, 8u);
+        double Lt[9], S[9], T1[9];
+        mul3(L, Finv, Lt);                     // L = Fdot Finv
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) S[3 * a + b] = Lt[3 * a + b] + Lt[3 * b + a];
+        mul3_at(R, S, T1); mul3(T1, R, D);     // R^T (L + L^T) R
+#pragma unroll
+        for (int i = 0; i < 9; i++) D[i] *= 0.5;
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.R[i][ip] = R[i];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) D[3 * a + b] = 0.5 * (L[3 * a + b] + L[3 * b + a]);
+      }
+    }
+    double sig[9], eel[9];
+    load_sym(s.sig, ip, sig); load_sym(s.eel, ip, eel);
+    double damage = damage_old;
+    if (mat.type == KML_MAT_LINEAR) {
+      const double tr = dt * D[0] + dt * D[4] + dt * D[8];
+#pragma unroll
+      for (int i = 0; i < 9; i++) { const double inc = dt * D[i]; eel[i] += inc; sig[i] += 2 * mat.G * inc; }
+      const double lt = mat.lambda * tr;
+      sig[0] += lt; sig[4] += lt; sig[8] += lt;
+    } else if (mat.type == KML_MAT_NEO_HOOKEAN) {
+      double PK1[9]; const double lJ = mat.lambda * log(J);
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) PK1[3 * a + b] = mat.G * (Fn[3 * a + b] - Finv[3 * b + a]) + lJ * Finv[3 * b + a];
+      if (TL) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.pk1[i][ip] = vol0 * PK1[i];
+      }
+      double FP[9]; mul3_bt(Fn, PK1, FP);
+      const double iJ = 1.0 / J;
+#pragma unroll
+      for (int i = 0; i < 9; i++) sig[i] = iJ * FP[i];
+      double C[9]; mul3_at(Fn, Fn, C);
+      C[0] -= 1; C[4] -= 1; C[8] -= 1;
+#pragma unroll
+      for (int i = 0; i < 9; i++) eel[i] = 0.5 * C[i];
+    } else { // EOS + strength (+ damage, + plastic-work heating): src/solid.cpp:1292-1374
+      const bool thermal = mat.cp != 0;
+      const double T = thermal ? s.T[ip] : 0.0;
+      const double trD = D[0] + D[4] + D[8];
+      double ien;
+      double pH = eos_pressure(mat, ien, J, rho, damage, trD, g.cellsize, T);
+      s.ien[ip] = ien;
+      if (thermal) pH += mat.tmp_alpha * (mat.tmp_T0 - T);
+      double sdev[9], dep;
+      double eps = s.eps[ip], epsdot = s.epsdot[ip];
+      strength_dev(mat, dt, sig, D, sdev, dep, eps, epsdot, damage, T);
+      eps += dep;
+      const double tav = 1000 * g.cellsize / mat.signal_velocity;
+      epsdot -= epsdot * dt / tav;
+      epsdot += dep / tav;
+      epsdot = (0.0 > epsdot) ? 0.0 : epsdot;
+      s.eps[ip] = eps; s.epsdot[ip] = epsdot;
+      if (mat.damage_type != KML_DAMAGE_NONE) {
+        double di = s.dmgi[ip];
+        damage_jc(mat, di, damage, pH, sdev, epsdot, dep, sp.temp ? s.T[ip] : 0.0);
+        s.dmgi[ip] = di; s.dmg[ip] = damage;
+      }
+      if (thermal) {
+        const double flow = KML_SQRT_3_OVER_2 * frob3(sdev);
+        double gam = (T < mat.tmp_Tm) ? mat.tmp_chi * flow * epsdot : 0.0;
+        gam *= (TL ? vol0 : vol) * mat.invcp;
+        s.gamma[ip] = gam;
+      }
+      const double pf = (damage == 0 || pH >= 0) ? -pH : -pH * (1.0 - damage);
+      const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) / 3.0;
+      const double Gd = (damage > 1e-10) ? mat.G * (1 - damage) : mat.G;
+#pragma unroll
+      for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] / Gd; }
+      sig[0] += pf; sig[4] += pf; sig[8] += pf;
+      eel[0] += te; eel[4] += te; eel[8] += te;
+    }
+    store_sym(s.sig, ip, sig); store_sym(s.eel, ip, eel);
+    if (TL && mat.type != KML_MAT_NEO_HOOKEAN) { // vol0PK1 = vol0 J (R sigma R^T) F^-T
+      double T1[9], T2[9], P[9];
+      mul3(R, sig, T1); mul3_bt(T1, R, T2); mul3_bt(T2, Finv, P);
+      const double c = vol0 * J;
+#pragma unroll
+      for (int i = 0; i < 9; i++) s.pk1[i][ip] = c * P[i];
+    }
+    if (sp.temp) {
+      const double c = (TL ? vol0 : vol) * mat.invcp * mat.kappa;
+#pragma unroll
+      for (int b = 0; b < 3; b++) s.q[b][ip] = qv[b] * c;
+    }
+    if (!(damage >= 1.0)) { // wave speed for the CFL limit, src/solid.cpp:1378-1385
+      const double vx = fabs(s.v[0][ip]), vy = fabs(s.v[1][ip]), vz = fabs(s.v[2][ip]);
+      wave = sqrt((mat.K + KML_FOUR_THIRD * mat.G) / rho) + fmax(fmax(vx, vy), vz);
+      if (isnan(wave)) { atomicOr(sp.flags, 4u); wave = 0; }
+      if (TL) { double e; if (eig3_min_abs_real(Fn, e)) hr = fmin(hr, e); }
+    }
+  }
+  // block reduction -> one atomic per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { wave = fmax(wave, __shfl_xor_sync(0xffffffffu, wave, o)); if (TL) hr = fmin(hr, __shfl_xor_sync(0xffffffffu, hr, o)); }
+  if ((threadIdx.x & 31) == 0) { if (wave > 0) atomic_max_pos(tp.max_wave, wave); if (TL && hr < 1.0) atomic_min_pos(tp.min_h_ratio, hr < 0 ? 0.0 : hr); }
+}
+
+// ---- fixes -----------------------------------------------------------------------------------
+// FixVelocityNodes, src/fix_velocity_nodes.cpp:130-268
+__global__ void k_fix_velocity_nodes(GridDev g, int groupbit, int set_mask, double v0, double v1, double v2, double p0, double p1, double p2,
+                                     int which, double inv_dt, double *ftot) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double f[3] = {0, 0, 0};
+  if (i < g.nn && (g.mask[i] & groupbit)) {
+    const double v[3] = {v0, v1, v2}, p[3] = {p0, p1, p2};
+    if (which == 0) {
+      const double c = inv_dt * g.mass[i];
+#pragma unroll
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = c * (v[d] - g.vu[d][i]); g.vu[d][i] = v[d]; g.v[d][i] = p[d]; }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) g.v[d][i] = v[d];
+    }
+  }
+  if (which == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double x = f[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
+    }
+  }
+}
+// FixBodyforce, src/fix_body_force.cpp:106-180
+__global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f0, double f1, double f2, double *ftot) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double f[3] = {0, 0, 0};
+  if (i < g.nn) {
+    const double m = g.mass[i];
+    if (m > 0 && (g.mask[i] & groupbit)) {
+      const double fv[3] = {f0, f1, f2};
+#pragma unroll
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = fv[d] * m; g.mb[d][i] += f[d]; }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double x = f[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
+  }
+}
+
+// FixContactHertz / FixContactMinPenetration, src/fix_contact_hertz.cpp:84-201,
+// src/fix_contact_min_penetration.cpp:88-258.  All-pairs like the reference, tiled through shared
+// memory: block = 128 particles of solid 1, loops over solid 2 in tiles.  The three screens of the
+// reference are applied in order so the pair set is identical.
+struct ContactParams { int dim, hertz, axisymmetric, temp; double Estar, max_cellsize, mu, dt, alpha, invcp1, invcp2; };
+
+__global__ void __launch_bounds__(128) k_contact(SolidDev s1, SolidDev s2, ContactParams cp, double *ftot) {
+  __shared__ double sx[128], sy[128], sz[128], svol[128], sm[128], svx[128], svy[128], svz[128];
+  const long long i1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i1 < s1.np;
+  double x1 = 0, y1 = 0, z1 = 0, vol1 = 1, m1 = 1, vx1 = 0, vy1 = 0, vz1 = 0;
+  if (act) { x1 = s1.x[0][i1]; y1 = s1.x[1][i1]; z1 = s1.x[2][i1]; vol1 = s1.vol[i1]; m1 = s1.mass[i1]; vx1 = s1.v[0][i1]; vy1 = s1.v[1][i1]; vz1 = s1.v[2][i1]; }
+  double Rp1;
+  if (cp.dim == 2) Rp1 = 0.5 * sqrt(cp.axisymmetric && !cp.hertz ? vol1 / x1 : vol1);
+  else Rp1 = cp.hertz ? 0.5 * pow(vol1, 0.333333333) : 0.5 * cbrt(vol1);
+  double f1[3] = {0, 0, 0}, g1 = 0, ft[3] = {0, 0, 0};
+  const double mc = cp.max_cellsize;
+  for (long long base = 0; base < s2.np; base += 128) {
+    const long long j = base + threadIdx.x;
+    __syncthreads();
+    if (j < s2.np) { sx[threadIdx.x] = s2.x[0][j]; sy[threadIdx.x] = s2.x[1][j]; sz[threadIdx.x] = s2.x[2][j]; svol[threadIdx.x] = s2.vol[j]; sm[threadIdx.x] = s2.mass[j];
+      svx[threadIdx.x] = s2.v[0][j]; svy[threadIdx.x] = s2.v[1][j]; svz[threadIdx.x] = s2.v[2][j]; }
+    __syncthreads();
+    const int cnt = (int)min((long long)128, s2.np - base);
+    if (!act) continue;
+    for (int t = 0; t < cnt; t++) {
+      const double dx = sx[t] - x1, dy = sy[t] - y1, dz = sz[t] - z1;
+      bool near = dx < mc && dy < mc && dx > -mc && dy > -mc;
+      if (cp.dim == 3 || cp.hertz) near = near && dz < mc && dz > -mc;
+      if (!near) continue;
+      double Rp2;
+      if (cp.dim == 2) Rp2 = 0.5 * sqrt(cp.axisymmetric && !cp.hertz ? svol[t] / sx[t] : svol[t]);
+      else Rp2 = cp.hertz ? 0.5 * pow(svol[t], 0.333333333) : 0.5 * cbrt(svol[t]);
+      const double Rp = Rp1 + Rp2;
+      bool near2 = dx < Rp && dy < Rp && dx > -Rp && dy > -Rp;
+      if (cp.dim == 3 || cp.hertz) near2 = near2 && dz < Rp && dz > -Rp;
+      if (!near2) continue;
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      if (!(r < Rp)) continue;
+      double f[3], g2 = 0;
+      if (cp.hertz) {
+        const double p = Rp - r;
+        const double fmag = (cp.dim == 2 ? 0.25 * M_PI : 1.333333333) * cp.Estar * sqrt(Rp1 * Rp2 / (Rp1 + Rp2) * p * p * p);
+        f[0] = fmag * dx / r; f[1] = fmag * dy / r; f[2] = fmag * dz / r;
+        // s1 -= f ; s2 += f
+        f1[0] -= f[0]; f1[1] -= f[1]; f1[2] -= f[2];
+        atomicAdd(&s2.mbp[0][base + t], f[0]); atomicAdd(&s2.mbp[1][base + t], f[1]); atomicAdd(&s2.mbp[2][base + t], f[2]);
+      } else {
+        const double inv_r = 1.0 / r;
+        const double m2 = sm[t];
+        const double fmag = m1 * m2 / ((m1 + m2) * cp.dt * cp.dt) * (1 - Rp * inv_r);
+        f[0] = fmag * dx; f[1] = fmag * dy; f[2] = fmag * dz;
+        if (cp.mu != 0) {
+          const double dvx = svx[t] - vx1, dvy = svy[t] - vy1, dvz = svz[t] - vz1;
+          const double dd = (dvx * dx + dvy * dy + dvz * dz) * inv_r * inv_r;
+          double vt[3] = {dvx - dd * dx, dvy - dd * dy, dvz - dd * dz};
+          const double vtn = sqrt(vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2]);
+          if (vtn != 0) {
+            const double ffric = cp.mu * fmag * r;
+            f[0] -= ffric * (vt[0] / vtn); f[1] -= ffric * (vt[1] / vtn); f[2] -= ffric * (vt[2] / vtn);
+            if (cp.temp) {
+              if (cp.dim == 2) { const double gm = ffric * vtn * cp.dt; g1 += cp.alpha * s1.vol0[i1] * cp.invcp1 * gm; g2 = (1.0 - cp.alpha) * s2.vol0[base + t] * cp.invcp2 * gm; }
+              else { const double gm = cp.alpha * ffric * vtn * cp.dt; g1 += s1.vol0[i1] * cp.invcp1 * gm; g2 = s2.vol0[base + t] * cp.invcp2 * gm; }
+            }
+          }
+        }
+        // s1 += f ; s2 -= f
+        f1[0] += f[0]; f1[1] += f[1]; f1[2] += f[2];
+        atomicAdd(&s2.mbp[0][base + t], -f[0]); atomicAdd(&s2.mbp[1][base + t], -f[1]); atomicAdd(&s2.mbp[2][base + t], -f[2]);
+        if (g2 != 0) atomicAdd(&s2.gamma[base + t], g2);
+      }
+      ft[0] += f[0]; ft[1] += f[1]; ft[2] += f[2];
+    }
+  }
+  if (act) {
+    if (f1[0] != 0 || f1[1] != 0 || f1[2] != 0) { s1.mbp[0][i1] += f1[0]; s1.mbp[1][i1] += f1[1]; s1.mbp[2][i1] += f1[2]; }
+    if (g1 != 0) s1.gamma[i1] += g1;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double x = ft[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
+  }
+}
+
+// ---- reductions for computes -----------------------------------------------------------------
+// ComputeKineticEnergy src/compute_kinetic_energy.cpp:62-102, ComputeStrainEnergy src/compute_strain_energy.cpp:64-117
+__global__ void k_energy(SolidDev s, int groupbit, int kinetic, double *out) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0;
+  if (ip < s.np && (s.mask[ip] & groupbit)) {
+    if (kinetic) { const double a = s.v[0][ip], b = s.v[1][ip], c = s.v[2][ip]; e = 0.5 * s.mass[ip] * (a * a + b * b + c * c); }
+    else {
+      double sg[9], el[9]; load_sym(s.sig, ip, sg); load_sym(s.eel, ip, el);
+      double acc = 0;
+#pragma unroll
+      for (int i = 0; i < 9; i++) acc += sg[i] * el[i];
+      e = 0.5 * s.vol[ip] * acc;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(out, e);
+}
+
+} // namespace kml

@@ -25,7 +25,7 @@ using namespace okml;
 #define MAXV(a, b) ((a) > (b) ? (a) : (b))  /* reference src/pointers.h:23-24 */
 #define MINV(a, b) ((a) < (b) ? (a) : (b))
 #define SQRT_3_OVER_2 1.224744871 /* reference src/solid.cpp:39 (truncated constant, kept) */
-#define FOUR_THIRD 1.333333333    /* reference src/solid.cpp:40 */
+#define FOUR_THIRD 1.333333333333333333333333333333333333333 /* reference src/solid.cpp:40 */
 
 static std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }

@@ -1,0 +1,274 @@
+"""Parity cases: Karamelo scripts (setup only - the tests append their own run commands).
+
+Each case is a reduced variant of one BASELINE.json config, written in the reference's own
+input language so the unmodified reference (oracle/_ref), the CPU oracle and the CUDA engine
+all run exactly the same text.  Discrepancies between BASELINE.json and the shipped example
+files are resolved as SURVEY.md section 8 prescribes (scheme(usl) added to C1, cubic-spline
+variant of C2, thermo-mechanical variant of C3, both contact fixes for C4).
+"""
+
+# C1: examples/two-disks.mpm - 2-D ULMPM, two elastic disks colliding, linear shape functions.
+# The disks start closer together so that they collide within the first 100 steps.
+def two_disks(scheme="usl", v=0.1, c=0.2):
+    return f"""
+E   = 1e+3
+nu  = 0.3
+rho = 1000
+L   = 1
+hL  = 0.5*L
+FLIP=1.0
+method(ulmpm, FLIP, linear, FLIP)
+scheme({scheme})
+N        = 20
+cellsize = L/N
+dimension(2,-hL, hL, -hL, hL, cellsize)
+R = 0.2
+c = {c}
+region(rBall1, cylinder, -c, -c, R)
+region(rBall2, cylinder,  c,  c, R)
+material(mat1, linear, rho, E, nu)
+ppc1d = 2
+solid(sBall1, region, rBall1, ppc1d, mat1, cellsize,0)
+solid(sBall2, region, rBall2, ppc1d, mat1, cellsize,0)
+group(gBall1, particles, region, rBall1, solid, sBall1)
+group(gBall2, particles, region, rBall2, solid, sBall2)
+v = {v}
+fix(v0Ball1, initial_velocity_particles, gBall1,  v,  v, NULL)
+fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, NULL)
+set_dt(0.01)
+"""
+
+
+# C2: examples/Taylor-bar/cylindrical/ULMPM - 3-D ULMPM, Johnson-Cook + shock EOS, MUSL, a short
+# bar one cell away from the rigid wall so that impact plasticity develops within 100 steps.
+def taylor_bar(shape="cubic-spline", N=2, scheme="musl"):
+    return f"""
+E   = 115
+nu  = 0.31
+K   = E/(3*(1-2*nu))
+G   = E/(2*(1+nu))
+rho = 8.94e-06
+sigmay  = 0.065
+B       = 0.356
+C       = 0.013
+n       = 0.37
+m       = 0
+eps0dot = 1e-3
+Tm      = 1600
+hLx   = 3
+R     = 1.6
+Df    = 3
+S     = 1.5
+c0    = 3933
+Gamma = 0
+cv = 0
+Tr = 25
+FLIP = 0.99
+method(ulmpm, FLIP, {shape}, FLIP)
+scheme({scheme})
+N        = {N}
+cellsize = 1/N
+x_wall = hLx + 2*cellsize
+dimension(3, -hLx-1, x_wall, -Df, Df, -Df, Df, cellsize)
+eos(eoss, shock, rho, K, c0, S, Gamma, cv, Tr, 0, 0)
+strength(strengthJC, johnson_cook, G, sigmay, B, n, eps0dot, C, m, Tr, Tm)
+material(mat, eos-strength, eoss, strengthJC)
+region(cyl, cylinder, x, 0, 0, R, -hLx, hLx)
+ppc1d = 2
+solid(solid1, region, cyl, ppc1d, mat, cellsize, Tr)
+region(region2, block, x_wall - cellsize, INF, INF, INF, INF, INF)
+group(groupn2, nodes, region, region2, solid, solid1)
+v = 190
+group(gBall1, particles, region, cyl, solid, solid1)
+fix(v0Ball1, initial_velocity_particles, gBall1, v, NULL, NULL)
+fix(BC_Wall, velocity_nodes, groupn2, 0, NULL, NULL)
+dt_factor(0.25)
+"""
+
+
+# C3: examples/Tensile_with_damage/Bernstein - TLMPM, Bernstein quadratic, JC strength + JC damage,
+# optionally plastic-work heating.  Grip velocity raised so that yield and damage occur within 100 steps.
+def tensile(thermal=False, shape="Bernstein-quadratic", vgrip=40):
+    method = f"method(tlmpm, FLIP, {shape}, FLIP" + (", thermo-mechanical)" if thermal else ")")
+    tmat = "temperature(tpw, plastic_work, 0.9, 452e+6, 50, 0, Tr, Tm)\n" if thermal else ""
+    mat4 = "material(mat4, eos-strength, eoss, strengthjc, damagejc" + (", tpw)" if thermal else ")")
+    return f"""
+E = 211
+nu = 0.33
+K = E/(3*(1-2*nu))
+G = E/(2*(1+nu))
+rho = 7.75e-06
+sigmay = 0.499
+B = 0.382
+n = 0.458
+hLx = 10
+hLy = 1.2
+hLz = 1.2
+S = 1.5
+c0 = 5030
+FLIP=0.99
+cellsize = 0.8
+{method}
+dimension(3, -2*hLx, 2*hLx, -2*hLy, 2*hLy, -2*hLz, 2*hLz, cellsize)
+region(box, block, -hLx, hLx, -hLy, hLy, -hLz, hLz)
+Q1 = 0.06
+Q2 = 1.5
+Tr = 25
+Tm = 1000
+cv = 0
+Gamma = 0
+eos(eoss,   shock, rho, K, c0, S, Gamma, cv, Tr, Q1, Q2)
+strength(strengthjc, johnson_cook, G, sigmay, B, n, 1, 0.01, 0, Tr, Tm)
+d1 = 0.0636
+d2 = 0.1936
+d3 = -2.969
+d4 = 0
+d5 = 0
+epsdot0 = 1
+damage(damagejc, damage_johnson_cook, d1, d2, d3, d4, d5, epsdot0, Tr, Tm)
+{tmat}{mat4}
+ppc = 2
+solid(solid1, region, box, ppc, mat4, cellsize, Tr)
+xBC = 9.7 - cellsize
+region(region1, block, INF, -xBC, INF, INF, INF, INF)
+group(groupn1, nodes, region, region1, solid, solid1)
+region(region2, block, xBC, INF, INF, INF, INF, INF)
+group(groupn2, nodes, region, region2, solid, solid1)
+v = {vgrip}*(1.0-exp(-20000*time))
+fix(BC_left, velocity_nodes, groupn1, -v, NULL, NULL)
+fix(BC_right, velocity_nodes, groupn2, v, NULL, NULL)
+"""
+
+
+# C4: examples/Bouncing_balls/TLMPM/FLIP - TLMPM, two solids on private grids, contact fix.
+def bouncing_balls(contact="minimize_penetration", v=0.5):
+    fix = "fix(contact, contact/minimize_penetration, sBall1, sBall2, 0.3)" if contact == "minimize_penetration" else "fix(contact, contact/hertz, sBall1, sBall2)"
+    return f"""
+E   = 1e+3
+nu  = 0.3
+rho = 1000
+L    = 1
+hL   = 0.5*L
+alphaFLIP=1
+method(tlmpm, FLIP, linear, alphaFLIP)
+N        = 40
+cellsize = L/N
+dimension(2,-hL, hL, -hL, hL, cellsize)
+R = 0.2
+c = 0.16
+region(rBall1, cylinder, -c, -c, R)
+region(rBall2, cylinder, c, c, R)
+material(mat1, linear, rho, E, nu)
+ppc1d = 2
+solid(sBall1, region, rBall1, ppc1d, mat1, cellsize,0)
+solid(sBall2, region, rBall2, ppc1d, mat1, cellsize,0)
+group(gBall1, particles, region, rBall1, solid, sBall1)
+group(gBall2, particles, region, rBall2, solid, sBall2)
+v = {v}
+fix(v0Ball1, initial_velocity_particles, gBall1, v, v, NULL)
+fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, NULL)
+{fix}
+set_dt(0.001)
+"""
+
+
+# C5: synthetic 3-D ULMPM elastoplastic block, cubic B-splines, at test size.
+def block(n=(8, 8, 8), scheme="musl", shape="cubic-spline", fixed_dt=False, a=2.5e-3, ppc=2, strength="plastic"):
+    nx, ny, nz = n
+    a_m, a_e = ("%e" % a).split("e")
+    a_txt = "%s%s%+d" % (a_m.rstrip("0").rstrip("."), "e", int(a_e))  # e.g. 2.5e-3: the parser needs a signed exponent
+    strength_cmd = {"plastic": "strength(s, plastic, G, sigmay)", "linear": "strength(s, linear, G)",
+                    "swift": "strength(s, swift, G, sigmay, 2, 0.001, 0.3)"}[strength]
+    return f"""
+E = 1000
+nu = 0.3
+rho = 1000
+K = E/(3*(1-2*nu))
+G = E/(2*(1+nu))
+sigmay = 3
+h = 1
+method(ulmpm, FLIP, {shape}, 0.99)
+scheme({scheme})
+dimension(3, 0, {nx + 8}, 0, {ny + 8}, 0, {nz + 8}, h)
+region(box, block, 4, {nx + 4}, 4, {ny + 4}, 4, {nz + 4})
+eos(e, linear, rho, K)
+{strength_cmd}
+material(m, eos-strength, e, s)
+solid(blk, region, box, {ppc}, m, h, 0)
+group(gall, particles, region, box, solid, blk)
+a = {a_txt}
+cx = {4 + nx / 2}
+cy = {4 + ny / 2}
+cz = {4 + nz / 2}
+fix(v0, initial_velocity_particles, gall, -a*(x-cx), 0.5*a*(y-cy), 0.5*a*(z-cz))
+{"set_dt(0.2)" if fixed_dt else "dt_factor(0.5)"}
+"""
+
+
+# extra coverage of the functor table (not BASELINE configs): neo-Hookean bar under gravity (USF, quadratic
+# splines) and a Tait-fluid column (EOS fluid + fluid strength, 2-D).
+def neo_hookean_bar(scheme="usf", shape="quadratic-spline"):
+    return f"""
+E = 1e+6
+nu = 0.3
+rho = 1050
+L = 1
+hL = 0.5*L
+method(ulmpm, FLIP, {shape}, 0.99)
+scheme({scheme})
+N = 4
+cellsize = L/N
+dimension(3,-hL-2*cellsize, hL+2*cellsize, -3*L, 2*cellsize, -hL-2*cellsize, hL+2*cellsize, cellsize)
+region(box, block, -hL, hL, -L, 0, -hL, hL)
+material(mat1, neo-hookean, rho, E, nu)
+solid(solid1, region, box, 2, mat1, cellsize, 0)
+region(rBCLX, block, INF, INF, -cellsize/4, INF, INF, INF)
+group(gBCLX, nodes, region, rBCLX, solid, solid1)
+fix(fBCLX, velocity_nodes, gBCLX, 0, 0, 0)
+gravity = -300
+fix(fbody, body_force, all, 0, gravity, 0)
+dt_factor(0.2)
+"""
+
+
+def fluid_column():
+    return """
+gamma = 7
+K     = 1.4e+6
+G     = 0.001
+rhoW  = 998
+method(ulmpm, FLIP, linear, 1.0)
+cellsize = 0.01
+dimension(2, -0.2, 0, 0, 0.14, cellsize)
+eos(eosf, fluid, rhoW, K, gamma)
+strength(strengthf, fluid, G)
+material(mat1, eos-strength, eosf, strengthf)
+region(water, block, -0.1, 0, 0, 0.08)
+solid(solidW, region, water, 2, mat1, cellsize,0)
+region(rBottomW, block, INF, INF, INF, cellsize/4)
+group(gBottomW, nodes, region, rBottomW, solid, solidW)
+region(rRight, block, -cellsize/4, INF, -INF, INF)
+group(gRight, nodes, region, rRight, solid, solidW)
+fix(fBCLYW, velocity_nodes, gBottomW, NULL, 0)
+fix(fBCRX, velocity_nodes, gRight,  0, NULL)
+gravity = -9.81
+fix(fbody, body_force, all, 0, gravity)
+set_dt(1e-6)
+"""
+
+
+# name -> (script, is_TL, thermal, steps)
+CASES = {
+    "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
+    "c1_two_disks_musl": (two_disks("musl"), False, False, 100),
+    "c2_taylor_cubic": (taylor_bar("cubic-spline"), False, False, 100),
+    "c2_taylor_linear": (taylor_bar("linear"), False, False, 100),
+    "c3_tensile_bernstein": (tensile(False), True, False, 100),
+    "c3_tensile_thermal": (tensile(True), True, True, 100),
+    "c4_balls_minpen": (bouncing_balls("minimize_penetration"), True, False, 100),
+    "c4_balls_hertz": (bouncing_balls("hertz"), True, False, 100),
+    "c5_block_musl": (block((8, 8, 8), "musl"), False, False, 100),
+    "c5_block_usl_fixed_dt": (block((6, 6, 6), "usl", fixed_dt=True), False, False, 100),
+    "x_neo_hookean_usf": (neo_hookean_bar(), False, False, 100),
+    "x_fluid_column": (fluid_column(), False, False, 100),
+}

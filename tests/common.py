@@ -1,0 +1,75 @@
+"""Shared comparison helpers for the parity tests."""
+import os
+
+import numpy as np
+
+from karamelo_b200.api import Engine, P
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SYM = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+FIELDS = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "DAMAGE", "DAMAGE_INIT")
+
+
+def run_case(lib, script, steps, thermal=False, extra_fields=()):
+    e = Engine(lib)
+    e.script(script + "\nrun(%d)\n" % steps)
+    snap = e.snapshot(FIELDS + (("T",) if thermal else ()) + tuple(extra_fields))
+    st = e.state()
+    e.close()
+    return snap, st
+
+
+def rel(a, b):
+    """max |a - b| relative to the magnitude of the reference field (north_star tolerance)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.size == 0:
+        return 0.0
+    scale = max(float(np.max(np.abs(b))), 1e-300)
+    return float(np.max(np.abs(a - b))) / scale
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = []
+    for i in range(int(g["nsolids"])):
+        d = {k: g["%s%d" % (k, i)] for k in ("ptag", "x", "v", "sigma", "F", "eps", "epsdot", "damage", "damage_init")}
+        if "T%d" % i in g:
+            d["T"] = g["T%d" % i]
+        out.append(d)
+    return out, g["log_last"]
+
+
+def compare_to_golden(snap, golden, tol, floors=None):
+    """Returns {field: worst relative error}; asserts tags are identical and errors within tol."""
+    worst = {}
+    assert len(snap) == len(golden)
+    for s, r in zip(snap, golden):
+        assert s["PTAG"].shape == r["ptag"].shape and (s["PTAG"] == r["ptag"]).all(), "particle counts / tags differ"
+        pairs = {
+            "x": (s["X"], r["x"]), "v": (s["V"], r["v"]),
+            "sigma": (np.stack([s["SIGMA"][:, a, b] for a, b in SYM], 1), r["sigma"]),
+            "F": (s["FDEF"].reshape(len(r["ptag"]), 9), r["F"]),
+            "eps": (s["EFF_PLASTIC_STRAIN"], r["eps"]), "epsdot": (s["EFF_PLASTIC_STRAIN_RATE"], r["epsdot"]),
+            "damage": (s["DAMAGE"], r["damage"]), "damage_init": (s["DAMAGE_INIT"], r["damage_init"]),
+        }
+        if "T" in r and "T" in s:
+            pairs["T"] = (s["T"], r["T"])
+        for k, (a, b) in pairs.items():
+            worst[k] = max(worst.get(k, 0.0), rel(a, b))
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, "fields beyond tolerance %g: %s (all: %s)" % (tol, bad, worst)
+    return worst
+
+
+def compare_snaps(a, b, tol):
+    worst = {}
+    assert len(a) == len(b)
+    for s, r in zip(a, b):
+        assert (s["PTAG"] == r["PTAG"]).all(), "particle counts / tags differ"
+        for k in s:
+            if k == "PTAG":
+                continue
+            worst[k] = max(worst.get(k, 0.0), rel(s[k], r[k]))
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, "fields beyond tolerance %g: %s (all: %s)" % (tol, bad, worst)
+    return worst
