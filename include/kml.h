@@ -249,6 +249,10 @@ enum { KML_STAGE_REBIN = 0, KML_STAGE_P2G, KML_STAGE_GRID, KML_STAGE_G2P, KML_ST
        KML_STAGE_CONTACT, KML_STAGE_OTHER, KML_STAGE_COUNT };
 int kml_profile(kml_ctx *ctx, int enable);
 int kml_stage_times(kml_ctx *ctx, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset);
+/* CUDA-event bracket on the context's stream: start records an event, stop records a second one,
+ * synchronises and returns the elapsed device time in milliseconds. */
+int kml_timer_start(kml_ctx *ctx);
+int kml_timer_stop(kml_ctx *ctx, double *ms);
 
 #ifdef __cplusplus
 }

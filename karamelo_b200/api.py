@@ -111,6 +111,8 @@ def load_host_library(path=None):
         "kml_stage_times": (i32, [vp, PD, PL, i32]),
         "kml_error_flags": (i32, [vp, C.POINTER(C.c_uint)]),
         "kml_get_dt": (i32, [vp, PD]),
+        "kml_timer_start": (i32, [vp]),
+        "kml_timer_stop": (i32, [vp, PD]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -238,6 +240,14 @@ class Engine:
         ln = (C.c_int64 * len(STAGES))()
         self._ckk(self.lib.kml_stage_times(self.ctx, ms, ln, 1 if reset else 0))
         return {s: (ms[i], ln[i]) for i, s in enumerate(STAGES)}
+
+    def timer_start(self):
+        self._ckk(self.lib.kml_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ckk(self.lib.kml_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
 
     def error_flags(self):
         f = C.c_uint()

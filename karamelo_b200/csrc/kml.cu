@@ -1,6 +1,7 @@
 // kml.cu - libkml.so: device state + the C ABI of include/kml.h on top of the sm_100a kernels.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a (see karamelo_b200/Makefile).
-#include "kml_kernels.cuh"
+#define KML_MISC_KERNELS
+#include "kml_launch.h"
 #include "kml_p2g_cell.cuh"
 
 #include <algorithm>
@@ -37,11 +38,12 @@ struct kml_ctx {
   double dt = 1e-16;
   unsigned *d_flags = nullptr; double *d_scratch = nullptr; // scratch: small reduction outputs
   double *h_pinned = nullptr;                                // pinned readback buffer
+  void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
   bool tl_mass_done = false;
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true;
   // profiling
-  bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
+  bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
 };
 
 namespace {
@@ -52,38 +54,51 @@ struct StageTimer {
     if (c->profile) { cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1); float t = 0; cudaEventElapsedTime(&t, c->ev0, c->ev1); c->ms[stage] += t; }
   }
 };
-inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 StepParams step_params(kml_ctx *c) {
   StepParams sp; sp.dt = c->dt; sp.alpha = c->c.PIC_FLIP;
   for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
   sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.flags = c->d_flags; return sp;
 }
 
-// kernel dispatch on (dimension, shape function, TL)
-#define KML_DISPATCH_SHAPE(DIMV, TLV, KERNEL, ...)                                                                         \
-  switch (c->c.shape_function) {                                                                                           \
-  case KML_SHAPE_LINEAR: KERNEL<DIMV, KML_SHAPE_LINEAR, TLV> __VA_ARGS__; break;                                           \
-  case KML_SHAPE_CUBIC_SPLINE: KERNEL<DIMV, KML_SHAPE_CUBIC_SPLINE, TLV> __VA_ARGS__; break;                               \
-  case KML_SHAPE_QUADRATIC_SPLINE: KERNEL<DIMV, KML_SHAPE_QUADRATIC_SPLINE, TLV> __VA_ARGS__; break;                       \
-  default: KERNEL<DIMV, KML_SHAPE_BERNSTEIN, TLV> __VA_ARGS__; break;                                                      \
-  }
-#define KML_DISPATCH(KERNEL, ...)                                                                                          \
+// kernel dispatch on (dimension, TL); the shape function is switched inside each launcher (kml_launch.h)
+#define KML_DISPATCH(FAMILY, ...)                                                                                          \
   do {                                                                                                                     \
+    const int sh_ = c->c.shape_function;                                                                                   \
     if (c->c.is_TL) {                                                                                                      \
-      if (c->c.dimension == 1) { KML_DISPATCH_SHAPE(1, true, KERNEL, __VA_ARGS__) }                                        \
-      else if (c->c.dimension == 2) { KML_DISPATCH_SHAPE(2, true, KERNEL, __VA_ARGS__) }                                   \
-      else { KML_DISPATCH_SHAPE(3, true, KERNEL, __VA_ARGS__) }                                                            \
+      if (c->c.dimension == 1) launch_##FAMILY##_d1_tl1(sh_, __VA_ARGS__);                                                 \
+      else if (c->c.dimension == 2) launch_##FAMILY##_d2_tl1(sh_, __VA_ARGS__);                                            \
+      else launch_##FAMILY##_d3_tl1(sh_, __VA_ARGS__);                                                                     \
     } else {                                                                                                               \
-      if (c->c.dimension == 1) { KML_DISPATCH_SHAPE(1, false, KERNEL, __VA_ARGS__) }                                       \
-      else if (c->c.dimension == 2) { KML_DISPATCH_SHAPE(2, false, KERNEL, __VA_ARGS__) }                                  \
-      else { KML_DISPATCH_SHAPE(3, false, KERNEL, __VA_ARGS__) }                                                           \
+      if (c->c.dimension == 1) launch_##FAMILY##_d1_tl0(sh_, __VA_ARGS__);                                                 \
+      else if (c->c.dimension == 2) launch_##FAMILY##_d2_tl0(sh_, __VA_ARGS__);                                            \
+      else launch_##FAMILY##_d3_tl0(sh_, __VA_ARGS__);                                                                     \
     }                                                                                                                      \
   } while (0)
+
+struct RowMap { double *comp[9]; int col[9]; int ncols, ncomp; };
+__global__ void k_rows_to_soa(const double *rows, RowMap rm, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < rm.ncomp; k++) rm.comp[k][i] = rows[i * rm.ncols + rm.col[k]];
+}
+__global__ void k_soa_to_rows(double *rows, RowMap rm, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < rm.ncomp; k++) rows[i * rm.ncols + rm.col[k]] = rm.comp[k][i];
+}
 
 int check_launch(const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
   return 0;
+}
+int stage_reserve(kml_ctx *c, size_t bytes) {
+  if (bytes <= c->stage_bytes) return 0;
+  if (c->d_stage) cudaFree(c->d_stage);
+  c->d_stage = nullptr; c->stage_bytes = 0;
+  cudaError_t e = cudaMalloc(&c->d_stage, bytes);
+  if (e != cudaSuccess) return fail(std::string("staging buffer: ") + cudaGetErrorString(e));
+  c->stage_bytes = bytes; return 0;
 }
 } // namespace
 
@@ -104,7 +119,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
   CU(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
   CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
-  CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
   memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
   const char *e = getenv("KML_P2G"); if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
   *out = c; return 0;
@@ -115,7 +130,7 @@ int kml_destroy(kml_ctx *c) {
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
   for (auto s : c->solids) { cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
-  cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned);
+  cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
   delete c; return 0;
 }
@@ -297,19 +312,16 @@ int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   if (field == KML_P_MBP) S->mbp_nonzero = true;
   double *comp[9]; int nc; bool sym;
   if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
-  std::vector<double> tmp(np); const double *s = (const double *)src;
-  if (sym) {
-    static const int RM_OF_SYM[6] = {0, 4, 8, 1, 2, 5};
-    for (int k = 0; k < 6; k++) {
-      for (long long i = 0; i < np; i++) tmp[i] = s[i * 9 + RM_OF_SYM[k]];
-      CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
-    }
-    return 0;
-  }
-  for (int k = 0; k < nc; k++) {
-    for (long long i = 0; i < np; i++) tmp[i] = s[i * nc + k];
-    CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
-  }
+  // rows [np][ncols] on the host -> SoA components on the device: one H2D copy + a transposition kernel
+  const int ncols = sym ? 9 : nc;
+  if (stage_reserve(c, sizeof(double) * np * ncols)) return 1;
+  CU(cudaMemcpyAsync(c->d_stage, src, sizeof(double) * np * ncols, cudaMemcpyHostToDevice, c->stream));
+  RowMap rm; rm.ncols = ncols; rm.ncomp = nc;
+  static const int RM_OF_SYM[6] = {0, 4, 8, 1, 2, 5};
+  for (int k = 0; k < nc; k++) { rm.comp[k] = comp[k]; rm.col[k] = sym ? RM_OF_SYM[k] : k; }
+  k_rows_to_soa<<<nblocks(np, 256), 256, 0, c->stream>>>((const double *)c->d_stage, rm, np);
+  if (check_launch("k_rows_to_soa")) return 1;
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -330,18 +342,14 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
   }
   double *comp[9]; int nc; bool sym;
   if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
-  std::vector<double> tmp(np); double *o = (double *)dst;
-  if (sym) {
-    std::vector<double> six(6 * np);
-    for (int k = 0; k < 6; k++) { CU(cudaMemcpyAsync(&six[k * np], comp[k], sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream)); }
-    CU(cudaStreamSynchronize(c->stream));
-    for (long long i = 0; i < np; i++) for (int e = 0; e < 9; e++) o[i * 9 + e] = six[SYM_OF[e] * np + i];
-    return 0;
-  }
-  for (int k = 0; k < nc; k++) {
-    CU(cudaMemcpyAsync(tmp.data(), comp[k], sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
-    for (long long i = 0; i < np; i++) o[i * nc + k] = tmp[i];
-  }
+  const int ncols = sym ? 9 : nc;
+  if (stage_reserve(c, sizeof(double) * np * ncols)) return 1;
+  RowMap rm; rm.ncols = ncols; rm.ncomp = ncols;
+  for (int k = 0; k < ncols; k++) { rm.comp[k] = comp[sym ? SYM_OF[k] : k]; rm.col[k] = k; }
+  k_soa_to_rows<<<nblocks(np, 256), 256, 0, c->stream>>>((double *)c->d_stage, rm, np);
+  if (check_launch("k_soa_to_rows")) return 1;
+  CU(cudaMemcpyAsync(dst, c->d_stage, sizeof(double) * np * ncols, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -418,7 +426,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
       c->launches[stage] += nl; done = true;
     }
     if (!done) {
-      KML_DISPATCH(k_p2g, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, g, sp, what));
+      KML_DISPATCH(p2g, S->s, g, sp, what, c->stream);
       c->launches[stage]++;
     }
     if (check_launch("k_p2g")) return 1;
@@ -471,7 +479,7 @@ int kml_advance_particles(kml_ctx *c) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
-    KML_DISPATCH(k_g2p, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, sp));
+    KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
     c->launches[KML_STAGE_G2P]++;
     if (check_launch("k_g2p")) return 1;
     if (!c->c.is_TL) S->moved = true;
@@ -522,7 +530,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     if (grid_normalize_if_needed(c, G)) return 1;
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
-    KML_DISPATCH(k_stress, <<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, sp, tp, S->d.mat));
+    KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);
     c->launches[KML_STAGE_STRESS]++;
     if (check_launch("k_stress")) return 1;
   }
@@ -643,6 +651,11 @@ int kml_comm_unique_id(void *) { return fail("kml: multi-GPU communicator not bu
 int kml_comm_init(kml_ctx *, const void *) { return fail("kml: multi-GPU communicator not built into this library version"); }
 
 int kml_profile(kml_ctx *c, int enable) { c->profile = enable != 0; return 0; }
+int kml_timer_start(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaEventRecord(c->evA, c->stream)); return 0; }
+int kml_timer_stop(kml_ctx *c, double *ms) {
+  CU(cudaSetDevice(c->dev)); CU(cudaEventRecord(c->evB, c->stream)); CU(cudaEventSynchronize(c->evB));
+  float t = 0; CU(cudaEventElapsedTime(&t, c->evA, c->evB)); *ms = t; return 0;
+}
 int kml_stage_times(kml_ctx *c, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset) {
   for (int i = 0; i < KML_STAGE_COUNT; i++) { ms[i] = c->ms[i]; launches[i] = c->launches[i]; }
   if (reset) { memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches); }

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   })
 }
 
+#ifdef KML_MISC_KERNELS  // non-template kernels: compiled once, in kml.cu
 // ---- grid kernels ----------------------------------------------------------------------------
 // normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
 // Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
@@ -159,6 +160,8 @@ __global__ void k_grid_positions(GridDev g, double dt) {
 #pragma unroll
   for (int d = 0; d < 3; d++) g.x[d][i] += dt * g.v[d][i];
 }
+
+#endif // KML_MISC_KERNELS
 
 // ---- G2P + advance ---------------------------------------------------------------------------
 // Solid::compute_particle_accelerations_velocities_and_positions src/solid.cpp:576-635 fused with
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
   if ((threadIdx.x & 31) == 0) { if (wave > 0) atomic_max_pos(tp.max_wave, wave); if (TL && hr < 1.0) atomic_min_pos(tp.min_h_ratio, hr < 0 ? 0.0 : hr); }
 }
 
+#ifdef KML_MISC_KERNELS
 // ---- fixes -----------------------------------------------------------------------------------
 // FixVelocityNodes, src/fix_velocity_nodes.cpp:130-268
 __global__ void k_fix_velocity_nodes(GridDev g, int groupbit, int set_mask, double v0, double v1, double v2, double p0, double p1, double p2,
@@ -526,5 +530,7 @@ __global__ void k_energy(SolidDev s, int groupbit, int kinetic, double *out) {
   for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
   if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(out, e);
 }
+
+#endif // KML_MISC_KERNELS
 
 } // namespace kml
