@@ -422,8 +422,9 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (!TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      if (cell_p2g_launch(S->s, g, G->cl, what, c->stream, &nl)) return fail("cell p2g launch failed");
-      c->launches[stage] += nl; done = true;
+      const int rc = cell_p2g_launch(S->s, g, G->cl, what, c->stream, &nl); // -1: combination not covered -> atomic kernel
+      if (rc > 0) return fail("cell p2g launch failed");
+      if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
     if (!done) {
       KML_DISPATCH(p2g, S->s, g, sp, what, c->stream);

@@ -87,7 +87,12 @@ dt_factor(0.25)
 
 
 # C3: examples/Tensile_with_damage/Bernstein - TLMPM, Bernstein quadratic, JC strength + JC damage,
-# optionally plastic-work heating.  Grip velocity raised so that yield and damage occur within 100 steps.
+# optionally plastic-work heating.  Grip velocity raised and the JC failure strain lowered so that yield and
+# damage (up to fully failed particles) occur within 100 steps.  The case is deliberately kept well conditioned:
+# an earlier variant (artificial viscosity Q2 = 1.5, above the explicit stability limit) made the REFERENCE itself
+# amplify a 1e-15 perturbation to 1e-5 in 100 steps, which no 1e-10 parity test can survive; this one amplifies
+# it to ~1e-11 (measured with the oracle).  The oblique impact of C4 exists for the same reason: in a head-on
+# collision the Coulomb friction direction v_t/|v_t| is rounding noise.
 def tensile(thermal=False, shape="Bernstein-quadratic", vgrip=40):
     method = f"method(tlmpm, FLIP, {shape}, FLIP" + (", thermo-mechanical)" if thermal else ")")
     tmat = "temperature(tpw, plastic_work, 0.9, 452e+6, 50, 0, Tr, Tm)\n" if thermal else ""
@@ -112,15 +117,15 @@ cellsize = 0.8
 dimension(3, -2*hLx, 2*hLx, -2*hLy, 2*hLy, -2*hLz, 2*hLz, cellsize)
 region(box, block, -hLx, hLx, -hLy, hLy, -hLz, hLz)
 Q1 = 0.06
-Q2 = 1.5
+Q2 = 0.1
 Tr = 25
 Tm = 1000
 cv = 0
 Gamma = 0
 eos(eoss,   shock, rho, K, c0, S, Gamma, cv, Tr, Q1, Q2)
 strength(strengthjc, johnson_cook, G, sigmay, B, n, 1, 0.01, 0, Tr, Tm)
-d1 = 0.0636
-d2 = 0.1936
+d1 = 0.0382
+d2 = 0.1162
 d3 = -2.969
 d4 = 0
 d5 = 0
@@ -165,8 +170,8 @@ solid(sBall2, region, rBall2, ppc1d, mat1, cellsize,0)
 group(gBall1, particles, region, rBall1, solid, sBall1)
 group(gBall2, particles, region, rBall2, solid, sBall2)
 v = {v}
-fix(v0Ball1, initial_velocity_particles, gBall1, v, v, NULL)
-fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, NULL)
+fix(v0Ball1, initial_velocity_particles, gBall1, v, 0.2*v, NULL)
+fix(v0Ball2, initial_velocity_particles, gBall2, -v, -0.3*v, NULL)
 {fix}
 set_dt(0.001)
 """
