@@ -138,7 +138,7 @@ int kml_synchronize(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaStreamSynchr
 int kml_set_domain_box(kml_ctx *c, const double lo[3], const double hi[3]) { for (int d = 0; d < 3; d++) { c->c.boxlo[d] = lo[d]; c->c.boxhi[d] = hi[d]; } return 0; }
 
 // ---- grids ------------------------------------------------------------------------------------
-static const int GRID_NDBL = 1 + 3 + 3 + 3 + 3 + 4 + 3; // mass v vu f mb T Tu Qext Qint x
+static const int GRID_NDBL = 4 + 4 + 3 + 3 + 3 + 3; // nv(4) nvu(4) f mb T Qext Qint x
 
 int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   CU(cudaSetDevice(c->dev));
@@ -149,10 +149,10 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   const long long nn = g.nn, stride = (nn + 31) / 32 * 32;
   CU(cudaMalloc(&G->buf, sizeof(double) * stride * GRID_NDBL)); CU(cudaMemsetAsync(G->buf, 0, sizeof(double) * stride * GRID_NDBL, c->stream));
   CU(cudaMalloc(&G->ibuf, sizeof(int) * stride * 2));
-  double *p = G->buf; auto take = [&]() { double *r = p; p += stride; return r; };
-  g.mass = take(); for (int k = 0; k < 3; k++) g.v[k] = take(); for (int k = 0; k < 3; k++) g.vu[k] = take();
+  double *p = G->buf; auto take = [&](int n = 1) { double *r = p; p += stride * n; return r; };
+  g.nv = (double4 *)take(4); g.nvu = (double4 *)take(4);
   for (int k = 0; k < 3; k++) g.f[k] = take(); for (int k = 0; k < 3; k++) g.mb[k] = take();
-  g.T = take(); g.Tu = take(); g.Qext = take(); g.Qint = take(); for (int k = 0; k < 3; k++) g.x[k] = take();
+  g.T = take(); g.Qext = take(); g.Qint = take(); for (int k = 0; k < 3; k++) g.x[k] = take();
   g.mask = G->ibuf; g.rigid = G->ibuf + stride;
   std::vector<int> ones(nn, 1);
   CU(cudaMemcpyAsync(g.mask, ones.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream));
@@ -179,16 +179,19 @@ static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
   return check_launch("k_grid_update(normalize)");
 }
 
-static int grid_field(kml_ctx *c, Grid *G, int field, double **comp, int *ncomp, int **icomp) {
-  GridDev &g = G->g; *icomp = nullptr; *ncomp = 1;
+// component pointers + element stride (in doubles) of a node field
+static int grid_field(kml_ctx *c, Grid *G, int field, double **comp, int *ncomp, int *stride, int **icomp) {
+  GridDev &g = G->g; *icomp = nullptr; *ncomp = 1; *stride = 1;
+  double *nv = (double *)g.nv, *nvu = (double *)g.nvu;
   switch (field) {
   case KML_N_X: for (int k = 0; k < 3; k++) comp[k] = g.x[k]; *ncomp = 3; break;
-  case KML_N_V: for (int k = 0; k < 3; k++) comp[k] = g.v[k]; *ncomp = 3; break;
-  case KML_N_V_UPDATE: for (int k = 0; k < 3; k++) comp[k] = g.vu[k]; *ncomp = 3; break;
+  case KML_N_V: for (int k = 0; k < 3; k++) comp[k] = nv + k; *ncomp = 3; *stride = 4; break;
+  case KML_N_V_UPDATE: for (int k = 0; k < 3; k++) comp[k] = nvu + k; *ncomp = 3; *stride = 4; break;
   case KML_N_MB: for (int k = 0; k < 3; k++) comp[k] = g.mb[k]; *ncomp = 3; break;
   case KML_N_F: for (int k = 0; k < 3; k++) comp[k] = g.f[k]; *ncomp = 3; break;
-  case KML_N_MASS: comp[0] = g.mass; break;
-  case KML_N_T: comp[0] = g.T; break; case KML_N_T_UPDATE: comp[0] = g.Tu; break;
+  case KML_N_MASS: comp[0] = nv + 3; *stride = 4; break;
+  case KML_N_T: comp[0] = g.T; break;
+  case KML_N_T_UPDATE: comp[0] = nvu + 3; *stride = 4; break;
   case KML_N_QEXT: comp[0] = g.Qext; break; case KML_N_QINT: comp[0] = g.Qint; break;
   case KML_N_MASK: *icomp = g.mask; break; case KML_N_RIGID: *icomp = g.rigid; break;
   default: return fail("grid field not supported");
@@ -199,16 +202,16 @@ static int grid_field(kml_ctx *c, Grid *G, int field, double **comp, int *ncomp,
 int kml_grid_upload(kml_ctx *c, int gid, int field, const void *src) {
   CU(cudaSetDevice(c->dev));
   Grid *G = c->grids[gid]; const long long nn = G->g.nn;
-  double *comp[3]; int nc; int *ic;
-  if (grid_field(c, G, field, comp, &nc, &ic)) return 1;
+  double *comp[3]; int nc, stride; int *ic;
+  if (grid_field(c, G, field, comp, &nc, &stride, &ic)) return 1;
   if (ic) { CU(cudaMemcpyAsync(ic, src, sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_N_V) G->v_is_momentum = false;
   if (field == KML_N_T) G->T_is_weighted = false;
-  std::vector<double> tmp(nn); const double *s = (const double *)src;
-  for (int k = 0; k < nc; k++) {
-    for (long long i = 0; i < nn; i++) tmp[i] = s[i * nc + k];
-    CU(cudaMemcpyAsync(comp[k], tmp.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  const double *s = (const double *)src;
+  for (int k = 0; k < nc; k++) { // strided 2-D copy: host column k of [nn][nc] -> device component
+    CU(cudaMemcpy2DAsync(comp[k], sizeof(double) * stride, s + k, sizeof(double) * nc, sizeof(double), nn, cudaMemcpyHostToDevice, c->stream));
   }
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 int kml_grid_download(kml_ctx *c, int gid, int field, void *dst) {
@@ -231,14 +234,13 @@ int kml_grid_download(kml_ctx *c, int gid, int field, void *dst) {
     return 0;
   }
   if (field == KML_N_V || field == KML_N_T) if (grid_normalize_if_needed(c, G)) return 1;
-  double *comp[3]; int nc; int *ic;
-  if (grid_field(c, G, field, comp, &nc, &ic)) return 1;
+  double *comp[3]; int nc, stride; int *ic;
+  if (grid_field(c, G, field, comp, &nc, &stride, &ic)) return 1;
   if (ic) { CU(cudaMemcpyAsync(dst, ic, sizeof(int) * nn, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
-  std::vector<double> tmp(nn); double *o = (double *)dst;
-  for (int k = 0; k < nc; k++) {
-    CU(cudaMemcpyAsync(tmp.data(), comp[k], sizeof(double) * nn, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
-    for (long long i = 0; i < nn; i++) o[i * nc + k] = tmp[i];
-  }
+  double *o = (double *)dst;
+  for (int k = 0; k < nc; k++)
+    CU(cudaMemcpy2DAsync(o + k, sizeof(double) * nc, comp[k], sizeof(double) * stride, sizeof(double), nn, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -411,8 +413,9 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if ((what & P2G_MB) && !S->mbp_nonzero) what &= ~P2G_MB;
     const size_t nb = sizeof(double) * g.nn;
     if (reset) {
-      if (what & P2G_MASS) CU(cudaMemsetAsync(g.mass, 0, nb, c->stream));
-      if (what & P2G_MOM) for (int k = 0; k < 3; k++) CU(cudaMemsetAsync(g.v[k], 0, nb, c->stream));
+      if ((what & P2G_MASS) && (what & P2G_MOM)) CU(cudaMemsetAsync(g.nv, 0, sizeof(double4) * g.nn, c->stream));
+      else if (what & P2G_MOM) { k_grid_zero_v<<<nblocks(g.nn, 256), 256, 0, c->stream>>>(g, 0); c->launches[stage]++; }
+      else if (what & P2G_MASS) return fail("mass-only P2G pass is not used by any scheme");
       if (what_in & P2G_FORCE) for (int k = 0; k < 3; k++) { CU(cudaMemsetAsync(g.f[k], 0, nb, c->stream)); CU(cudaMemsetAsync(g.mb[k], 0, nb, c->stream)); }
       if (what & P2G_TEMP) CU(cudaMemsetAsync(g.T, 0, nb, c->stream));
       if (what & P2G_HEAT) { CU(cudaMemsetAsync(g.Qext, 0, nb, c->stream)); CU(cudaMemsetAsync(g.Qint, 0, nb, c->stream)); }

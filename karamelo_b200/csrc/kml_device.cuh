@@ -97,11 +97,21 @@ template <> struct Basis<KML_SHAPE_BERNSTEIN> {
 struct GridDev {
   double lo[3]; double h; double inv_cellsize; double cellsize;
   int n[3]; long long nn;
-  // node SoA
-  double *mass; double *v[3]; double *vu[3]; double *f[3]; double *mb[3];
-  double *T, *Tu, *Qext, *Qint; double *x[3];
+  // Node records read by the gather kernels are 32-byte AoS so that one LDG.128 pair fetches a node:
+  //   nv  = {vx, vy, vz, mass}      (momentum until the grid kernel divides by the mass)
+  //   nvu = {vux, vuy, vuz, T_update}
+  // The scatter-only quantities stay SoA.
+  double4 *nv, *nvu;
+  double *f[3]; double *mb[3];
+  double *T, *Qext, *Qint; double *x[3];
   int *mask; int *rigid;
 };
+__device__ __forceinline__ double4 ldg4(const double4 *p) { // read-only path, two LDG.128
+  const double2 lo = __ldg((const double2 *)p), hi = __ldg((const double2 *)p + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ double &comp(double4 &r, int d) { return d == 0 ? r.x : (d == 1 ? r.y : r.z); }
+__device__ __forceinline__ double *comp_ptr(double4 *r, int d) { return d == 0 ? &r->x : (d == 1 ? &r->y : &r->z); }
 
 // ntype per axis, src/grid.cpp:229-240
 template <int SHAPE> __device__ __forceinline__ int node_type(int i, int n) {

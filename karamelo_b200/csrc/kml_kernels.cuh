@@ -103,12 +103,12 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   if (what & P2G_HEAT) { gam = s.gamma[ip]; qv[0] = s.q[0][ip]; qv[1] = s.q[1][ip]; qv[2] = s.q[2][ip]; }
 
   KML_FOR_STENCIL(st, g, {
-    if (what & P2G_MASS) atomicAdd(&g.mass[node], wf * m);
+    if (what & P2G_MASS) atomicAdd(&g.nv[node].w, wf * m);
     if (what & P2G_MOM) {
       const double wm = wf * m;
-      atomicAdd(&g.v[0][node], wm * mv[0]);
-      if (DIM >= 2) atomicAdd(&g.v[1][node], wm * mv[1]);
-      if (DIM == 3) atomicAdd(&g.v[2][node], wm * mv[2]);
+      atomicAdd(&g.nv[node].x, wm * mv[0]);
+      if (DIM >= 2) atomicAdd(&g.nv[node].y, wm * mv[1]);
+      if (DIM == 3) atomicAdd(&g.nv[node].z, wm * mv[2]);
     }
     if (what & P2G_FORCE) {
       double f0 = -(A[0] * wfd0 + A[1] * wfd1 + A[2] * wfd2);
@@ -137,19 +137,24 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
 __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
-  const double m = g.mass[i];
-  double v[3];
+  double4 rec = g.nv[i];
+  const double m = rec.w;
+  double v[3] = {rec.x, rec.y, rec.z};
+  if (normalize) {
 #pragma unroll
-  for (int d = 0; d < 3; d++) {
-    v[d] = g.v[d][i];
-    if (normalize) { v[d] = (m > 0) ? v[d] / m : 0.0; g.v[d][i] = v[d]; }
+    for (int d = 0; d < 3; d++) v[d] = (m > 0) ? v[d] / m : 0.0;
+    rec.x = v[0]; rec.y = v[1]; rec.z = v[2];
+    g.nv[i] = rec;
   }
   double T = 0;
   if (temp) { T = g.T[i]; if (normalize_T) { T = (m > 0) ? T / m : 0.0; g.T[i] = T; } }
   if (update) {
-#pragma unroll
-    for (int d = 0; d < 3; d++) g.vu[d][i] = (m != 0) ? v[d] + dt * (g.f[d][i] + g.mb[d][i]) / m : v[d];
-    if (temp) g.Tu[i] = (m != 0) ? T + dt * (g.Qint[i] + g.Qext[i]) / m : T;
+    double4 u;
+    u.x = (m != 0) ? v[0] + dt * (g.f[0][i] + g.mb[0][i]) / m : v[0];
+    u.y = (m != 0) ? v[1] + dt * (g.f[1][i] + g.mb[1][i]) / m : v[1];
+    u.z = (m != 0) ? v[2] + dt * (g.f[2][i] + g.mb[2][i]) / m : v[2];
+    u.w = temp ? ((m != 0) ? T + dt * (g.Qint[i] + g.Qext[i]) / m : T) : 0.0;
+    g.nvu[i] = u;
   }
 }
 
@@ -157,8 +162,18 @@ __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, i
 __global__ void k_grid_positions(GridDev g, double dt) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
-#pragma unroll
-  for (int d = 0; d < 3; d++) g.x[d][i] += dt * g.v[d][i];
+  const double4 rec = g.nv[i];
+  g.x[0][i] += dt * rec.x; g.x[1][i] += dt * rec.y; g.x[2][i] += dt * rec.z;
+}
+
+// zero the velocity (momentum) part of the node records, keeping the mass (MUSL re-projection, TL passes)
+__global__ void k_grid_zero_v(GridDev g, int zero_mass) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nn) return;
+  double4 rec = g.nv[i];
+  rec.x = rec.y = rec.z = 0.0;
+  if (zero_mass) rec.w = 0.0;
+  g.nv[i] = rec;
 }
 
 #endif // KML_MISC_KERNELS
@@ -174,13 +189,12 @@ __global__ void __launch_bounds__(128) k_g2p(SolidDev s, GridDev g, StepParams s
   Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
   double vu[3] = {0, 0, 0}, a[3] = {0, 0, 0}, Tp = 0;
   KML_FOR_STENCIL(st, g, {
-#pragma unroll
-    for (int d = 0; d < DIM; d++) {
-      const double gvu = g.vu[d][node];
-      vu[d] += wf * gvu;
-      a[d] += wf * (gvu - g.v[d][node]);
-    }
-    if (sp.temp) Tp += wf * g.Tu[node];
+    const double4 ru = ldg4(&g.nvu[node]);
+    const double4 rv = ldg4(&g.nv[node]);
+    vu[0] += wf * ru.x; a[0] += wf * (ru.x - rv.x);
+    if (DIM >= 2) { vu[1] += wf * ru.y; a[1] += wf * (ru.y - rv.y); }
+    if (DIM == 3) { vu[2] += wf * ru.z; a[2] += wf * (ru.z - rv.z); }
+    if (sp.temp) Tp += wf * ru.w;
     (void)wfd0; (void)wfd1; (void)wfd2;
   })
   const double inv_dt = 1.0 / sp.dt;
@@ -218,20 +232,20 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
   if (ip < s.np) {
     const double px = TL ? s.x0[0][ip] : s.x[0][ip], py = TL ? s.x0[1][ip] : s.x[1][ip], pz = TL ? s.x0[2][ip] : s.x[2][ip];
     Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
-    double *const *gv = tp.doublemapping ? g.v : g.vu;
-    const double *gT = tp.doublemapping ? g.T : g.Tu;
+    const double4 *__restrict__ gv = tp.doublemapping ? g.nv : g.nvu;
     double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hoop = 0, qv[3] = {0, 0, 0};
     KML_FOR_STENCIL(st, g, {
       const double wfd[3] = {wfd0, wfd1, wfd2};
+      const double4 rec = ldg4(&gv[node]);
+      const double vn[3] = {rec.x, rec.y, rec.z};
 #pragma unroll
       for (int a = 0; a < DIM; a++) {
-        const double va = gv[a][node];
 #pragma unroll
-        for (int b = 0; b < DIM; b++) L[3 * a + b] += va * wfd[b];
-        if (a == 0 && DIM == 2 && sp.axisymmetric) hoop += va * wf;
+        for (int b = 0; b < DIM; b++) L[3 * a + b] += vn[a] * wfd[b];
       }
+      if (DIM == 2 && sp.axisymmetric) hoop += vn[0] * wf;
       if (sp.temp) {
-        const double Tn = gT[node];
+        const double Tn = tp.doublemapping ? g.T[node] : rec.w;
 #pragma unroll
         for (int b = 0; b < 3; b++) qv[b] -= wfd[b] * Tn;
       }
@@ -384,14 +398,18 @@ __global__ void k_fix_velocity_nodes(GridDev g, int groupbit, int set_mask, doub
   double f[3] = {0, 0, 0};
   if (i < g.nn && (g.mask[i] & groupbit)) {
     const double v[3] = {v0, v1, v2}, p[3] = {p0, p1, p2};
+    double4 rv = g.nv[i];
     if (which == 0) {
-      const double c = inv_dt * g.mass[i];
+      double4 ru = g.nvu[i];
+      const double c = inv_dt * rv.w;
 #pragma unroll
-      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = c * (v[d] - g.vu[d][i]); g.vu[d][i] = v[d]; g.v[d][i] = p[d]; }
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = c * (v[d] - comp(ru, d)); comp(ru, d) = v[d]; comp(rv, d) = p[d]; }
+      g.nvu[i] = ru;
     } else {
 #pragma unroll
-      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) g.v[d][i] = v[d];
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) comp(rv, d) = v[d];
     }
+    g.nv[i] = rv;
   }
   if (which == 0) {
 #pragma unroll
@@ -408,7 +426,7 @@ __global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double f[3] = {0, 0, 0};
   if (i < g.nn) {
-    const double m = g.mass[i];
+    const double m = g.nv[i].w;
     if (m > 0 && (g.mask[i] & groupbit)) {
       const double fv[3] = {f0, f1, f2};
 #pragma unroll

@@ -90,117 +90,145 @@ __device__ __forceinline__ void cubic_node(double xp, double lo, double h, doubl
 // FULL: mass + momentum + internal force (7 sums per node); !FULL: momentum only (MUSL re-projection)
 template <bool FULL> struct CellAcc { static constexpr int Q = FULL ? 7 : 3; };
 
+// Staged particle record in shared memory (doubles), written once per particle by the staging lanes:
+//   [0..7]   x axis: (w0,dw0, w1,dw1, w2,dw2, w3,dw3)      [8..15] y axis likewise
+//   [16..23] z axis: (w0,w1,w2,w3, dw0,dw1,dw2,dw3)
+//   [24..27] m, m*vx, m*vy, m*vz                             [28..33] vol*sigma (xx,yy,zz,xy,xz,yz)
+constexpr int CELL_REC = 36;                       // padded to a multiple of 2 doubles (LDS.128 alignment)
+constexpr int CELL_CHUNK = 8;                      // particles staged per round
+constexpr int CELL_GROUP_STRIDE = CELL_REC * CELL_CHUNK + 2; // +16 B: the two half-warps of a warp use different banks
+constexpr int CELL_GROUPS_PER_BLOCK = 8;           // 128 threads = 8 groups of 16 lanes
+
+// A group of 16 lanes (a,b) owns one column segment of cells; lane (a,b) accumulates the 4 nodes (i0+a, j0+b, k..k+3).
 template <bool FULL, bool MASS>
-__global__ void __launch_bounds__(128) k_p2g_cell(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
+__global__ void __launch_bounds__(128, 4) k_p2g_cell(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
   constexpr int Q = CellAcc<FULL>::Q;
+  __shared__ __align__(16) double stage[CELL_GROUPS_PER_BLOCK * CELL_GROUP_STRIDE];
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long group = gid >> 3;
-  const int lane8 = (int)(gid & 7), a = lane8 >> 1, b0 = (lane8 & 1) * 2;
+  const long long group = gid >> 4;
+  const int lane16 = threadIdx.x & 15, a = lane16 >> 2, b = lane16 & 3;
+  const unsigned halfmask = 0xFFFFu << (threadIdx.x & 16);
+  double *rec0 = stage + (threadIdx.x >> 4) * CELL_GROUP_STRIDE;
   const long long ncol = (long long)g.n[0] * g.n[1];
   const long long col = group / nseg; const int seg = (int)(group % nseg);
   if (col >= ncol) return;
   const int i0 = (int)(col / g.n[1]), j0 = (int)(col % g.n[1]);
   const int kbeg = seg * seglen, kend = min(kbeg + seglen, g.n[2]);
   if (kbeg >= kend) return;
-  const int ni = i0 + a;                       // this lane's node row
-  const bool row_ok = ni < g.n[0];
+  const int ni = i0 + a, nj = j0 + b;
+  const bool col_ok = ni < g.n[0] && nj < g.n[1];
   const long long cellbase = col * g.n[2];
-  // quick exit: no particle in the whole segment
-  if (start[cellbase + kend] == start[cellbase + kbeg]) return;
+  if (start[cellbase + kend] == start[cellbase + kbeg]) return; // no particle in the whole segment (uniform per group)
 
-  double acc[2][4][Q];
+  double acc[4][Q];
 #pragma unroll
-  for (int b = 0; b < 2; b++)
+  for (int c = 0; c < 4; c++)
 #pragma unroll
-    for (int c = 0; c < 4; c++)
-#pragma unroll
-      for (int q = 0; q < Q; q++) acc[b][c][q] = 0.0;
+    for (int q = 0; q < Q; q++) acc[c][q] = 0.0;
 
-  // add plane `slot` (node plane kk) to the grid and clear it
-  auto emit = [&](int slot, int kk) {
-    if (row_ok && kk < g.n[2]) {
+  auto emit = [&](int slot, int kk) { // add node plane kk (register slot `slot`) to the grid and clear it
+    if (col_ok && kk < g.n[2]) {
+      const long long node = ((long long)ni * g.n[1] + nj) * g.n[2] + kk;
+      double4 *rec = &g.nv[node];
+      if (FULL) {
+        if (MASS && acc[slot][0] != 0.0) atomicAdd(&rec->w, acc[slot][0]);
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
-        const int nj = j0 + b0 + b;
-        if (nj < g.n[1]) {
-          const long long node = ((long long)ni * g.n[1] + nj) * g.n[2] + kk;
-          if (FULL) {
-            if (MASS && acc[b][slot][0] != 0.0) atomicAdd(&g.mass[node], acc[b][slot][0]);
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-              if (acc[b][slot][1 + d] != 0.0) atomicAdd(&g.v[d][node], acc[b][slot][1 + d]);
-              if (acc[b][slot][4 + d] != 0.0) atomicAdd(&g.f[d][node], acc[b][slot][4 + d]);
-            }
-          } else {
-#pragma unroll
-            for (int d = 0; d < 3; d++) if (acc[b][slot][d] != 0.0) atomicAdd(&g.v[d][node], acc[b][slot][d]);
-          }
+        for (int d = 0; d < 3; d++) {
+          if (acc[slot][1 + d] != 0.0) atomicAdd(comp_ptr(rec, d), acc[slot][1 + d]);
+          if (acc[slot][4 + d] != 0.0) atomicAdd(&g.f[d][node], acc[slot][4 + d]);
         }
+      } else {
+#pragma unroll
+        for (int d = 0; d < 3; d++) if (acc[slot][d] != 0.0) atomicAdd(comp_ptr(rec, d), acc[slot][d]);
       }
     }
 #pragma unroll
-    for (int b = 0; b < 2; b++)
-#pragma unroll
-      for (int q = 0; q < Q; q++) acc[b][slot][q] = 0.0;
+    for (int q = 0; q < Q; q++) acc[slot][q] = 0.0;
   };
 
-  // process cell kk with plane c living in register slot (c + R) & 3
-#define KML_CELL_STEP(R)                                                                                         \
-  {                                                                                                              \
-    const int kk = k + R;                                                                                        \
-    if (kk < kend) {                                                                                             \
-      const int pbeg = start[cellbase + kk], pend = start[cellbase + kk + 1];                                    \
-      for (int p = pbeg; p < pend; p++) {                                                                        \
-        const int ip = order[p];                                                                                 \
-        const double px = s.x[0][ip], py = s.x[1][ip], pz = s.x[2][ip];                                          \
-        double wx, dwx, wy[2], dwy[2], wz[4], dwz[4];                                                            \
-        cubic_node(px, g.lo[0], g.h, g.inv_cellsize, ni, g.n[0], wx, dwx);                                       \
-        _Pragma("unroll") for (int b = 0; b < 2; b++) cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + b0 + b, g.n[1], wy[b], dwy[b]); \
-        _Pragma("unroll") for (int c = 0; c < 4; c++) cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kk + c, g.n[2], wz[c], dwz[c]);     \
-        const double m = s.mass[ip];                                                                             \
-        const double v0 = s.v[0][ip], v1 = s.v[1][ip], v2 = s.v[2][ip];                                          \
-        double A[9];                                                                                             \
-        if (FULL) {                                                                                              \
-          load_sym(s.sig, ip, A);                                                                                \
-          const double vol = s.vol[ip];                                                                          \
-          _Pragma("unroll") for (int e = 0; e < 9; e++) A[e] *= vol;                                             \
-        }                                                                                                        \
-        _Pragma("unroll") for (int b = 0; b < 2; b++) {                                                          \
-          const double gxy = wx * wy[b];                                                                         \
-          const double mm = gxy * m;                                                                             \
-          const double M0 = mm * v0, M1 = mm * v1, M2 = mm * v2;                                                 \
-          double P0 = 0, P1 = 0, P2 = 0, Q0 = 0, Q1 = 0, Q2 = 0;                                                 \
-          if (FULL) {                                                                                            \
-            const double gx = dwx * wy[b], gy = wx * dwy[b];                                                     \
-            P0 = -(A[0] * gx + A[1] * gy); P1 = -(A[3] * gx + A[4] * gy); P2 = -(A[6] * gx + A[7] * gy);         \
-            Q0 = -(A[2] * gxy); Q1 = -(A[5] * gxy); Q2 = -(A[8] * gxy);                                          \
-          }                                                                                                      \
-          _Pragma("unroll") for (int c = 0; c < 4; c++) {                                                        \
-            double *ac = acc[b][(c + R) & 3];                                                                    \
-            if (FULL) {                                                                                          \
-              ac[0] += mm * wz[c];                                                                               \
-              ac[1] += M0 * wz[c]; ac[2] += M1 * wz[c]; ac[3] += M2 * wz[c];                                     \
-              ac[4] += P0 * wz[c] + Q0 * dwz[c]; ac[5] += P1 * wz[c] + Q1 * dwz[c]; ac[6] += P2 * wz[c] + Q2 * dwz[c]; \
-            } else {                                                                                             \
-              ac[0] += M0 * wz[c]; ac[1] += M1 * wz[c]; ac[2] += M2 * wz[c];                                     \
-            }                                                                                                    \
-          }                                                                                                      \
-        }                                                                                                        \
-      }                                                                                                          \
-      emit(R, kk);                                                                                               \
-    }                                                                                                            \
+  // stage up to CELL_CHUNK particles [pbeg, pbeg+n) of cell kk: lanes 0-7 evaluate the 12 (w,dw) pairs and m*v of
+  // one particle each, lanes 8-15 its vol*sigma
+  auto stage_chunk = [&](int pbeg, int n, int kk) {
+    const int q = lane16 & 7;
+    if (q < n) {
+      const int ip = order[pbeg + q];
+      double *r = rec0 + q * CELL_REC;
+      if (lane16 < 8) {
+        const double px = s.x[0][ip], py = s.x[1][ip], pz = s.x[2][ip];
+        const double m = s.mass[ip];
+        const double v0 = s.v[0][ip], v1 = s.v[1][ip], v2 = s.v[2][ip];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          double w, dw;
+          cubic_node(px, g.lo[0], g.h, g.inv_cellsize, i0 + t, g.n[0], w, dw); r[2 * t] = w; r[2 * t + 1] = dw;
+          cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + t, g.n[1], w, dw); r[8 + 2 * t] = w; r[8 + 2 * t + 1] = dw;
+          cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kk + t, g.n[2], w, dw); r[16 + t] = w; r[20 + t] = dw;
+        }
+        r[24] = m; r[25] = m * v0; r[26] = m * v1; r[27] = m * v2;
+      } else if (FULL) {
+        const double vol = s.vol[ip];
+#pragma unroll
+        for (int e = 0; e < 6; e++) r[28 + e] = vol * s.sig[e][ip];
+      }
+    }
+  };
+
+  // accumulate the n staged particles into the 4 node planes; plane c lives in register slot (c + R) & 3
+#define KML_CELL_ACCUM(R, n)                                                                                      \
+  for (int q = 0; q < (n); q++) {                                                                                 \
+    const double *r = rec0 + q * CELL_REC;                                                                        \
+    const double2 X = *(const double2 *)(r + 2 * a), Y = *(const double2 *)(r + 8 + 2 * b);                        \
+    const double2 Z01 = *(const double2 *)(r + 16), Z23 = *(const double2 *)(r + 18);                              \
+    const double2 D01 = *(const double2 *)(r + 20), D23 = *(const double2 *)(r + 22);                              \
+    const double2 MM = *(const double2 *)(r + 24), MV = *(const double2 *)(r + 26);                                \
+    const double wz[4] = {Z01.x, Z01.y, Z23.x, Z23.y}, dwz[4] = {D01.x, D01.y, D23.x, D23.y};                      \
+    const double gxy = X.x * Y.x;                                                                                  \
+    const double M0 = gxy * MM.y, M1 = gxy * MV.x, M2 = gxy * MV.y;                                                \
+    if (FULL) {                                                                                                    \
+      const double2 A01 = *(const double2 *)(r + 28), A23 = *(const double2 *)(r + 30), A45 = *(const double2 *)(r + 32); \
+      const double gx = X.y * Y.x, gy = X.x * Y.y, mm = gxy * MM.x;                                                \
+      /* A = (xx,yy,zz,xy,xz,yz): f_x = -(xx gx + xy gy) wz - xz gxy dwz, ... */                                   \
+      const double P0 = -(A01.x * gx + A23.y * gy), P1 = -(A23.y * gx + A01.y * gy), P2 = -(A45.x * gx + A45.y * gy); \
+      const double Q0 = -(A45.x * gxy), Q1 = -(A45.y * gxy), Q2 = -(A23.x * gxy);                                  \
+      _Pragma("unroll") for (int c = 0; c < 4; c++) {                                                              \
+        double *ac = acc[(c + R) & 3];                                                                             \
+        ac[0] += mm * wz[c];                                                                                       \
+        ac[1] += M0 * wz[c]; ac[2] += M1 * wz[c]; ac[3] += M2 * wz[c];                                             \
+        ac[4] += P0 * wz[c] + Q0 * dwz[c]; ac[5] += P1 * wz[c] + Q1 * dwz[c]; ac[6] += P2 * wz[c] + Q2 * dwz[c];    \
+      }                                                                                                            \
+    } else {                                                                                                       \
+      _Pragma("unroll") for (int c = 0; c < 4; c++) {                                                              \
+        double *ac = acc[(c + R) & 3];                                                                             \
+        ac[0] += M0 * wz[c]; ac[1] += M1 * wz[c]; ac[2] += M2 * wz[c];                                             \
+      }                                                                                                            \
+    }                                                                                                              \
+  }
+
+#define KML_CELL_STEP(R)                                                                                          \
+  {                                                                                                               \
+    const int kk = k + R;                                                                                         \
+    if (kk < kend) {                                                                                              \
+      const int pbeg = start[cellbase + kk], pend = start[cellbase + kk + 1];                                     \
+      for (int p = pbeg; p < pend; p += CELL_CHUNK) {                                                             \
+        const int n = min(CELL_CHUNK, pend - p);                                                                  \
+        stage_chunk(p, n, kk);                                                                                    \
+        __syncwarp(halfmask);                                                                                     \
+        KML_CELL_ACCUM(R, n)                                                                                      \
+        __syncwarp(halfmask);                                                                                     \
+      }                                                                                                           \
+      emit(R, kk);                                                                                                \
+    }                                                                                                             \
   }
 
   int k = kbeg;
   for (; k < kend; k += 4) { KML_CELL_STEP(0) KML_CELL_STEP(1) KML_CELL_STEP(2) KML_CELL_STEP(3) }
 #undef KML_CELL_STEP
+#undef KML_CELL_ACCUM
   // the three node planes above the last cell of the segment: plane c of cell (kend-1) sits in slot (c + r) & 3
-  // with r = (kend - 1 - kbeg) & 3
   const int r = (kend - 1 - kbeg) & 3;
 #pragma unroll
   for (int c = 1; c < 4; c++) {
-    const int slot = (c + r) & 3;
-    // slot is a runtime value here: select through a small switch so the accumulators stay in registers
+    const int slot = (c + r) & 3; // runtime value: select through a switch so the accumulators stay in registers
     switch (slot) { case 0: emit(0, kend - 1 + c); break; case 1: emit(1, kend - 1 + c); break; case 2: emit(2, kend - 1 + c); break; default: emit(3, kend - 1 + c); break; }
   }
 }
@@ -216,7 +244,7 @@ inline int cell_p2g_launch(const SolidDev &s, const GridDev &g, const CellLists 
   const int seglen = 32;
   const int nseg = (g.n[2] + seglen - 1) / seglen;
   const long long ngroups = (long long)g.n[0] * g.n[1] * nseg;
-  const unsigned nb = (unsigned)((ngroups * 8 + 127) / 128);
+  const unsigned nb = (unsigned)((ngroups * 16 + 127) / 128);
   if (full) {
     if (what & P2G_MASS) k_p2g_cell<true, true><<<nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
     else k_p2g_cell<true, false><<<nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
