@@ -2,7 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a (see karamelo_b200/Makefile).
 #define KML_MISC_KERNELS
 #include "kml_launch.h"
-#include "kml_p2g_cell.cuh"
+#include "kml_gather_cell.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -483,7 +483,12 @@ int kml_advance_particles(kml_ctx *c) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
-    KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
+    int rc = -1;
+    if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+      StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream);
+      if (rc > 0) return fail("cell g2p launch failed");
+    }
+    if (rc < 0) KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
     c->launches[KML_STAGE_G2P]++;
     if (check_launch("k_g2p")) return 1;
     if (!c->c.is_TL) S->moved = true;
@@ -534,7 +539,12 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     if (grid_normalize_if_needed(c, G)) return 1;
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
-    KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);
+    int rc = -1;
+    if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream);
+      if (rc > 0) return fail("cell stress launch failed");
+    }
+    if (rc < 0) KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);
     c->launches[KML_STAGE_STRESS]++;
     if (check_launch("k_stress")) return 1;
   }

@@ -178,6 +178,26 @@ __global__ void k_grid_zero_v(GridDev g, int zero_mass) {
 
 #endif // KML_MISC_KERNELS
 
+// tail of G2P for one particle: a_p, x_p += dt v~_p, FLIP/PIC blend (src/solid.cpp:613-616, :786-796)
+template <bool TL>
+__device__ __forceinline__ void particle_advance(const SolidDev &s, const StepParams &sp, long long ip, const double *vu, const double *a, double Tp) {
+  const double inv_dt = 1.0 / sp.dt;
+  double xnew[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double ad = a[d] * inv_dt;
+    const double xo = s.x[d][ip];
+    xnew[d] = xo + sp.dt * vu[d];
+    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * (s.v[d][ip] + sp.dt * ad);
+    if (TL) s.x[d][ip] = xnew[d]; else s.xn[d][ip] = xnew[d];
+  }
+  if (sp.temp) s.T[ip] = Tp;
+  if (!TL) { // Domain::inside, src/domain.cpp:176-185 -> error flag instead of abort (src/solid.cpp:617-627)
+    bool in = xnew[0] >= sp.boxlo[0] && xnew[0] <= sp.boxhi[0] && xnew[1] >= sp.boxlo[1] && xnew[1] <= sp.boxhi[1] && xnew[2] >= sp.boxlo[2] && xnew[2] <= sp.boxhi[2];
+    if (!in) atomicOr(sp.flags, 1u);
+  }
+}
+
 // ---- G2P + advance ---------------------------------------------------------------------------
 // Solid::compute_particle_accelerations_velocities_and_positions src/solid.cpp:576-635 fused with
 // Solid::update_particle_velocities src/solid.cpp:786-796 and update_particle_temperature :2798-2808.
@@ -197,21 +217,7 @@ __global__ void __launch_bounds__(128) k_g2p(SolidDev s, GridDev g, StepParams s
     if (sp.temp) Tp += wf * ru.w;
     (void)wfd0; (void)wfd1; (void)wfd2;
   })
-  const double inv_dt = 1.0 / sp.dt;
-  double xnew[3];
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    const double ad = a[d] * inv_dt;
-    const double xo = s.x[d][ip];
-    xnew[d] = xo + sp.dt * vu[d];
-    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * (s.v[d][ip] + sp.dt * ad);
-    if (TL) s.x[d][ip] = xnew[d]; else s.xn[d][ip] = xnew[d];
-  }
-  if (sp.temp) s.T[ip] = Tp;
-  if (!TL) { // Domain::inside, src/domain.cpp:176-185 -> error flag instead of abort (src/solid.cpp:617-627)
-    bool in = xnew[0] >= sp.boxlo[0] && xnew[0] <= sp.boxhi[0] && xnew[1] >= sp.boxlo[1] && xnew[1] <= sp.boxhi[1] && xnew[2] >= sp.boxlo[2] && xnew[2] <= sp.boxhi[2];
-    if (!in) atomicOr(sp.flags, 1u);
-  }
+  particle_advance<TL>(s, sp, ip, vu, a, Tp);
 }
 
 // ---- velocity gradient + deformation gradient + stress, fused ---------------------------------
@@ -224,6 +230,142 @@ struct StressParams {
   double *max_wave;     // device scalar: max_p (c_p + |v|_inf)
   double *min_h_ratio;  // device scalar (TL)
 };
+
+// Everything after the velocity-gradient gather for one particle: F update, J, vol, D (R for TL), the
+// constitutive update and the particle's CFL wave speed (src/solid.cpp:1155-1438, :2810-2839).
+// L is the gathered velocity gradient (Fdot for TL); qv the gathered -grad(T).
+template <bool TL>
+__device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev &g, const StepParams &sp, const kml_material &mat, long long ip,
+                                                double *L, const double *qv, double &wave, double &hr) {
+  const double dt = sp.dt;
+  double F[9], Fn[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) F[i] = s.F[i][ip];
+  if (TL) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) Fn[i] = F[i] + dt * L[i]; // here L holds Fdot
+  } else {
+    double IL[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) IL[i] = dt * L[i];
+    IL[0] += 1; IL[4] += 1; IL[8] += 1;
+    mul3(IL, F, Fn);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
+  double Finv[9]; inv3(Fn, Finv);
+  const double J = det3(Fn);
+  const double vol0 = s.vol0[ip];
+  const double vol = J * vol0;
+  s.vol[ip] = vol;
+  const double damage_old = s.dmg[ip];
+  if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);
+  const double rho = s.rho0[ip] / J;
+  double D[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (mat.type != KML_MAT_NEO_HOOKEAN) {
+    if (TL) {
+      if (!poldec3(Fn, R)) atomicOr(sp.flags, 8u);
+      double Lt[9], S[9], T1[9];
+      mul3(L, Finv, Lt);                     // L = Fdot Finv
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) S[3 * a + b] = Lt[3 * a + b] + Lt[3 * b + a];
+      mul3_at(R, S, T1); mul3(T1, R, D);     // R^T (L + L^T) R
+#pragma unroll
+      for (int i = 0; i < 9; i++) D[i] *= 0.5;
+#pragma unroll
+      for (int i = 0; i < 9; i++) s.R[i][ip] = R[i];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) D[3 * a + b] = 0.5 * (L[3 * a + b] + L[3 * b + a]);
+    }
+  }
+  double sig[9], eel[9];
+  load_sym(s.sig, ip, sig); load_sym(s.eel, ip, eel);
+  double damage = damage_old;
+  if (mat.type == KML_MAT_LINEAR) {
+    const double tr = dt * D[0] + dt * D[4] + dt * D[8];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { const double inc = dt * D[i]; eel[i] += inc; sig[i] += 2 * mat.G * inc; }
+    const double lt = mat.lambda * tr;
+    sig[0] += lt; sig[4] += lt; sig[8] += lt;
+  } else if (mat.type == KML_MAT_NEO_HOOKEAN) {
+    double PK1[9]; const double lJ = mat.lambda * log(J);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) PK1[3 * a + b] = mat.G * (Fn[3 * a + b] - Finv[3 * b + a]) + lJ * Finv[3 * b + a];
+    if (TL) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) s.pk1[i][ip] = vol0 * PK1[i];
+    }
+    double FP[9]; mul3_bt(Fn, PK1, FP);
+    const double iJ = 1.0 / J;
+#pragma unroll
+    for (int i = 0; i < 9; i++) sig[i] = iJ * FP[i];
+    double C[9]; mul3_at(Fn, Fn, C);
+    C[0] -= 1; C[4] -= 1; C[8] -= 1;
+#pragma unroll
+    for (int i = 0; i < 9; i++) eel[i] = 0.5 * C[i];
+  } else { // EOS + strength (+ damage, + plastic-work heating): src/solid.cpp:1292-1374
+    const bool thermal = mat.cp != 0;
+    const double T = thermal ? s.T[ip] : 0.0;
+    const double trD = D[0] + D[4] + D[8];
+    double ien;
+    double pH = eos_pressure(mat, ien, J, rho, damage, trD, g.cellsize, T);
+    s.ien[ip] = ien;
+    if (thermal) pH += mat.tmp_alpha * (mat.tmp_T0 - T);
+    double sdev[9], dep;
+    double eps = s.eps[ip], epsdot = s.epsdot[ip];
+    strength_dev(mat, dt, sig, D, sdev, dep, eps, epsdot, damage, T);
+    eps += dep;
+    const double tav = 1000 * g.cellsize / mat.signal_velocity;
+    epsdot -= epsdot * dt / tav;
+    epsdot += dep / tav;
+    epsdot = (0.0 > epsdot) ? 0.0 : epsdot;
+    s.eps[ip] = eps; s.epsdot[ip] = epsdot;
+    if (mat.damage_type != KML_DAMAGE_NONE) {
+      double di = s.dmgi[ip];
+      damage_jc(mat, di, damage, pH, sdev, epsdot, dep, sp.temp ? s.T[ip] : 0.0);
+      s.dmgi[ip] = di; s.dmg[ip] = damage;
+    }
+    if (thermal) {
+      const double flow = KML_SQRT_3_OVER_2 * frob3(sdev);
+      double gam = (T < mat.tmp_Tm) ? mat.tmp_chi * flow * epsdot : 0.0;
+      gam *= (TL ? vol0 : vol) * mat.invcp;
+      s.gamma[ip] = gam;
+    }
+    const double pf = (damage == 0 || pH >= 0) ? -pH : -pH * (1.0 - damage);
+    const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) / 3.0;
+    const double Gd = (damage > 1e-10) ? mat.G * (1 - damage) : mat.G;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] / Gd; }
+    sig[0] += pf; sig[4] += pf; sig[8] += pf;
+    eel[0] += te; eel[4] += te; eel[8] += te;
+  }
+  store_sym(s.sig, ip, sig); store_sym(s.eel, ip, eel);
+  if (TL && mat.type != KML_MAT_NEO_HOOKEAN) { // vol0PK1 = vol0 J (R sigma R^T) F^-T
+    double T1[9], T2[9], P[9];
+    mul3(R, sig, T1); mul3_bt(T1, R, T2); mul3_bt(T2, Finv, P);
+    const double c = vol0 * J;
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.pk1[i][ip] = c * P[i];
+  }
+  if (sp.temp) {
+    const double c = (TL ? vol0 : vol) * mat.invcp * mat.kappa;
+#pragma unroll
+    for (int b = 0; b < 3; b++) s.q[b][ip] = qv[b] * c;
+  }
+  if (!(damage >= 1.0)) { // wave speed for the CFL limit, src/solid.cpp:1378-1385
+    const double vx = fabs(s.v[0][ip]), vy = fabs(s.v[1][ip]), vz = fabs(s.v[2][ip]);
+    wave = sqrt((mat.K + KML_FOUR_THIRD * mat.G) / rho) + fmax(fmax(vx, vy), vz);
+    if (isnan(wave)) { atomicOr(sp.flags, 4u); wave = 0; }
+    if (TL) { double e; if (eig3_min_abs_real(Fn, e)) hr = fmin(hr, e); }
+  }
+}
 
 template <int DIM, int SHAPE, bool TL>
 __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat) {
@@ -254,134 +396,7 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
       const double xr = TL ? s.x0[0][ip] : (tp.moved ? s.xn[0][ip] : s.x[0][ip]);
       L[8] += hoop / xr; // the reference divides term by term; same value up to rounding
     }
-    const double dt = sp.dt;
-    double F[9], Fn[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) F[i] = s.F[i][ip];
-    if (TL) {
-#pragma unroll
-      for (int i = 0; i < 9; i++) Fn[i] = F[i] + dt * L[i]; // here L holds Fdot
-    } else {
-      double IL[9];
-#pragma unroll
-      for (int i = 0; i < 9; i++) IL[i] = dt * L[i];
-      IL[0] += 1; IL[4] += 1; IL[8] += 1;
-      mul3(IL, F, Fn);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
-    double Finv[9]; inv3(Fn, Finv);
-    const double J = det3(Fn);
-    const double vol0 = s.vol0[ip];
-    const double vol = J * vol0;
-    s.vol[ip] = vol;
-    const double damage_old = s.dmg[ip];
-    if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);
-    const double rho = s.rho0[ip] / J;
-    double D[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    if (mat.type != KML_MAT_NEO_HOOKEAN) {
-      if (TL) {
-        if (!poldec3(Fn, R)) atomicOr(sp.flags, 8u);
-        double Lt[9], S[9], T1[9];
-        mul3(L, Finv, Lt);                     // L = Fdot Finv
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int b = 0; b < 3; b++) S[3 * a + b] = Lt[3 * a + b] + Lt[3 * b + a];
-        mul3_at(R, S, T1); mul3(T1, R, D);     // R^T (L + L^T) R
-#pragma unroll
-        for (int i = 0; i < 9; i++) D[i] *= 0.5;
-#pragma unroll
-        for (int i = 0; i < 9; i++) s.R[i][ip] = R[i];
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int b = 0; b < 3; b++) D[3 * a + b] = 0.5 * (L[3 * a + b] + L[3 * b + a]);
-      }
-    }
-    double sig[9], eel[9];
-    load_sym(s.sig, ip, sig); load_sym(s.eel, ip, eel);
-    double damage = damage_old;
-    if (mat.type == KML_MAT_LINEAR) {
-      const double tr = dt * D[0] + dt * D[4] + dt * D[8];
-#pragma unroll
-      for (int i = 0; i < 9; i++) { const double inc = dt * D[i]; eel[i] += inc; sig[i] += 2 * mat.G * inc; }
-      const double lt = mat.lambda * tr;
-      sig[0] += lt; sig[4] += lt; sig[8] += lt;
-    } else if (mat.type == KML_MAT_NEO_HOOKEAN) {
-      double PK1[9]; const double lJ = mat.lambda * log(J);
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) PK1[3 * a + b] = mat.G * (Fn[3 * a + b] - Finv[3 * b + a]) + lJ * Finv[3 * b + a];
-      if (TL) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) s.pk1[i][ip] = vol0 * PK1[i];
-      }
-      double FP[9]; mul3_bt(Fn, PK1, FP);
-      const double iJ = 1.0 / J;
-#pragma unroll
-      for (int i = 0; i < 9; i++) sig[i] = iJ * FP[i];
-      double C[9]; mul3_at(Fn, Fn, C);
-      C[0] -= 1; C[4] -= 1; C[8] -= 1;
-#pragma unroll
-      for (int i = 0; i < 9; i++) eel[i] = 0.5 * C[i];
-    } else { // EOS + strength (+ damage, + plastic-work heating): src/solid.cpp:1292-1374
-      const bool thermal = mat.cp != 0;
-      const double T = thermal ? s.T[ip] : 0.0;
-      const double trD = D[0] + D[4] + D[8];
-      double ien;
-      double pH = eos_pressure(mat, ien, J, rho, damage, trD, g.cellsize, T);
-      s.ien[ip] = ien;
-      if (thermal) pH += mat.tmp_alpha * (mat.tmp_T0 - T);
-      double sdev[9], dep;
-      double eps = s.eps[ip], epsdot = s.epsdot[ip];
-      strength_dev(mat, dt, sig, D, sdev, dep, eps, epsdot, damage, T);
-      eps += dep;
-      const double tav = 1000 * g.cellsize / mat.signal_velocity;
-      epsdot -= epsdot * dt / tav;
-      epsdot += dep / tav;
-      epsdot = (0.0 > epsdot) ? 0.0 : epsdot;
-      s.eps[ip] = eps; s.epsdot[ip] = epsdot;
-      if (mat.damage_type != KML_DAMAGE_NONE) {
-        double di = s.dmgi[ip];
-        damage_jc(mat, di, damage, pH, sdev, epsdot, dep, sp.temp ? s.T[ip] : 0.0);
-        s.dmgi[ip] = di; s.dmg[ip] = damage;
-      }
-      if (thermal) {
-        const double flow = KML_SQRT_3_OVER_2 * frob3(sdev);
-        double gam = (T < mat.tmp_Tm) ? mat.tmp_chi * flow * epsdot : 0.0;
-        gam *= (TL ? vol0 : vol) * mat.invcp;
-        s.gamma[ip] = gam;
-      }
-      const double pf = (damage == 0 || pH >= 0) ? -pH : -pH * (1.0 - damage);
-      const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) / 3.0;
-      const double Gd = (damage > 1e-10) ? mat.G * (1 - damage) : mat.G;
-#pragma unroll
-      for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] / Gd; }
-      sig[0] += pf; sig[4] += pf; sig[8] += pf;
-      eel[0] += te; eel[4] += te; eel[8] += te;
-    }
-    store_sym(s.sig, ip, sig); store_sym(s.eel, ip, eel);
-    if (TL && mat.type != KML_MAT_NEO_HOOKEAN) { // vol0PK1 = vol0 J (R sigma R^T) F^-T
-      double T1[9], T2[9], P[9];
-      mul3(R, sig, T1); mul3_bt(T1, R, T2); mul3_bt(T2, Finv, P);
-      const double c = vol0 * J;
-#pragma unroll
-      for (int i = 0; i < 9; i++) s.pk1[i][ip] = c * P[i];
-    }
-    if (sp.temp) {
-      const double c = (TL ? vol0 : vol) * mat.invcp * mat.kappa;
-#pragma unroll
-      for (int b = 0; b < 3; b++) s.q[b][ip] = qv[b] * c;
-    }
-    if (!(damage >= 1.0)) { // wave speed for the CFL limit, src/solid.cpp:1378-1385
-      const double vx = fabs(s.v[0][ip]), vy = fabs(s.v[1][ip]), vz = fabs(s.v[2][ip]);
-      wave = sqrt((mat.K + KML_FOUR_THIRD * mat.G) / rho) + fmax(fmax(vx, vy), vz);
-      if (isnan(wave)) { atomicOr(sp.flags, 4u); wave = 0; }
-      if (TL) { double e; if (eig3_min_abs_real(Fn, e)) hr = fmin(hr, e); }
-    }
+    particle_stress<TL>(s, g, sp, mat, ip, L, qv, wave, hr);
   }
   // block reduction -> one atomic per warp
 #pragma unroll
