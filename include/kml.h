@@ -69,7 +69,14 @@ typedef struct kml_grid_desc {
   double lo[3];
   double h;        /* node spacing */
   double cellsize; /* Grid::cellsize: inv_cellsize = 1/cellsize scales r and the derivatives */
-  int n[3];        /* nx, ny, nz (1 in unused dimensions) */
+  int n[3];        /* nx, ny, nz of THIS rank's grid (1 in unused dimensions) */
+  /* Slab decomposition along x (all zero = not decomposed).  lo[] stays the GLOBAL origin; local node
+   * plane i is global plane i + goff of gn (node positions, tags and ntype are those of the global grid,
+   * src/grid.cpp:236-251).  Planes [own_lo, own_hi) are owned by this rank; the planes above own_hi are
+   * shared with (and owned by) the right neighbour and are summed after every scatter. */
+  int goff, gn, own_lo, own_hi;
+  /* particles whose GLOBAL stencil base lies in [base_lo, base_hi) belong to this rank */
+  int base_lo, base_hi;
 } kml_grid_desc;
 
 /* Mat record + functor parameter blocks: src/material.h:28-56, src/material.cpp:720-778,

@@ -14,6 +14,11 @@ int kmlh_create(kmlh_sim **out);
 int kmlh_destroy(kmlh_sim *s);
 int kmlh_set_quiet(kmlh_sim *s, int quiet);
 int kmlh_set_device(kmlh_sim *s, int device);
+/* one process per GPU: this process is rank `rank` of `nranks` slabs; nccl_id128 = the 128-byte id from
+ * kml_comm_unique_id() of rank 0 (NULL for host-only tests of the partition).  Call before the script. */
+int kmlh_set_ranks(kmlh_sim *s, int rank, int nranks, const void *nccl_id128);
+/* slab of solid i: base_lo, base_hi, goff, local nx, own_lo, own_hi, global particle count, tag offset */
+int kmlh_slab_info(kmlh_sim *s, int i, int64_t info[8]);
 int kmlh_run_file(kmlh_sim *s, const char *path);   /* Input::file */
 int kmlh_run_line(kmlh_sim *s, const char *line);   /* one script line through Input::parsev */
 int kmlh_get_var(kmlh_sim *s, const char *name, double *value);

@@ -97,6 +97,9 @@ def load_host_library(path=None):
         "kmlh_solid_info": (i32, [vp, i32, PL, PI, PI, PI]),
         "kmlh_state": (i32, [vp, PL, PD, PD]),
         "kmlh_ctx": (vp, [vp]),
+        "kmlh_set_ranks": (i32, [vp, i32, i32, vp]),
+        "kmlh_slab_info": (i32, [vp, i32, PL]),
+        "kml_comm_unique_id": (i32, [vp]),
         # engine ABI, resolved through the host library's dependency
         "kml_last_error": (C.c_char_p, []),
         "kml_backend": (C.c_char_p, []),
@@ -123,13 +126,30 @@ def load_host_library(path=None):
 class Engine:
     """One simulation: a script interpreter + device state."""
 
-    def __init__(self, lib=None, quiet=True, device=0):
+    def __init__(self, lib=None, quiet=True, device=0, rank=0, nranks=1, nccl_id=None):
+        """``rank``/``nranks``: this process drives slab ``rank`` of ``nranks`` (one process per GPU);
+        ``nccl_id`` is the 128-byte id of ``nccl_unique_id()`` on rank 0, shared with every rank."""
         self.lib = lib if lib is not None and not isinstance(lib, str) else load_host_library(lib)
         h = C.c_void_p()
         self._ck(self.lib.kmlh_create(C.byref(h)))
         self.h = h
         self.lib.kmlh_set_quiet(h, 1 if quiet else 0)
         self.lib.kmlh_set_device(h, device)
+        self.rank, self.nranks = rank, nranks
+        if nranks > 1:
+            buf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
+            self._ck(self.lib.kmlh_set_ranks(h, rank, nranks, C.cast(buf, C.c_void_p) if buf is not None else None))
+
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._ckk(self.lib.kml_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf.raw)
+
+    def slab_info(self, i=0):
+        info = (C.c_int64 * 8)()
+        self._ck(self.lib.kmlh_slab_info(self.h, i, info))
+        keys = ["base_lo", "base_hi", "goff", "nx_local", "own_lo", "own_hi", "np_global", "tag_offset"]
+        return dict(zip(keys, [int(v) for v in info]))
 
     # -- errors -------------------------------------------------------------------------
     def _ck(self, rc):

@@ -3,6 +3,7 @@
 #define KML_MISC_KERNELS
 #include "kml_launch.h"
 #include "kml_gather_cell.cuh"
+#include "kml_comm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -42,6 +43,7 @@ struct kml_ctx {
   bool tl_mass_done = false;
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true;
+  Comm comm;
   // profiling
   bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
 };
@@ -130,8 +132,13 @@ int kml_destroy(kml_ctx *c) {
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
   for (auto s : c->solids) { cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
+  if (c->comm.comm) {
+    nccl().CommDestroy(c->comm.comm);
+    cudaFree(c->comm.halo_recv); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
+    cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
+  }
   cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaStreamDestroy(c->stream);
   delete c; return 0;
 }
 int kml_synchronize(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaStreamSynchronize(c->stream)); return 0; }
@@ -145,6 +152,8 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   Grid *G = new Grid(); G->d = *d; GridDev &g = G->g;
   for (int k = 0; k < 3; k++) { g.lo[k] = d->lo[k]; g.n[k] = d->n[k]; }
   g.h = d->h; g.cellsize = d->cellsize; g.inv_cellsize = 1.0 / d->cellsize;
+  g.goff0 = d->goff; g.gn0 = d->gn > 0 ? d->gn : d->n[0];
+  g.own_lo = d->gn > 0 ? d->own_lo : 0; g.own_hi = d->gn > 0 ? d->own_hi : d->n[0];
   g.nn = (long long)d->n[0] * d->n[1] * d->n[2];
   const long long nn = g.nn, stride = (nn + 31) / 32 * 32;
   CU(cudaMalloc(&G->buf, sizeof(double) * stride * GRID_NDBL)); CU(cudaMemsetAsync(G->buf, 0, sizeof(double) * stride * GRID_NDBL, c->stream));
@@ -162,7 +171,7 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   for (int k = 0; k < 3; k++) {
     long long l = 0;
     for (int i = 0; i < d->n[0]; i++) for (int j = 0; j < d->n[1]; j++) for (int kk = 0; kk < d->n[2]; kk++, l++) {
-      int idx = k == 0 ? i : (k == 1 ? j : kk);
+      int idx = k == 0 ? i + g.goff0 : (k == 1 ? j : kk);
       xs[l] = (k < c->c.dimension) ? d->lo[k] + idx * d->h : 0.0;
     }
     CU(cudaMemcpyAsync(g.x[k], xs.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
@@ -220,11 +229,11 @@ int kml_grid_download(kml_ctx *c, int gid, int field, void *dst) {
   if (field == KML_N_X0 || field == KML_N_NTYPE) {
     long long l = 0;
     for (int i = 0; i < d.n[0]; i++) for (int j = 0; j < d.n[1]; j++) for (int k = 0; k < d.n[2]; k++, l++) {
-      int idx[3] = {i, j, k};
+      int idx[3] = {i + G->g.goff0, j, k};
       for (int a = 0; a < 3; a++) {
         if (field == KML_N_X0) ((double *)dst)[3 * l + a] = a < c->c.dimension ? d.lo[a] + idx[a] * d.h : 0.0;
         else {
-          int nt = 0, n = d.n[a], ii = idx[a];
+          int nt = 0, n = a == 0 ? G->g.gn0 : d.n[a], ii = idx[a];
           if (c->c.shape_function == KML_SHAPE_BERNSTEIN) nt = ii % 2;
           else if (c->c.shape_function != KML_SHAPE_LINEAR) nt = std::min(2, ii) - std::min(n - 1 - ii, 2);
           ((int *)dst)[3 * l + a] = nt;
@@ -400,6 +409,61 @@ int kml_reset(kml_ctx *c) { // ULMPM::reset: mbp = 0, dtCFL = 1e22
   return 0;
 }
 
+static std::vector<Grid *> active_grids(kml_ctx *c) {
+  std::vector<Grid *> r;
+  for (Solid *S : c->solids) { Grid *G = c->grids[S->d.grid]; if (std::find(r.begin(), r.end(), G) == r.end()) r.push_back(G); }
+  return r;
+}
+
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + nccl().GetErrorString(r_)); } while (0)
+
+// Sum of the node planes shared with the slab neighbours (see kml_comm.cuh).  Local planes [0, nsh) are shared
+// with the left neighbour, [n0 - nsh, n0) with the right one, nsh = stencil span - 1.
+static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
+  Comm &cm = c->comm; GridDev &g = G->g;
+  const int span = c->c.shape_function == KML_SHAPE_LINEAR ? 2 : 4;
+  const int nsh = span - 1;
+  const long long plane = (long long)g.n[1] * g.n[2], cnt = plane * nsh;
+  struct Field { double *ptr; int width; };
+  std::vector<Field> fields;
+  if (what & P2G_MOM) fields.push_back({(double *)g.nv, 4});
+  if (what & P2G_FORCE) for (int d = 0; d < 3; d++) fields.push_back({g.f[d], 1});
+  if (what & P2G_MB) for (int d = 0; d < 3; d++) fields.push_back({g.mb[d], 1});
+  if (what & P2G_TEMP) fields.push_back({g.T, 1});
+  if (what & P2G_HEAT) { fields.push_back({g.Qext, 1}); fields.push_back({g.Qint, 1}); }
+  size_t total = 0; for (auto &f : fields) total += (size_t)cnt * f.width;
+  const size_t need = total * 2 * sizeof(double);
+  if (need > cm.halo_bytes) { cudaFree(cm.halo_recv); CU(cudaMalloc(&cm.halo_recv, need)); cm.halo_bytes = need; }
+  const bool left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+  double *rl = cm.halo_recv, *rr = cm.halo_recv + total;
+  NC(nccl().GroupStart());
+  size_t off = 0;
+  for (auto &f : fields) {
+    const size_t n = (size_t)cnt * f.width;
+    if (left) { NC(nccl().Send(f.ptr, n, ncclDouble, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(rl + off, n, ncclDouble, cm.rank - 1, cm.comm, c->stream)); }
+    if (right) {
+      double *top = f.ptr + (size_t)(g.n[0] - nsh) * plane * f.width;
+      NC(nccl().Send(top, n, ncclDouble, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(rr + off, n, ncclDouble, cm.rank + 1, cm.comm, c->stream));
+    }
+    off += n;
+  }
+  NC(nccl().GroupEnd());
+  off = 0;
+  for (auto &f : fields) {
+    const size_t n = (size_t)cnt * f.width;
+    for (int side = 0; side < 2; side++) {
+      if (!(side == 0 ? left : right)) continue;
+      double *dst = side == 0 ? f.ptr : f.ptr + (size_t)(g.n[0] - nsh) * plane * f.width;
+      const double *src = (side == 0 ? rl : rr) + off;
+      if (f.width == 4) k_halo_add_nv<<<nblocks(cnt, 256), 256, 0, c->stream>>>((double4 *)dst, (const double4 *)src, cnt, (what & P2G_MASS) ? 1 : 0);
+      else k_halo_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(dst, src, cnt);
+      c->launches[stage]++;
+    }
+    off += n;
+  }
+  return check_launch("halo_sum");
+}
+
 static int p2g_launch(kml_ctx *c, int what_in, int stage) {
   StageTimer t(c, stage);
   StepParams sp = step_params(c);
@@ -438,6 +502,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (what & P2G_TEMP) G->T_is_weighted = true;
   }
   if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
+  if (c->comm.nranks > 1) for (Grid *G : active_grids(c)) if (halo_sum(c, G, what_in, stage)) return 1;
   return 0;
 }
 
@@ -453,12 +518,6 @@ int kml_particles_to_grid_USF_1(kml_ctx *c) {
 int kml_particles_to_grid_USF_2(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   return p2g_launch(c, P2G_FORCE | P2G_MB | (c->c.temp ? P2G_HEAT : 0), KML_STAGE_P2G);
-}
-
-static std::vector<Grid *> active_grids(kml_ctx *c) {
-  std::vector<Grid *> r;
-  for (Solid *S : c->solids) { Grid *G = c->grids[S->d.grid]; if (std::find(r.begin(), r.end(), G) == r.end()) r.push_back(G); }
-  return r;
 }
 
 int kml_update_grid_state(kml_ctx *c) {
@@ -557,6 +616,10 @@ int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
   StageTimer t(c, KML_STAGE_OTHER);
   const int ns = (int)c->solids.size();
   if (ns * 2 + 1 > 64) return fail("too many solids");
+  if (c->comm.nranks > 1) { // MPI_Allreduce(MIN) of dtCFL in the reference (src/ulmpm.cpp:547) == max of the wave speed here
+    for (int i = 0; i < ns; i++) NC(nccl().AllReduce(c->solids[i]->red, c->solids[i]->red, 1, ncclDouble, ncclMax, c->comm.comm, c->stream));
+    NC(nccl().AllReduce(c->d_flags, c->d_flags, 1, ncclUint32, ncclMax, c->comm.comm, c->stream));
+  }
   for (int i = 0; i < ns; i++) CU(cudaMemcpyAsync(c->h_pinned + 2 * i, c->solids[i]->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_pinned + 2 * ns, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -575,10 +638,74 @@ int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
   return 0;
 }
 
-int kml_exchange_particles(kml_ctx *) { return 0; }
+// ULMPM::exchange_particles (src/ulmpm.cpp:565-667): particles whose stencil base left this rank's slab move to the
+// neighbour that owns it.  The positions advanced by grid_to_points become current here.
+int kml_exchange_particles(kml_ctx *c) {
+  Comm &cm = c->comm;
+  if (cm.nranks <= 1) return 0;
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_OTHER);
+  for (Solid *S : c->solids) {
+    Grid *G = c->grids[S->d.grid]; SolidDev &s = S->s;
+    if (S->moved) { for (int k = 0; k < 3; k++) std::swap(s.x[k], s.xn[k]); S->moved = false; }
+    const int narr = SOLID_NDBL_UL;
+    const int cap_mig = (int)std::min<long long>(std::max<long long>(s.np / 8, 1024), 1 << 24);
+    if (cap_mig > cm.mig_cap) {
+      cudaFree(cm.mig_list); cudaFree(cm.mig_send); cudaFree(cm.mig_recv); cudaFree(cm.mig_flag);
+      CU(cudaMalloc(&cm.mig_list, sizeof(int) * 4 * (size_t)cap_mig));
+      CU(cudaMalloc(&cm.mig_flag, sizeof(int) * 2 * (size_t)cap_mig));
+      cm.mig_bytes = sizeof(double) * (size_t)(narr + 2) * 2 * cap_mig;
+      CU(cudaMalloc(&cm.mig_send, cm.mig_bytes)); CU(cudaMalloc(&cm.mig_recv, cm.mig_bytes));
+      cm.mig_cap = cap_mig;
+    }
+    CU(cudaMemsetAsync(cm.mig_cnt, 0, 8 * sizeof(int), c->stream));
+    k_mig_mark<<<nblocks(s.np, 256), 256, 0, c->stream>>>(s.x[0], s.np, G->g.lo[0], G->g.inv_cellsize, c->c.shape_function == KML_SHAPE_LINEAR,
+                                                          G->d.base_lo, G->d.base_hi, cm.rank, cm.nranks, cm.mig_cnt, cm.mig_list, cm.mig_cap);
+    const bool left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+    NC(nccl().GroupStart());
+    if (left) { NC(nccl().Send(cm.mig_cnt + 0, 1, ncclInt, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(cm.mig_cnt + 2, 1, ncclInt, cm.rank - 1, cm.comm, c->stream)); }
+    if (right) { NC(nccl().Send(cm.mig_cnt + 1, 1, ncclInt, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(cm.mig_cnt + 3, 1, ncclInt, cm.rank + 1, cm.comm, c->stream)); }
+    NC(nccl().GroupEnd());
+    CU(cudaMemcpyAsync(cm.h_cnt, cm.mig_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int nL = cm.h_cnt[0], nR = cm.h_cnt[1], rL = cm.h_cnt[2], rR = cm.h_cnt[3];
+    c->launches[KML_STAGE_OTHER]++;
+    if (nL > cm.mig_cap || nR > cm.mig_cap || rL > cm.mig_cap || rR > cm.mig_cap) return fail("particle migration buffer overflow");
+    if (nL + nR + rL + rR == 0) continue;
+    const long long np_new = s.np - nL - nR;
+    if (np_new + rL + rR > S->cap) return fail("particle capacity exceeded by migration");
+    double *sendL = cm.mig_send, *sendR = cm.mig_send + (size_t)(narr + 2) * cm.mig_cap;
+    double *recvL = cm.mig_recv, *recvR = cm.mig_recv + (size_t)(narr + 2) * cm.mig_cap;
+    if (nL) k_mig_pack<<<nblocks(nL, 128), 128, 0, c->stream>>>(sendL, cm.mig_list, nL, S->buf, S->cap, narr, s.ptag, s.mask);
+    if (nR) k_mig_pack<<<nblocks(nR, 128), 128, 0, c->stream>>>(sendR, cm.mig_list + cm.mig_cap, nR, S->buf, S->cap, narr, s.ptag, s.mask);
+    NC(nccl().GroupStart());
+    if (left) { if (nL) NC(nccl().Send(sendL, (size_t)(narr + 2) * nL, ncclDouble, cm.rank - 1, cm.comm, c->stream)); if (rL) NC(nccl().Recv(recvL, (size_t)(narr + 2) * rL, ncclDouble, cm.rank - 1, cm.comm, c->stream)); }
+    if (right) { if (nR) NC(nccl().Send(sendR, (size_t)(narr + 2) * nR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); if (rR) NC(nccl().Recv(recvR, (size_t)(narr + 2) * rR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); }
+    NC(nccl().GroupEnd());
+    if (nL + nR) { // close the holes left by the leavers with stayers from the tail
+      int *holes = cm.mig_list + 2 * (size_t)cm.mig_cap, *fillers = cm.mig_list + 3 * (size_t)cm.mig_cap;
+      const int ntail = nL + nR; // the last ntail slots [np_new, np) are vacated
+      CU(cudaMemsetAsync(cm.mig_flag, 0, sizeof(int) * ntail, c->stream));
+      k_mig_flag<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_list, cm.mig_cap, nL, nR, cm.mig_flag, np_new);
+      k_mig_holes<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_list, cm.mig_cap, nL, nR, np_new, cm.mig_cnt, holes);
+      k_mig_fillers<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_flag, np_new, ntail, cm.mig_cnt, fillers);
+      CU(cudaMemcpyAsync(cm.h_cnt + 4, cm.mig_cnt + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (cm.h_cnt[4] != cm.h_cnt[5]) return fail("migration: hole / filler count mismatch");
+      if (cm.h_cnt[4]) k_mig_move<<<nblocks(cm.h_cnt[4], 128), 128, 0, c->stream>>>(holes, fillers, cm.h_cnt[4], S->buf, S->cap, narr, s.ptag, s.mask);
+    }
+    if (rL) k_mig_unpack<<<nblocks(rL, 128), 128, 0, c->stream>>>(recvL, rL, np_new, S->buf, S->cap, narr, s.ptag, s.mask);
+    if (rR) k_mig_unpack<<<nblocks(rR, 128), 128, 0, c->stream>>>(recvR, rR, np_new + rL, S->buf, S->cap, narr, s.ptag, s.mask);
+    s.np = np_new + rL + rR;
+    c->launches[KML_STAGE_OTHER] += 6;
+    if (check_launch("migration")) return 1;
+  }
+  return 0;
+}
 
 // ---- fixes ------------------------------------------------------------------------------------
 static int read_scratch3(kml_ctx *c, double out[3]) {
+  if (c->comm.nranks > 1) NC(nccl().AllReduce(c->d_scratch, c->d_scratch, 3, ncclDouble, ncclSum, c->comm.comm, c->stream));
   CU(cudaMemcpyAsync(c->h_pinned + 32, c->d_scratch, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   for (int d = 0; d < 3; d++) out[d] = c->h_pinned[32 + d];
@@ -647,6 +774,7 @@ static int energy(kml_ctx *c, int solid, int groupbit, int kinetic, double *out)
     c->launches[KML_STAGE_OTHER]++;
   }
   if (check_launch("k_energy")) return 1;
+  if (c->comm.nranks > 1) NC(nccl().AllReduce(c->d_scratch + 8, c->d_scratch + 8, 1, ncclDouble, ncclSum, c->comm.comm, c->stream));
   CU(cudaMemcpyAsync(c->h_pinned + 40, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *out = c->h_pinned[40]; return 0;
@@ -661,8 +789,23 @@ int kml_error_flags(kml_ctx *c, unsigned *flags) {
   memcpy(flags, c->h_pinned + 48, sizeof(unsigned)); return 0;
 }
 
-int kml_comm_unique_id(void *) { return fail("kml: multi-GPU communicator not built into this library version"); }
-int kml_comm_init(kml_ctx *, const void *) { return fail("kml: multi-GPU communicator not built into this library version"); }
+int kml_comm_unique_id(void *id128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  { const std::string why = nccl().load(); if (!why.empty()) return fail("kml: " + why); }
+  ncclUniqueId id; NC(nccl().GetUniqueId(&id)); memcpy(id128, &id, sizeof id); return 0;
+}
+int kml_comm_init(kml_ctx *c, const void *id128) {
+  CU(cudaSetDevice(c->dev));
+  if (c->c.nranks <= 1) return 0;
+  if (c->c.is_TL) return fail("kml: the slab decomposition covers ULMPM (TL solids own private grids; replicate them instead)");
+  { const std::string why = nccl().load(); if (!why.empty()) return fail("kml: " + why); }
+  ncclUniqueId id; memcpy(&id, id128, sizeof id);
+  NC(nccl().CommInitRank(&c->comm.comm, c->c.nranks, id, c->c.rank));
+  c->comm.rank = c->c.rank; c->comm.nranks = c->c.nranks;
+  CU(cudaMalloc(&c->comm.mig_cnt, 8 * sizeof(int)));
+  CU(cudaMallocHost(&c->comm.h_cnt, 8 * sizeof(int)));
+  return 0;
+}
 
 int kml_profile(kml_ctx *c, int enable) { c->profile = enable != 0; return 0; }
 int kml_timer_start(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaEventRecord(c->evA, c->stream)); return 0; }

@@ -97,6 +97,10 @@ template <> struct Basis<KML_SHAPE_BERNSTEIN> {
 struct GridDev {
   double lo[3]; double h; double inv_cellsize; double cellsize;
   int n[3]; long long nn;
+  // slab decomposition along x: local node plane i is global plane i + goff0 of gn0; lo[] is always the GLOBAL
+  // origin so node positions and node types are bit-identical to the undecomposed grid
+  int goff0, gn0;
+  int own_lo, own_hi; // local planes [own_lo, own_hi) are owned by this rank (shared planes belong to the right neighbour)
   // Node records read by the gather kernels are 32-byte AoS so that one LDG.128 pair fetches a node:
   //   nv  = {vx, vy, vz, mass}      (momentum until the grid kernel divides by the mass)
   //   nvu = {vux, vuy, vuz, T_update}
@@ -128,18 +132,24 @@ template <int SHAPE, bool TL> struct StencilSpan {
 };
 
 template <int SHAPE, bool TL, int SPAN>
-__device__ __forceinline__ void axis_weights(double xp, double lo, double h, double ih, int n, int &i0, double (&w)[SPAN], double (&dw)[SPAN]) {
+__device__ __forceinline__ int stencil_base(double xp, double lo, double ih) { // GLOBAL base node index
   double t = __dmul_rn(__dsub_rn(xp, lo), ih);
-  if (SHAPE == KML_SHAPE_LINEAR) i0 = (int)t;
-  else if (SHAPE == KML_SHAPE_BERNSTEIN && TL) { i0 = 2 * (int)t; if (i0 >= 1 && (i0 & 1)) i0--; }
-  else i0 = (int)__dsub_rn(t, 1.0);
+  if (SHAPE == KML_SHAPE_LINEAR) return (int)t;
+  if (SHAPE == KML_SHAPE_BERNSTEIN && TL) { int i0 = 2 * (int)t; if (i0 >= 1 && (i0 & 1)) i0--; return i0; }
+  return (int)__dsub_rn(t, 1.0);
+}
+// n = local node count, goff = global index of local node 0, gn = global node count; i0 is returned LOCAL
+template <int SHAPE, bool TL, int SPAN>
+__device__ __forceinline__ void axis_weights(double xp, double lo, double h, double ih, int n, int goff, int gn, int &i0, double (&w)[SPAN], double (&dw)[SPAN]) {
+  const int ig0 = stencil_base<SHAPE, TL, SPAN>(xp, lo, ih);
+  i0 = ig0 - goff;
 #pragma unroll
   for (int a = 0; a < SPAN; a++) {
-    int i = i0 + a;
+    const int i = i0 + a, ig = ig0 + a;
     if (i < 0 || i >= n) { w[a] = 0; dw[a] = 0; continue; }
-    double xn = __dadd_rn(lo, __dmul_rn((double)i, h));          // node position, src/grid.cpp:222-227
+    double xn = __dadd_rn(lo, __dmul_rn((double)ig, h));         // node position, src/grid.cpp:222-227
     double r = __dmul_rn(__dsub_rn(xp, xn), ih);                  // src/ulmpm.cpp:246
-    Basis<SHAPE>::eval(r, node_type<SHAPE>(i, n), ih, w[a], dw[a]);
+    Basis<SHAPE>::eval(r, node_type<SHAPE>(ig, gn), ih, w[a], dw[a]);
   }
 }
 

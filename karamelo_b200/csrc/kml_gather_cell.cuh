@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(128) k_gather_cell(SolidDev s, GridDev g, Step
     double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
 #pragma unroll
     for (int t = 0; t < 4; t++) {
-      cubic_node(px, g.lo[0], g.h, g.inv_cellsize, i0 + t, g.n[0], wx[t], dwx[t]);
-      cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + t, g.n[1], wy[t], dwy[t]);
-      cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kbeg + koff + t, g.n[2], wz[t], dwz[t]);
+      cubic_node(px, g.lo[0], g.h, g.inv_cellsize, i0 + t, g.n[0], g.goff0, g.gn0, wx[t], dwx[t]);
+      cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + t, g.n[1], 0, g.n[1], wy[t], dwy[t]);
+      cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kbeg + koff + t, g.n[2], 0, g.n[2], wz[t], dwz[t]);
     }
     if (STRESS) {
       double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

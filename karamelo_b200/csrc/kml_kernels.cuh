@@ -40,10 +40,10 @@ template <int DIM, int SHAPE, bool TL> struct Stencil {
   int i0[3];
   double w[3][SPAN], dw[3][SPAN];
   __device__ __forceinline__ void build(const GridDev &g, double px, double py, double pz) {
-    axis_weights<SHAPE, TL, SPAN>(px, g.lo[0], g.h, g.inv_cellsize, g.n[0], i0[0], w[0], dw[0]);
-    if (DIM >= 2) axis_weights<SHAPE, TL, SPAN>(py, g.lo[1], g.h, g.inv_cellsize, g.n[1], i0[1], w[1], dw[1]);
+    axis_weights<SHAPE, TL, SPAN>(px, g.lo[0], g.h, g.inv_cellsize, g.n[0], g.goff0, g.gn0, i0[0], w[0], dw[0]);
+    if (DIM >= 2) axis_weights<SHAPE, TL, SPAN>(py, g.lo[1], g.h, g.inv_cellsize, g.n[1], 0, g.n[1], i0[1], w[1], dw[1]);
     else { i0[1] = 0; w[1][0] = 1; dw[1][0] = 0; }
-    if (DIM == 3) axis_weights<SHAPE, TL, SPAN>(pz, g.lo[2], g.h, g.inv_cellsize, g.n[2], i0[2], w[2], dw[2]);
+    if (DIM == 3) axis_weights<SHAPE, TL, SPAN>(pz, g.lo[2], g.h, g.inv_cellsize, g.n[2], 0, g.n[2], i0[2], w[2], dw[2]);
     else { i0[2] = 0; w[2][0] = 1; dw[2][0] = 0; }
   }
 };
@@ -427,9 +427,11 @@ __global__ void k_fix_velocity_nodes(GridDev g, int groupbit, int set_mask, doub
     g.nv[i] = rv;
   }
   if (which == 0) {
+    const int plane = (int)(min(i, g.nn - 1) / ((long long)g.n[1] * g.n[2]));
+    const bool own = plane >= g.own_lo && plane < g.own_hi; // shared slab planes are counted by their owner only
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      double x = f[d];
+      double x = own ? f[d] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
@@ -448,9 +450,11 @@ __global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f
       for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = fv[d] * m; g.mb[d][i] += f[d]; }
     }
   }
+  const int plane = (int)(min(i, g.nn - 1) / ((long long)g.n[1] * g.n[2]));
+  const bool own = plane >= g.own_lo && plane < g.own_hi;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    double x = f[d];
+    double x = own ? f[d] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);

@@ -37,17 +37,17 @@ struct CellLists {
 
 inline bool cell_p2g_supported(int dimension, int shape) { return dimension == 3 && shape == KML_SHAPE_CUBIC_SPLINE; }
 
-__device__ __forceinline__ int cell_axis(double xp, double lo, double ih, int n) {
-  int i0 = (int)__dsub_rn(__dmul_rn(__dsub_rn(xp, lo), ih), 1.0); // identical to axis_weights<cubic>
+__device__ __forceinline__ int cell_axis(double xp, double lo, double ih, int n, int goff) { // LOCAL stencil base
+  int i0 = (int)__dsub_rn(__dmul_rn(__dsub_rn(xp, lo), ih), 1.0) - goff; // identical to axis_weights<cubic>
   return min(max(i0, 0), n - 1);
 }
 
 __global__ void k_cell_count(SolidDev s, GridDev g, int *cell_of, int *rank, int *count) {
   long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ip >= s.np) return;
-  const int i0 = cell_axis(s.x[0][ip], g.lo[0], g.inv_cellsize, g.n[0]);
-  const int j0 = cell_axis(s.x[1][ip], g.lo[1], g.inv_cellsize, g.n[1]);
-  const int k0 = cell_axis(s.x[2][ip], g.lo[2], g.inv_cellsize, g.n[2]);
+  const int i0 = cell_axis(s.x[0][ip], g.lo[0], g.inv_cellsize, g.n[0], g.goff0);
+  const int j0 = cell_axis(s.x[1][ip], g.lo[1], g.inv_cellsize, g.n[1], 0);
+  const int k0 = cell_axis(s.x[2][ip], g.lo[2], g.inv_cellsize, g.n[2], 0);
   const int key = (i0 * g.n[1] + j0) * g.n[2] + k0;
   cell_of[ip] = key;
   rank[ip] = atomicAdd(&count[key], 1);
@@ -80,11 +80,12 @@ inline int CellLists::build(const SolidDev &s, const GridDev &g, cudaStream_t st
 }
 
 // one cubic-spline (value, derivative) pair of node i for a particle at xp; same expressions as axis_weights
-__device__ __forceinline__ void cubic_node(double xp, double lo, double h, double ih, int i, int n, double &w, double &dw) {
+// (i = LOCAL node index of n, global index i + goff of gn)
+__device__ __forceinline__ void cubic_node(double xp, double lo, double h, double ih, int i, int n, int goff, int gn, double &w, double &dw) {
   if (i < 0 || i >= n) { w = 0; dw = 0; return; }
-  const double xn = __dadd_rn(lo, __dmul_rn((double)i, h));
+  const double xn = __dadd_rn(lo, __dmul_rn((double)(i + goff), h));
   const double r = __dmul_rn(__dsub_rn(xp, xn), ih);
-  Basis<KML_SHAPE_CUBIC_SPLINE>::eval(r, node_type<KML_SHAPE_CUBIC_SPLINE>(i, n), ih, w, dw);
+  Basis<KML_SHAPE_CUBIC_SPLINE>::eval(r, node_type<KML_SHAPE_CUBIC_SPLINE>(i + goff, gn), ih, w, dw);
 }
 
 // FULL: mass + momentum + internal force (7 sums per node); !FULL: momentum only (MUSL re-projection)
@@ -160,9 +161,9 @@ __global__ void __launch_bounds__(128, 4) k_p2g_cell(SolidDev s, GridDev g, cons
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           double w, dw;
-          cubic_node(px, g.lo[0], g.h, g.inv_cellsize, i0 + t, g.n[0], w, dw); r[2 * t] = w; r[2 * t + 1] = dw;
-          cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + t, g.n[1], w, dw); r[8 + 2 * t] = w; r[8 + 2 * t + 1] = dw;
-          cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kk + t, g.n[2], w, dw); r[16 + t] = w; r[20 + t] = dw;
+          cubic_node(px, g.lo[0], g.h, g.inv_cellsize, i0 + t, g.n[0], g.goff0, g.gn0, w, dw); r[2 * t] = w; r[2 * t + 1] = dw;
+          cubic_node(py, g.lo[1], g.h, g.inv_cellsize, j0 + t, g.n[1], 0, g.n[1], w, dw); r[8 + 2 * t] = w; r[8 + 2 * t + 1] = dw;
+          cubic_node(pz, g.lo[2], g.h, g.inv_cellsize, kk + t, g.n[2], 0, g.n[2], w, dw); r[16 + t] = w; r[20 + t] = dw;
         }
         r[24] = m; r[25] = m * v0; r[26] = m * v1; r[27] = m * v2;
       } else if (FULL) {
@@ -204,33 +205,24 @@ __global__ void __launch_bounds__(128, 4) k_p2g_cell(SolidDev s, GridDev g, cons
     }                                                                                                              \
   }
 
-#define KML_CELL_STEP(R)                                                                                          \
-  {                                                                                                               \
-    const int kk = k + R;                                                                                         \
-    if (kk < kend) {                                                                                              \
-      const int pbeg = start[cellbase + kk], pend = start[cellbase + kk + 1];                                     \
-      for (int p = pbeg; p < pend; p += CELL_CHUNK) {                                                             \
-        const int n = min(CELL_CHUNK, pend - p);                                                                  \
-        stage_chunk(p, n, kk);                                                                                    \
-        __syncwarp(halfmask);                                                                                     \
-        KML_CELL_ACCUM(R, n)                                                                                      \
-        __syncwarp(halfmask);                                                                                     \
-      }                                                                                                           \
-      emit(R, kk);                                                                                                \
-    }                                                                                                             \
-  }
-
-  int k = kbeg;
-  for (; k < kend; k += 4) { KML_CELL_STEP(0) KML_CELL_STEP(1) KML_CELL_STEP(2) KML_CELL_STEP(3) }
-#undef KML_CELL_STEP
-#undef KML_CELL_ACCUM
-  // the three node planes above the last cell of the segment: plane c of cell (kend-1) sits in slot (c + r) & 3
-  const int r = (kend - 1 - kbeg) & 3;
+  // walk the cells of the segment; after a cell its lowest node plane is complete: add it to the grid and slide the
+  // register window down by one plane (21 register moves per cell, one copy of the loop body in the I-cache)
+  for (int kk = kbeg; kk < kend; kk++) {
+    const int pbeg = start[cellbase + kk], pend = start[cellbase + kk + 1];
+    for (int p = pbeg; p < pend; p += CELL_CHUNK) {
+      const int n = min(CELL_CHUNK, pend - p);
+      stage_chunk(p, n, kk);
+      __syncwarp(halfmask);
+      KML_CELL_ACCUM(0, n)
+      __syncwarp(halfmask);
+    }
+    emit(0, kk);
 #pragma unroll
-  for (int c = 1; c < 4; c++) {
-    const int slot = (c + r) & 3; // runtime value: select through a switch so the accumulators stay in registers
-    switch (slot) { case 0: emit(0, kend - 1 + c); break; case 1: emit(1, kend - 1 + c); break; case 2: emit(2, kend - 1 + c); break; default: emit(3, kend - 1 + c); break; }
+    for (int q = 0; q < Q; q++) { acc[0][q] = acc[1][q]; acc[1][q] = acc[2][q]; acc[2][q] = acc[3][q]; acc[3][q] = 0.0; }
   }
+#undef KML_CELL_ACCUM
+  // the three node planes above the last cell of the segment
+  emit(0, kend); emit(1, kend + 1); emit(2, kend + 2);
 }
 
 inline int cell_p2g_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, cudaStream_t st, int *nlaunch) {

@@ -14,6 +14,19 @@ int kmlh_create(kmlh_sim **out) { GUARD(*out = new kmlh_sim()) }
 int kmlh_destroy(kmlh_sim *s) { delete s; return 0; }
 int kmlh_set_quiet(kmlh_sim *s, int q) { s->sim.quiet = q != 0; s->sim.input.echo = !q; return 0; }
 int kmlh_set_device(kmlh_sim *s, int d) { s->sim.device = d; return 0; }
+int kmlh_set_ranks(kmlh_sim *s, int rank, int nranks, const void *nccl_id128) {
+  s->sim.rank = rank; s->sim.nranks = nranks;
+  if (nccl_id128) s->sim.nccl_id.assign((const unsigned char *)nccl_id128, (const unsigned char *)nccl_id128 + 128);
+  if (rank != 0) { s->sim.quiet = true; s->sim.input.echo = false; }
+  return 0;
+}
+int kmlh_slab_info(kmlh_sim *s, int i, int64_t info[8]) {
+  if (i < 0 || i >= (int)s->sim.solids.size()) { g_herr = "bad solid index"; return 1; }
+  SolidH &S = *s->sim.solids[i]; const kml_grid_desc &d = S.grid->desc;
+  info[0] = d.base_lo; info[1] = d.base_hi; info[2] = d.goff; info[3] = d.n[0]; info[4] = d.own_lo; info[5] = d.own_hi;
+  info[6] = s->sim.np_global_last; info[7] = s->sim.tag_offset_last;
+  return 0;
+}
 int kmlh_run_file(kmlh_sim *s, const char *path) { GUARD(s->sim.input.file(path)) }
 int kmlh_run_line(kmlh_sim *s, const char *line) { GUARD(s->sim.input.line(line)) }
 int kmlh_get_var(kmlh_sim *s, const char *name, double *value) {

@@ -138,9 +138,13 @@ void Sim::ensure_ctx() {
   cfg.shape_function = shape_function; cfg.sub_method = sub_method; cfg.PIC_FLIP = PIC_FLIP;
   cfg.axisymmetric = axisymmetric; cfg.temp = temp; cfg.ge = ge;
   for (int d = 0; d < 3; d++) { cfg.boxlo[d] = boxlo[d]; cfg.boxhi[d] = boxhi[d]; }
-  cfg.device = device; cfg.rank = 0; cfg.nranks = 1;
+  cfg.device = device; cfg.rank = rank; cfg.nranks = nranks;
   check(kml_create(&cfg, &ctx));
   check(kml_set_dt(ctx, dt));
+  if (nranks > 1) {
+    if (is_TL) fatal("multi-GPU runs cover ULMPM (slab decomposition of the background grid)\n");
+    if (nccl_id.size() == 128) check(kml_comm_init(ctx, nccl_id.data())); // absent in host-only (CPU) tests of the partition
+  }
 }
 
 // Grid::init on one rank, src/grid.cpp:68-264 (node counts) - the device creates the nodes themselves.
@@ -175,8 +179,24 @@ void Sim::init_grid(GridH &g, const double *solidlo, const double *solidhi) {
   g.desc.h = h; g.desc.cellsize = g.cellsize; g.desc.n[0] = nx; g.desc.n[1] = ny; g.desc.n[2] = nz;
   g.nnodes = (int64_t)nx * ny * nz;
   ensure_ctx();
+  if (nranks > 1 && !is_TL) { grid_pending = true; return; } // the slab is cut when the first solid's particles are known
   check(kml_grid_create(ctx, &g.desc, &g.id));
   g.mask.assign(g.nnodes, 1);
+}
+
+// This rank's slab of the background grid: node planes [base_lo, base_hi + span - 1) of the global grid.
+void Sim::create_device_grid(GridH &g, int base_lo, int base_hi) {
+  const int span = shape_function == KML_SHAPE_LINEAR ? 2 : 4;
+  const int nxg = g.nx_global;
+  const int p0 = std::max(base_lo, 0), p1 = std::min(base_hi + span - 1, nxg);
+  if (base_hi - base_lo < span - 1 && rank < nranks - 1) fatal("slab decomposition: a slab is thinner than the stencil overlap; use fewer GPUs\n");
+  g.desc.n[0] = p1 - p0; g.desc.goff = p0; g.desc.gn = nxg;
+  g.desc.own_lo = 0; g.desc.own_hi = rank == nranks - 1 ? p1 - p0 : std::max(0, base_hi - p0);
+  g.desc.base_lo = base_lo; g.desc.base_hi = base_hi;
+  g.nnodes = (int64_t)g.desc.n[0] * g.desc.n[1] * g.desc.n[2];
+  check(kml_grid_create(ctx, &g.desc, &g.id));
+  g.mask.assign(g.nnodes, 1);
+  grid_pending = false;
 }
 
 // Domain::set_dimension, src/domain.cpp:496-551 (+ set_local_box on a 1x1x1 proc grid, src/domain.cpp:366-394)
@@ -459,13 +479,39 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
 
   s.x0.clear();
   const int dim = dimension;
-  for (int i = 0; i < nsub[0]; i++) for (int j = 0; j < nsub[1]; j++) for (int k = 0; k < nsub[2]; k++) for (int q = 0; q < nip; q++) {
-    std::array<double, 3> x;
-    x[0] = boundlo[0] + delta * (noffsetlo[0] + i + 0.5 + ip[3 * q + 0]);
-    x[1] = boundlo[1] + delta * (noffsetlo[1] + j + 0.5 + ip[3 * q + 1]);
-    x[2] = dim == 3 ? boundlo[2] + delta * (noffsetlo[2] + k + 0.5 + ip[3 * q + 2]) : 0;
-    bool in_sub = !(x[0] < sublo[0] || x[0] > subhi[0] || x[1] < sublo[1] || x[1] > subhi[1] || x[2] < sublo[2] || x[2] > subhi[2]); // Domain::inside_subdomain
-    if (in_sub && reg.inside(x[0], x[1], x[2]) == 1) s.x0.push_back(x);
+  auto lattice = [&](auto &&accept) {
+    for (int i = 0; i < nsub[0]; i++) for (int j = 0; j < nsub[1]; j++) for (int k = 0; k < nsub[2]; k++) for (int q = 0; q < nip; q++) {
+      std::array<double, 3> x;
+      x[0] = boundlo[0] + delta * (noffsetlo[0] + i + 0.5 + ip[3 * q + 0]);
+      x[1] = boundlo[1] + delta * (noffsetlo[1] + j + 0.5 + ip[3 * q + 1]);
+      x[2] = dim == 3 ? boundlo[2] + delta * (noffsetlo[2] + k + 0.5 + ip[3 * q + 2]) : 0;
+      bool in_sub = !(x[0] < sublo[0] || x[0] > subhi[0] || x[1] < sublo[1] || x[1] > subhi[1] || x[2] < sublo[2] || x[2] > subhi[2]); // Domain::inside_subdomain
+      if (in_sub && reg.inside(x[0], x[1], x[2]) == 1) accept(x);
+    }
+  };
+  int64_t tag_offset = 0, np_global = 0;
+  if (nranks > 1 && !is_TL) {
+    // slab ownership by the GLOBAL stencil base of the particle (what the kernels use); cuts balance the particle count
+    GridH &g = *s.grid;
+    const double ih = 1.0 / g.cellsize; const bool lin = shape_function == KML_SHAPE_LINEAR;
+    auto base_of = [&](double x) { double t = (x - boxlo[0]) * ih; return lin ? (int)t : (int)(t - 1.0); };
+    std::vector<int64_t> hist(g.nx_global + 1, 0);
+    int last = -1; bool monotone = true;
+    lattice([&](const std::array<double, 3> &x) { int b = std::min(std::max(base_of(x[0]), 0), g.nx_global); if (b < last) monotone = false; last = b; hist[b]++; np_global++; });
+    if (!monotone) fatal("slab decomposition: the particle lattice is not ordered along x\n");
+    int base_lo, base_hi;
+    if (grid_pending) {
+      std::vector<int> cut(nranks + 1, 0); cut[nranks] = g.nx_global + 4;
+      int64_t cum = 0; int r = 1;
+      for (int b = 0; b <= g.nx_global && r < nranks; b++) { cum += hist[b]; while (r < nranks && cum >= (np_global * r) / nranks) cut[r++] = b + 1; }
+      base_lo = rank == 0 ? -4 : cut[rank]; base_hi = cut[rank + 1];
+      create_device_grid(g, base_lo, base_hi);
+    } else { base_lo = g.desc.base_lo; base_hi = g.desc.base_hi; }
+    for (int b = 0; b < std::min(std::max(base_lo, 0), g.nx_global + 1); b++) tag_offset += hist[b];
+    lattice([&](const std::array<double, 3> &x) { int b = base_of(x[0]); if (b >= base_lo && b < base_hi) s.x0.push_back(x); });
+  } else {
+    lattice([&](const std::array<double, 3> &x) { s.x0.push_back(x); });
+    np_global = (int64_t)s.x0.size();
   }
   s.np = (int64_t)s.x0.size();
   if (s.np == 0) fatal("Error: solid does not have any particles.\n");
@@ -475,12 +521,13 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   for (int64_t i = 0; i < s.np; i++) {
     if (axisymmetric) { mass[i] = mass_ * s.x0[i][0]; vol[i] = mass[i] / mat.rho0; }
     else { mass[i] = mass_; vol[i] = vol_; }
-    s.ptag[i] = i + 1 + np_total; // src/solid.cpp:2322
+    s.ptag[i] = tag_offset + i + 1 + np_total; // src/solid.cpp:2322 (tag_offset: particles of lower slabs)
   }
-  np_total += s.np; // domain->np_total += np, src/solid.cpp:2334
+  np_total += np_global; // domain->np_total += np, src/solid.cpp:2334
+  np_global_last = np_global; tag_offset_last = tag_offset;
 
   // upload; everything not set here starts at the values of src/solid.cpp:2283-2321 (F = R = I, J = 1, mask = 1, rest 0)
-  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = s.np; d.grid = s.grid->id; d.mat = mat;
+  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.mat = mat;
   check(kml_solid_create(ctx, &d, &s.dev));
   check(kml_solid_upload(ctx, s.dev, KML_P_PTAG, s.ptag.data()));
   check(kml_solid_upload(ctx, s.dev, KML_P_X, s.x0.data()));
@@ -523,7 +570,7 @@ Var Sim::cmd_group(std::vector<std::string> &a) {
     } else {
       GridH &g = *s.grid; const kml_grid_desc &d = g.desc; int64_t l = 0;
       for (int i = 0; i < d.n[0]; i++) for (int j = 0; j < d.n[1]; j++) for (int k = 0; k < d.n[2]; k++, l++) {
-        double x = d.lo[0] + i * d.h, y = dimension >= 2 ? d.lo[1] + j * d.h : 0, z = dimension == 3 ? d.lo[2] + k * d.h : 0; // node positions, src/grid.cpp:222-227
+        double x = d.lo[0] + (i + d.goff) * d.h, y = dimension >= 2 ? d.lo[1] + j * d.h : 0, z = dimension == 3 ? d.lo[2] + k * d.h : 0; // node positions, src/grid.cpp:222-227
         if (reg.match(x, y, z)) { g.mask[l] |= bit; n++; }
       }
       check(kml_grid_upload(ctx, g.id, KML_N_MASK, g.mask.data()));

@@ -119,6 +119,10 @@ public:
 
   // ---- device ----
   kml_ctx *ctx = nullptr; int device = 0;
+  // ---- slab decomposition over several GPUs (one process per GPU; replaces Universe/Domain sub-boxes) ----
+  int rank = 0, nranks = 1; std::vector<unsigned char> nccl_id; bool grid_pending = false;
+  int64_t np_global_last = 0, tag_offset_last = 0; // of the solid created last (for tests / reports)
+  void create_device_grid(GridH &g, int base_lo, int base_hi);
 
   // helpers
   int find_region(const std::string &n) const; int find_solid(const std::string &n) const; int find_material(const std::string &n) const;

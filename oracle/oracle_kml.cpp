@@ -216,13 +216,17 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   g->mask.assign(nn, 1); g->rigid.assign(nn, 0); g->ntype.resize(nn);
   int dim = c->c.dimension; int sf = c->c.shape_function; double h = d->h;
   int64_t l = 0;
-  for (int i = 0; i < g->nx; i++) for (int j = 0; j < g->ny; j++) for (int k = 0; k < g->nz; k++) {
+  // a slab of a decomposed grid keeps the node positions / types of the global grid (the oracle itself only ever
+  // steps undecomposed grids; slab grids are created by the host-logic tests of the partition)
+  const int goff = d->gn > 0 ? d->goff : 0, gnx = d->gn > 0 ? d->gn : g->nx;
+  for (int il = 0; il < g->nx; il++) for (int j = 0; j < g->ny; j++) for (int k = 0; k < g->nz; k++) {
+    const int i = il + goff;
     g->x0[l][0] = d->lo[0] + i * h;
     g->x0[l][1] = dim >= 2 ? d->lo[1] + j * h : 0;
     g->x0[l][2] = dim == 3 ? d->lo[2] + k * h : 0;
     if (sf == KML_SHAPE_LINEAR) g->ntype[l] = {0, 0, 0};
     else if (sf == KML_SHAPE_BERNSTEIN) g->ntype[l] = {i % 2, j % 2, k % 2};
-    else g->ntype[l] = {std::min(2, i) - std::min(g->nx - 1 - i, 2), std::min(2, j) - std::min(g->ny - 1 - j, 2),
+    else g->ntype[l] = {std::min(2, i) - std::min(gnx - 1 - i, 2), std::min(2, j) - std::min(g->ny - 1 - j, 2),
                         std::min(2, k) - std::min(g->nz - 1 - k, 2)};
     g->x[l] = g->x0[l]; g->v[l].setZero(); g->v_update[l].setZero(); g->f[l].setZero(); g->mb[l].setZero();
     l++;

@@ -178,7 +178,8 @@ set_dt(0.001)
 
 
 # C5: synthetic 3-D ULMPM elastoplastic block, cubic B-splines, at test size.
-def block(n=(8, 8, 8), scheme="musl", shape="cubic-spline", fixed_dt=False, a=2.5e-3, ppc=2, strength="plastic"):
+def block(n=(8, 8, 8), scheme="musl", shape="cubic-spline", fixed_dt=False, a=2.5e-3, ppc=2, strength="plastic", drift=0.0):
+    """drift: uniform x velocity added to the squeeze (moves particles across slab cuts in the multi-GPU tests)"""
     nx, ny, nz = n
     a_m, a_e = ("%e" % a).split("e")
     a_txt = "%s%s%+d" % (a_m.rstrip("0").rstrip("."), "e", int(a_e))  # e.g. 2.5e-3: the parser needs a signed exponent
@@ -205,7 +206,7 @@ a = {a_txt}
 cx = {4 + nx / 2}
 cy = {4 + ny / 2}
 cz = {4 + nz / 2}
-fix(v0, initial_velocity_particles, gall, -a*(x-cx), 0.5*a*(y-cy), 0.5*a*(z-cz))
+fix(v0, initial_velocity_particles, gall, {drift}-a*(x-cx), 0.5*a*(y-cy), 0.5*a*(z-cz))
 {"set_dt(0.2)" if fixed_dt else "dt_factor(0.5)"}
 """
 
