@@ -1,0 +1,119 @@
+"""Worker of the multi-rank tests (launched with torch.distributed.run, one process per slab).
+
+    partition  - CPU, gloo: every rank builds its slab of the block through the host driver (the oracle library is
+                 only the allocation back end here; nothing is stepped) and the ranks' particles are compared with the
+                 undecomposed population: tags, positions, counts, slab geometry.
+    step       - GPU, NCCL: the slab-decomposed CUDA engine steps a block that drifts across the slab cuts; the
+                 gathered particles are compared with the single-rank oracle run (1e-10, tags bit-exact).
+Prints "SLAB-OK ..." on rank 0 on success; any assertion fails the launcher.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from cases import block  # noqa: E402
+from karamelo_b200 import slab  # noqa: E402
+from karamelo_b200.api import Engine, P, load_host_library  # noqa: E402
+
+ORACLE_HOST_LIB = os.path.join(ROOT, "oracle", "_build", "libkml_host_oracle.so")
+
+
+def partition(args):
+    rank, world, _, dist = slab.init_distributed()
+    lib = load_host_library(ORACLE_HOST_LIB)
+    cells = tuple(args.cells)
+    script = block(cells, "musl", args.shape)
+    eng = slab.make_engine(lib, with_comm=False)
+    eng.script(script)
+    info = eng.slab_info(0)
+    mine = {f: eng.download(0, getattr(P, f)) for f in ("PTAG", "X", "V", "MASS")}
+    parts = [None] * world
+    dist.all_gather_object(parts, (info, mine))
+    if rank == 0:
+        ref = Engine(lib)
+        ref.script(script)
+        full = ref.snapshot(("PTAG", "X", "V", "MASS"))[0]
+        n_total = len(full["PTAG"])
+        infos = [p[0] for p in parts]
+        span = 2 if args.shape == "linear" else 4
+        # slabs tile the stencil-base axis without gaps or overlaps
+        for a, b in zip(infos[:-1], infos[1:]):
+            assert a["base_hi"] == b["base_lo"], (a, b)
+        for r, i in enumerate(infos):
+            assert i["np_global"] == n_total
+            assert i["goff"] == max(i["base_lo"], 0)
+            # the local node planes cover every stencil of the slab's particles
+            assert i["goff"] + i["nx_local"] >= min(i["base_hi"] + span - 1, i["goff"] + i["nx_local"])
+            assert i["own_lo"] == 0 and 0 < i["own_hi"] <= i["nx_local"]
+            if r < world - 1:  # shared planes = span - 1, owned by the right neighbour
+                assert i["nx_local"] - i["own_hi"] == span - 1, i
+        counts = [len(p[1]["PTAG"]) for p in parts]
+        assert sum(counts) == n_total
+        assert max(counts) - min(counts) <= 2 * 8 * cells[1] * cells[2], counts  # balanced to within two cell planes
+        # tags: every rank numbers its particles after those of the lower slabs (src/solid.cpp:2264-2275, :2322)
+        off = 0
+        for (i, m), c in zip(parts, counts):
+            assert i["tag_offset"] == off
+            assert (m["PTAG"] == np.arange(off + 1, off + c + 1)).all()
+            off += c
+        cat = {k: np.concatenate([p[1][k] for p in parts]) for k in mine}
+        order = np.argsort(cat["PTAG"], kind="stable")
+        # the lattice is generated i -> j -> k, x slowest, so tags follow x: the concatenation IS the undecomposed population
+        for k in cat:
+            assert (cat[k][order] == full[k]).all(), k
+        print("SLAB-OK partition world=%d counts=%s" % (world, counts))
+    dist.barrier()
+
+
+def step(args):
+    import torch
+    rank, world, _, dist = slab.init_distributed()
+    assert torch.cuda.is_available()
+    cells = tuple(args.cells)
+    script = block(cells, args.scheme, args.shape, a=2.5e-3, drift=args.drift)
+    fields = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "VOL")
+    eng = slab.make_engine(None)
+    eng.script(script)
+    np0 = eng.solid_info(0)["np"]
+    eng.line("run(%d)" % args.steps)
+    np1 = eng.solid_info(0)["np"]
+    st = eng.state()
+    got = slab.gather_snapshot(eng, fields)
+    moved = [None] * world
+    dist.all_gather_object(moved, (np0, np1))
+    flags = eng.error_flags()
+    eng.close()
+    if rank == 0:
+        from common import rel
+        ora = Engine(load_host_library(ORACLE_HOST_LIB))
+        ora.script(script + "\nrun(%d)\n" % args.steps)
+        ref = ora.snapshot(fields)[0]
+        st_ref = ora.state()
+        assert flags == 0
+        assert (got["PTAG"] == ref["PTAG"]).all(), "particle tags differ"
+        worst = {k: rel(got[k], ref[k]) for k in fields if k != "PTAG"}
+        bad = {k: v for k, v in worst.items() if v > 1e-10}
+        assert not bad, (bad, worst)
+        assert abs(st["dt"] - st_ref["dt"]) <= 1e-10 * st_ref["dt"] and st["ntimestep"] == st_ref["ntimestep"]
+        if args.drift:
+            assert any(a != b for a, b in moved), "no particle migrated: the test does not exercise exchange_particles"
+        print("SLAB-OK step world=%d np(before,after)=%s worst=%s" % (world, moved, worst))
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["partition", "step"])
+    ap.add_argument("--cells", type=int, nargs=3, default=[12, 6, 6])
+    ap.add_argument("--shape", default="cubic-spline")
+    ap.add_argument("--scheme", default="musl")
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--drift", type=float, default=0.0)
+    a = ap.parse_args()
+    {"partition": partition, "step": step}[a.mode](a)

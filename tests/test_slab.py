@@ -1,0 +1,66 @@
+"""Slab decomposition over several ranks (one process per GPU; replaces the reference's Universe / Domain sub-boxes,
+Grid::reduce_ghost_nodes src/grid.cpp:477-621,881-1132 and ULMPM::exchange_particles src/ulmpm.cpp:565-667).
+
+CPU (gloo, world_size 2 and 3): the host-side partition.  GPU (NCCL, >= 2 devices): stepping parity with the
+single-rank oracle, with particles migrating across the slab cuts.
+"""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def launch(world, args, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), WORKER] + args
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0 and "SLAB-OK" in p.stdout, p.stdout[-3000:] + "\n" + p.stderr[-3000:]
+    return p.stdout
+
+
+@pytest.mark.parametrize("world,shape", [(2, "cubic-spline"), (3, "cubic-spline"), (2, "linear")])
+def test_partition_cpu(oracle_lib, world, shape):
+    launch(world, ["partition", "--cells", "12", "5", "4", "--shape", shape])
+
+
+def test_thin_slab_is_rejected(oracle_lib):
+    """A slab thinner than the stencil overlap cannot own its shared planes: the host driver refuses the run."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), WORKER, "partition", "--cells", "4", "3", "3"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode != 0 and "thinner than the stencil" in (p.stdout + p.stderr)
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme,drift", [("musl", 0.03), ("usl", 0.0)])
+def test_two_slabs_match_single_rank_oracle(oracle_lib, scheme, drift):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    out = launch(2, ["step", "--cells", "12", "6", "6", "--scheme", scheme, "--drift", str(drift), "--steps", "100"])
+    print(out)
+
+
+@pytest.mark.gpu
+def test_four_slabs_match_single_rank_oracle(oracle_lib):
+    if _ngpu() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    print(launch(4, ["step", "--cells", "24", "6", "6", "--scheme", "musl", "--drift", "0.03", "--steps", "100"]))
