@@ -7,7 +7,7 @@
 // every one of their 64 node reads is an LDS.128 pair instead of an L1/L2 round trip.  Arithmetic per
 // particle is the same as the generic kernels (k_g2p / k_stress) - same (i,j,k) summation order.
 #pragma once
-#include "kml_p2g_cell.cuh"
+#include "kml_p2g_cell3.cuh"
 
 namespace kml {
 
@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(128) k_gather_cell(SolidDev s, GridDev g, Step
             L[6] += rec.z * wfd0; L[7] += rec.z * wfd1; L[8] += rec.z * wfd2;
           }
         }
-      particle_stress<false>(s, g, sp, mat, ip, L, qv, wave, hr);
+      PState ps; ps.load(s, mat, sp, ip);
+      particle_stress<false>(s, g, sp, mat, ip, ps, L, qv, wave, hr);
     } else {
       double vu[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
 #pragma unroll

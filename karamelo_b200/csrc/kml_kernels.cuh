@@ -180,7 +180,8 @@ __global__ void k_grid_zero_v(GridDev g, int zero_mass) {
 
 // tail of G2P for one particle: a_p, x_p += dt v~_p, FLIP/PIC blend (src/solid.cpp:613-616, :786-796)
 template <bool TL>
-__device__ __forceinline__ void particle_advance(const SolidDev &s, const StepParams &sp, long long ip, const double *vu, const double *a, double Tp) {
+__device__ __forceinline__ void particle_advance(const SolidDev &s, const StepParams &sp, long long ip, const double *vu, const double *a, double Tp,
+                                                 const double *vold = nullptr) { // vold: the particle's velocity if the caller already loaded it
   const double inv_dt = 1.0 / sp.dt;
   double xnew[3];
 #pragma unroll
@@ -188,7 +189,7 @@ __device__ __forceinline__ void particle_advance(const SolidDev &s, const StepPa
     const double ad = a[d] * inv_dt;
     const double xo = s.x[d][ip];
     xnew[d] = xo + sp.dt * vu[d];
-    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * (s.v[d][ip] + sp.dt * ad);
+    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * ((vold ? vold[d] : s.v[d][ip]) + sp.dt * ad);
     if (TL) s.x[d][ip] = xnew[d]; else s.xn[d][ip] = xnew[d];
   }
   if (sp.temp) s.T[ip] = Tp;
@@ -234,13 +235,37 @@ struct StressParams {
 // Everything after the velocity-gradient gather for one particle: F update, J, vol, D (R for TL), the
 // constitutive update and the particle's CFL wave speed (src/solid.cpp:1155-1438, :2810-2839).
 // L is the gathered velocity gradient (Fdot for TL); qv the gathered -grad(T).
+// The particle state the stress update reads; loading it is separate from the update so that callers can put the
+// loads in flight before the velocity-gradient gather.
+struct PState {
+  double F[9], sig[6], eel[6], vol0, rho0, eps, epsdot, dmg, dmgi, T, v[3];
+  __device__ __forceinline__ void load(const SolidDev &s, const kml_material &mat, const StepParams &sp, long long ip) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = s.F[i][ip];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { sig[i] = s.sig[i][ip]; eel[i] = s.eel[i][ip]; }
+    vol0 = s.vol0[ip]; rho0 = s.rho0[ip]; dmg = s.dmg[ip];
+#pragma unroll
+    for (int i = 0; i < 3; i++) v[i] = s.v[i][ip];
+    eps = epsdot = dmgi = T = 0.0;
+    if (mat.type == KML_MAT_EOS_STRENGTH) {
+      eps = s.eps[ip]; epsdot = s.epsdot[ip];
+      if (mat.damage_type != KML_DAMAGE_NONE) dmgi = s.dmgi[ip];
+      if (mat.cp != 0 || sp.temp) T = s.T[ip];
+    }
+  }
+};
+__device__ __forceinline__ void sym_to_full(const double *a, double *m) { // (xx,yy,zz,xy,xz,yz) -> row-major 3x3
+  m[0] = a[0]; m[1] = a[3]; m[2] = a[4]; m[3] = a[3]; m[4] = a[1]; m[5] = a[5]; m[6] = a[4]; m[7] = a[5]; m[8] = a[2];
+}
+
 template <bool TL>
 __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev &g, const StepParams &sp, const kml_material &mat, long long ip,
-                                                double *L, const double *qv, double &wave, double &hr) {
+                                                const PState &ps, double *L, const double *qv, double &wave, double &hr) {
   const double dt = sp.dt;
   double F[9], Fn[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) F[i] = s.F[i][ip];
+  for (int i = 0; i < 9; i++) F[i] = ps.F[i];
   if (TL) {
 #pragma unroll
     for (int i = 0; i < 9; i++) Fn[i] = F[i] + dt * L[i]; // here L holds Fdot
@@ -255,12 +280,12 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
   for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
   double Finv[9]; inv3(Fn, Finv);
   const double J = det3(Fn);
-  const double vol0 = s.vol0[ip];
+  const double vol0 = ps.vol0;
   const double vol = J * vol0;
   s.vol[ip] = vol;
-  const double damage_old = s.dmg[ip];
+  const double damage_old = ps.dmg;
   if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);
-  const double rho = s.rho0[ip] / J;
+  const double rho = ps.rho0 / J;
   double D[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   if (mat.type != KML_MAT_NEO_HOOKEAN) {
     if (TL) {
@@ -284,7 +309,7 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     }
   }
   double sig[9], eel[9];
-  load_sym(s.sig, ip, sig); load_sym(s.eel, ip, eel);
+  sym_to_full(ps.sig, sig); sym_to_full(ps.eel, eel);
   double damage = damage_old;
   if (mat.type == KML_MAT_LINEAR) {
     const double tr = dt * D[0] + dt * D[4] + dt * D[8];
@@ -312,14 +337,14 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     for (int i = 0; i < 9; i++) eel[i] = 0.5 * C[i];
   } else { // EOS + strength (+ damage, + plastic-work heating): src/solid.cpp:1292-1374
     const bool thermal = mat.cp != 0;
-    const double T = thermal ? s.T[ip] : 0.0;
+    const double T = thermal ? ps.T : 0.0;
     const double trD = D[0] + D[4] + D[8];
     double ien;
     double pH = eos_pressure(mat, ien, J, rho, damage, trD, g.cellsize, T);
     s.ien[ip] = ien;
     if (thermal) pH += mat.tmp_alpha * (mat.tmp_T0 - T);
     double sdev[9], dep;
-    double eps = s.eps[ip], epsdot = s.epsdot[ip];
+    double eps = ps.eps, epsdot = ps.epsdot;
     strength_dev(mat, dt, sig, D, sdev, dep, eps, epsdot, damage, T);
     eps += dep;
     const double tav = 1000 * g.cellsize / mat.signal_velocity;
@@ -328,8 +353,8 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     epsdot = (0.0 > epsdot) ? 0.0 : epsdot;
     s.eps[ip] = eps; s.epsdot[ip] = epsdot;
     if (mat.damage_type != KML_DAMAGE_NONE) {
-      double di = s.dmgi[ip];
-      damage_jc(mat, di, damage, pH, sdev, epsdot, dep, sp.temp ? s.T[ip] : 0.0);
+      double di = ps.dmgi;
+      damage_jc(mat, di, damage, pH, sdev, epsdot, dep, sp.temp ? ps.T : 0.0);
       s.dmgi[ip] = di; s.dmg[ip] = damage;
     }
     if (thermal) {
@@ -340,9 +365,9 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     }
     const double pf = (damage == 0 || pH >= 0) ? -pH : -pH * (1.0 - damage);
     const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) / 3.0;
-    const double Gd = (damage > 1e-10) ? mat.G * (1 - damage) : mat.G;
+    const double iGd = 1.0 / ((damage > 1e-10) ? mat.G * (1 - damage) : mat.G); // one reciprocal instead of nine FP64 divisions
 #pragma unroll
-    for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] / Gd; }
+    for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] * iGd; }
     sig[0] += pf; sig[4] += pf; sig[8] += pf;
     eel[0] += te; eel[4] += te; eel[8] += te;
   }
@@ -360,7 +385,7 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     for (int b = 0; b < 3; b++) s.q[b][ip] = qv[b] * c;
   }
   if (!(damage >= 1.0)) { // wave speed for the CFL limit, src/solid.cpp:1378-1385
-    const double vx = fabs(s.v[0][ip]), vy = fabs(s.v[1][ip]), vz = fabs(s.v[2][ip]);
+    const double vx = fabs(ps.v[0]), vy = fabs(ps.v[1]), vz = fabs(ps.v[2]);
     wave = sqrt((mat.K + KML_FOUR_THIRD * mat.G) / rho) + fmax(fmax(vx, vy), vz);
     if (isnan(wave)) { atomicOr(sp.flags, 4u); wave = 0; }
     if (TL) { double e; if (eig3_min_abs_real(Fn, e)) hr = fmin(hr, e); }
@@ -396,7 +421,8 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
       const double xr = TL ? s.x0[0][ip] : (tp.moved ? s.xn[0][ip] : s.x[0][ip]);
       L[8] += hoop / xr; // the reference divides term by term; same value up to rounding
     }
-    particle_stress<TL>(s, g, sp, mat, ip, L, qv, wave, hr);
+    PState ps; ps.load(s, mat, sp, ip);
+    particle_stress<TL>(s, g, sp, mat, ip, ps, L, qv, wave, hr);
   }
   // block reduction -> one atomic per warp
 #pragma unroll

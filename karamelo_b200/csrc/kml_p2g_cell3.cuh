@@ -1,0 +1,260 @@
+// kml_p2g_cell3.cuh - cell-centric particle-to-grid, third generation (3-D cubic B-splines, ULMPM).
+//
+// Same decomposition as kml_p2g_cell.cuh (a lane group walks a column of cells along k and keeps a
+// sliding 4-plane window of node sums in registers; only completed planes go to the grid as fp64 RED),
+// rebuilt around the instruction budget of the FP64 pipe, which co-bounds this stage:
+//   * every lane stages ONE particle per round (all 24 weights, m*v, vol*sigma) - no half-idle staging;
+//   * interior columns evaluate the cubic B-spline pieces branch-free (node a of the stencil always lies in
+//     the same interval of src/basis_functions.h:40-104); boundary columns keep the reference's branches;
+//   * the raw data of the next round is loaded before the current round is accumulated (register prefetch);
+//   * a lane may own NB = 2 node columns (8-lane groups): half the shared-memory traffic per FP64 FMA;
+//   * no FP64 compares in the emit path (an integer dirty mask tracks non-empty planes).
+// Arithmetic per (particle, node) is that of src/solid.cpp:317-335, :337-390, :482-522; the summation
+// order differs (tolerance 1e-10, tests/test_parity_gpu.py).
+#pragma once
+#include "kml_p2g_cell.cuh"
+
+namespace kml {
+
+// the four cubic B-spline pieces of an interior stencil (ntype 0 everywhere): node a sees r in [1-a, 2-a)
+__device__ __forceinline__ void cubic_piece(int a, double r, double ih, double &w, double &dw) {
+  if (a == 0) { w = ((-1.0 / 6.0 * r + 1) * r - 2) * r + 4.0 / 3.0; dw = ih * ((-0.5 * r + 2) * r - 2); }
+  else if (a == 1) { w = (0.5 * r - 1) * r * r + 2.0 / 3.0; dw = ih * (3.0 / 2.0 * r - 2) * r; }
+  else if (a == 2) { w = (-0.5 * r - 1) * r * r + 2.0 / 3.0; dw = ih * (-3.0 / 2.0 * r - 2) * r; }
+  else { w = ((1.0 / 6.0 * r + 1) * r + 2) * r + 4.0 / 3.0; dw = ih * ((0.5 * r + 2) * r + 2); }
+}
+
+// (w, dw) of the 4 stencil nodes i0..i0+3 (LOCAL indices) of one axis; interior = all four nodes exist and have ntype 0
+template <bool DERIV>
+__device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, double ih, int i0, int n, int goff, int gn, bool interior, double (&w)[4], double (&dw)[4]) {
+  if (interior) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double xn = __dadd_rn(lo, __dmul_rn((double)(i0 + a + goff), h));
+      const double r = __dmul_rn(__dsub_rn(xp, xn), ih);
+      cubic_piece(a, r, ih, w[a], dw[a]);
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; a++) cubic_node(xp, lo, h, ih, i0 + a, n, goff, gn, w[a], dw[a]);
+  }
+  (void)DERIV;
+}
+__device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) {
+  const int ig = i0 + goff;
+  return i0 >= 0 && i0 + 3 < n && ig >= 2 && ig + 3 <= gn - 3;
+}
+
+// Staged particle record (doubles).  FULL:  [0..7] x (w,dw)x4  [8..15] y (w,dw)x4  [16..19] z w  [20..23] z dw
+//                                           [24..27] m, m*vx, m*vy, m*vz  [28..33] vol*sigma (xx,yy,zz,xy,xz,yz)  [34] cell plane k
+//                                    !FULL: [0..3] x w  [4..7] y w  [8..11] z w  [12..14] m*v  [15] cell plane k
+template <bool FULL> struct Rec3 { static constexpr int N = FULL ? 36 : 16; static constexpr int K = FULL ? 34 : 15; };
+
+template <bool FULL, bool MASS, int NB>
+__global__ void __launch_bounds__(128, FULL ? (NB == 2 ? 2 : 3) : (NB == 4 ? 3 : 4))
+k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
+  constexpr int Q = FULL ? 7 : 3;
+  constexpr int GL = 16 / NB;          // lanes per group = particles per staging round
+  constexpr int GPB = 128 / GL;        // groups per block
+  constexpr int REC = Rec3<FULL>::N;
+  constexpr int GSTRIDE = GL * REC + (NB == 1 ? 8 : (NB == 2 ? 4 : 2)); // the groups of one warp start at different bank offsets (64 / 32 / 16 B apart)
+  __shared__ __align__(16) double stage[GPB * GSTRIDE];
+
+  const int lg = threadIdx.x % GL;
+  const int a = lg / (4 / NB), b0 = (lg % (4 / NB)) * NB;
+  const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u)) << ((threadIdx.x & 31) / GL * GL);
+  double *rec0 = stage + (threadIdx.x / GL) * GSTRIDE;
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GL;
+  const long long ncol = (long long)g.n[0] * g.n[1];
+  // consecutive groups = consecutive columns (j fastest) of the SAME segment: the groups of a warp carry equal work
+  // and the planes a block emits overlap in L2
+  const int seg = (int)(group / ncol); const long long col = group % ncol;
+  if (seg >= nseg) return;
+  const int i0 = (int)(col / g.n[1]), j0 = (int)(col % g.n[1]);
+  const int kbeg = seg * seglen, kend = min(kbeg + seglen, g.n[2]);
+  if (kbeg >= kend) return;
+  const long long cellbase = col * g.n[2];
+  const int pbeg = start[cellbase + kbeg], pend = start[cellbase + kend];
+  if (pbeg == pend) return; // no particle in the whole segment (uniform per group)
+
+  const int ni = i0 + a;
+  const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
+  const double h = g.h, ih = g.inv_cellsize;
+
+  double acc[NB][4][Q];
+#pragma unroll
+  for (int e = 0; e < NB; e++)
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int q = 0; q < Q; q++) acc[e][c][q] = 0.0;
+
+  auto emit0 = [&](int kk) { // add plane kk (window slot 0) to the grid
+    if (kk >= g.n[2] || ni >= g.n[0]) return;
+#pragma unroll
+    for (int e = 0; e < NB; e++) {
+      const int nj = j0 + b0 + e;
+      if (nj >= g.n[1]) continue;
+      const long long node = ((long long)ni * g.n[1] + nj) * g.n[2] + kk;
+      double4 *rec = &g.nv[node];
+      if (FULL) {
+        if (MASS) atomicAdd(&rec->w, acc[e][0][0]);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { atomicAdd(comp_ptr(rec, d), acc[e][0][1 + d]); atomicAdd(&g.f[d][node], acc[e][0][4 + d]); }
+      } else {
+#pragma unroll
+        for (int d = 0; d < 3; d++) atomicAdd(comp_ptr(rec, d), acc[e][0][d]);
+      }
+    }
+  };
+  auto slide = [&]() {
+#pragma unroll
+    for (int e = 0; e < NB; e++)
+#pragma unroll
+      for (int q = 0; q < Q; q++) { acc[e][0][q] = acc[e][1][q]; acc[e][1][q] = acc[e][2][q]; acc[e][2][q] = acc[e][3][q]; acc[e][3][q] = 0.0; }
+  };
+
+  // raw particle data of one staging round, one particle per lane
+  double rx = 0, ry = 0, rz = 0, rm = 0, rv0 = 0, rv1 = 0, rv2 = 0, rvol = 0, rs[6] = {0, 0, 0, 0, 0, 0};
+  auto load_raw = [&](int p) {
+    const int ip = order[p];
+    rx = s.x[0][ip]; ry = s.x[1][ip]; rz = s.x[2][ip]; rm = s.mass[ip];
+    rv0 = s.v[0][ip]; rv1 = s.v[1][ip]; rv2 = s.v[2][ip];
+    if (FULL) {
+      rvol = s.vol[ip];
+#pragma unroll
+      for (int e = 0; e < 6; e++) rs[e] = s.sig[e][ip];
+    }
+  };
+  auto stage_raw = [&]() { // weights + products of the lane's particle -> its record
+    double *r = rec0 + lg * REC;
+    const int k0 = cell_axis(rz, g.lo[2], ih, g.n[2], 0);
+    const bool int_z = cubic_interior(k0, g.n[2], 0, g.n[2]);
+    double w[4], dw[4];
+    cubic_axis4<FULL>(rx, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, w, dw);
+    if (FULL) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) *(double2 *)(r + 2 * t) = make_double2(w[t], dw[t]);
+    } else { *(double2 *)(r + 0) = make_double2(w[0], w[1]); *(double2 *)(r + 2) = make_double2(w[2], w[3]); }
+    cubic_axis4<FULL>(ry, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, w, dw);
+    if (FULL) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) *(double2 *)(r + 8 + 2 * t) = make_double2(w[t], dw[t]);
+    } else { *(double2 *)(r + 4) = make_double2(w[0], w[1]); *(double2 *)(r + 6) = make_double2(w[2], w[3]); }
+    cubic_axis4<FULL>(rz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, w, dw);
+    if (FULL) {
+      *(double2 *)(r + 16) = make_double2(w[0], w[1]); *(double2 *)(r + 18) = make_double2(w[2], w[3]);
+      *(double2 *)(r + 20) = make_double2(dw[0], dw[1]); *(double2 *)(r + 22) = make_double2(dw[2], dw[3]);
+      *(double2 *)(r + 24) = make_double2(rm, rm * rv0); *(double2 *)(r + 26) = make_double2(rm * rv1, rm * rv2);
+      *(double2 *)(r + 28) = make_double2(rvol * rs[0], rvol * rs[1]); *(double2 *)(r + 30) = make_double2(rvol * rs[2], rvol * rs[3]);
+      *(double2 *)(r + 32) = make_double2(rvol * rs[4], rvol * rs[5]);
+      *(double2 *)(r + 34) = make_double2(__longlong_as_double((long long)k0), 0.0);
+    } else {
+      *(double2 *)(r + 8) = make_double2(w[0], w[1]); *(double2 *)(r + 10) = make_double2(w[2], w[3]);
+      *(double2 *)(r + 12) = make_double2(rm * rv0, rm * rv1);
+      *(double2 *)(r + 14) = make_double2(rm * rv2, __longlong_as_double((long long)k0));
+    }
+  };
+
+  int kcur = kbeg, dirty = 0;
+  int p = pbeg;
+  if (p + lg < pend) load_raw(p + lg);
+  while (p < pend) {
+    const int n = min(GL, pend - p);
+    if (lg < n) stage_raw();
+    __syncwarp(gmask);
+    const int pn = p + n;
+    if (pn + lg < pend) load_raw(pn + lg); // in flight while this round is accumulated
+    for (int q = 0; q < n; q++) {
+      const double *r = rec0 + q * REC;
+      const int kq = (int)__double_as_longlong(r[Rec3<FULL>::K]);
+      if (kq != kcur) { // group-uniform: slide the window up to the particle's cell, emitting completed planes
+        while (kcur < kq && dirty) { if (dirty & 1) emit0(kcur); slide(); dirty >>= 1; kcur++; }
+        kcur = kq;
+      }
+      dirty = 0xF;
+      if (FULL) {
+        const double2 X = *(const double2 *)(r + 2 * a);
+        const double2 Z01 = *(const double2 *)(r + 16), Z23 = *(const double2 *)(r + 18);
+        const double2 D01 = *(const double2 *)(r + 20), D23 = *(const double2 *)(r + 22);
+        const double2 MM = *(const double2 *)(r + 24), MV = *(const double2 *)(r + 26);
+        const double2 A01 = *(const double2 *)(r + 28), A23 = *(const double2 *)(r + 30), A45 = *(const double2 *)(r + 32);
+        const double wz[4] = {Z01.x, Z01.y, Z23.x, Z23.y}, dwz[4] = {D01.x, D01.y, D23.x, D23.y};
+#pragma unroll
+        for (int e = 0; e < NB; e++) {
+          const double2 Y = *(const double2 *)(r + 8 + 2 * (b0 + e));
+          const double gxy = X.x * Y.x, gx = X.y * Y.x, gy = X.x * Y.y;
+          const double mm = gxy * MM.x, M0 = gxy * MM.y, M1 = gxy * MV.x, M2 = gxy * MV.y;
+          // A = (xx,yy,zz,xy,xz,yz): f_x = -(xx gx + xy gy) wz - xz gxy dwz, ...
+          const double P0 = -(A01.x * gx + A23.y * gy), P1 = -(A23.y * gx + A01.y * gy), P2 = -(A45.x * gx + A45.y * gy);
+          const double Q0 = -(A45.x * gxy), Q1 = -(A45.y * gxy), Q2 = -(A23.x * gxy);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            double *ac = acc[e][c];
+            ac[0] += mm * wz[c];
+            ac[1] += M0 * wz[c]; ac[2] += M1 * wz[c]; ac[3] += M2 * wz[c];
+            ac[4] = fma(Q0, dwz[c], fma(P0, wz[c], ac[4])); // two FMAs per component (a sum of products would cost three FP64 instructions)
+            ac[5] = fma(Q1, dwz[c], fma(P1, wz[c], ac[5])); ac[6] = fma(Q2, dwz[c], fma(P2, wz[c], ac[6]));
+          }
+        }
+      } else {
+        const double X = r[a];
+        const double2 Z01 = *(const double2 *)(r + 8), Z23 = *(const double2 *)(r + 10);
+        const double2 V01 = *(const double2 *)(r + 12); const double V2 = r[14];
+        const double wz[4] = {Z01.x, Z01.y, Z23.x, Z23.y};
+#pragma unroll
+        for (int e = 0; e < NB; e++) {
+          const double gxy = X * r[4 + b0 + e];
+          const double M0 = gxy * V01.x, M1 = gxy * V01.y, M2 = gxy * V2;
+#pragma unroll
+          for (int c = 0; c < 4; c++) { double *ac = acc[e][c]; ac[0] += M0 * wz[c]; ac[1] += M1 * wz[c]; ac[2] += M2 * wz[c]; }
+        }
+      }
+    }
+    __syncwarp(gmask);
+    p = pn;
+  }
+  // the node planes still in the window
+  while (dirty) { if (dirty & 1) emit0(kcur); slide(); dirty >>= 1; kcur++; }
+}
+
+// returns 0 = launched, -1 = combination not covered (caller uses the atomic kernel), 1 = CUDA error
+// segments of (almost) equal length, at most `target` cells long
+inline void cell_segments(int n2, int target, int *seglen, int *nseg) {
+  *nseg = (n2 + target - 1) / target; *seglen = (n2 + *nseg - 1) / *nseg;
+}
+
+// returns 0 = launched, -1 = combination not covered (caller uses the atomic kernel), 1 = CUDA error
+template <int NB>
+inline int cell_p2g3_launch_nb(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int seg_target, cudaStream_t st) {
+  const bool full = (what & P2G_FORCE) != 0;
+  constexpr int GL = 16 / NB;
+  int seglen, nseg; cell_segments(g.n[2], seg_target, &seglen, &nseg);
+  const long long ngroups = (long long)g.n[0] * g.n[1] * nseg;
+  const long long nb = (ngroups * GL + 127) / 128;
+  if (nb >= (1ll << 31)) return -1;
+  if (full) {
+    if (NB == 4) return -1;
+    if (what & P2G_MASS) k_p2g_cell3<true, true, NB == 4 ? 1 : NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+    else k_p2g_cell3<true, false, NB == 4 ? 1 : NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+  } else k_p2g_cell3<false, false, NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+  return cudaGetLastError() != cudaSuccess;
+}
+
+// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4)
+inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int seg_target, cudaStream_t st, int *nlaunch) {
+  *nlaunch = 0;
+  const bool full = (what & P2G_FORCE) != 0;
+  if (what & (P2G_MB | P2G_TEMP | P2G_HEAT)) return -1;
+  if (full && !(what & P2G_MOM)) return -1;
+  if (!full && (what & P2G_MASS)) return -1; // mass-only / mass+momentum passes (USF) use the atomic kernel
+  if (!full && !(what & P2G_MOM)) return -1;
+  int rc;
+  if (full) rc = nb_full == 2 ? cell_p2g3_launch_nb<2>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1>(s, g, cl, what, seg_target, st);
+  else rc = nb_mom == 4 ? cell_p2g3_launch_nb<4>(s, g, cl, what, seg_target, st)
+          : (nb_mom == 2 ? cell_p2g3_launch_nb<2>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1>(s, g, cl, what, seg_target, st));
+  if (rc == 0) *nlaunch = 1;
+  return rc;
+}
+
+} // namespace kml
