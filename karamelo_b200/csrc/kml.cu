@@ -42,7 +42,7 @@ struct kml_ctx {
   void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
   bool tl_mass_done = false;
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
-  bool use_cell_p2g = true; int p2g_version = 3, p2g_nb = 1, v2g_nb = 4, gather_version = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic|v2|v3, KML_P2G_NB, KML_V2G_NB, KML_GATHER=v1|v2, KML_SEGLEN, KML_GATHER_THREADS, KML_STRESS_BLOCKS
+  bool use_cell_p2g = true; int p2g_version = 3, p2g_nb = 1, v2g_nb = 2, p2g_pipe = 0, gather_version = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic|v2|v3, KML_P2G_NB, KML_V2G_NB, KML_GATHER=v1|v2, KML_SEGLEN, KML_GATHER_THREADS, KML_STRESS_BLOCKS
   Comm comm;
   // profiling
   bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
@@ -128,11 +128,13 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (e && !strcmp(e, "v2")) c->p2g_version = 2;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
-  { const int v = env_int("KML_V2G_NB", 4); c->v2g_nb = (v == 1 || v == 2) ? v : 4; }
+  { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
+  c->p2g_pipe = env_int("KML_P2G_PIPE", 0) ? 1 : 0;
   e = getenv("KML_GATHER"); if (e && !strcmp(e, "v1")) c->gather_version = 1;
   c->gtune.seg_target = std::min(std::max(env_int("KML_SEGLEN", 32), 8), 96);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;
-  c->gtune.stress_blocks = env_int("KML_STRESS_BLOCKS", 2) == 3 ? 3 : 2;
+  { const int v = env_int("KML_STRESS_BLOCKS", 3); c->gtune.stress_blocks = (v == 2 || v == 4) ? v : 3; }
+  c->gtune.stress_version = env_int("KML_STRESS", 3) == 2 ? 2 : 3;
   *out = c; return 0;
 }
 
@@ -499,7 +501,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
       const int rc = c->p2g_version == 2 ? cell_p2g_launch(S->s, g, G->cl, what, c->stream, &nl)   // -1: combination not covered -> atomic kernel
-                                         : cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl);
+                                         : cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->p2g_pipe, c->gtune.seg_target, c->stream, &nl);
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }

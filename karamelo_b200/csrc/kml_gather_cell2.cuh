@@ -128,8 +128,103 @@ k_gather_cell2(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materi
   }
 }
 
+// ---- velocity gradient + F + stress, third generation: asynchronous staging ----------------------------------
+// Same tile / thread-per-particle scheme, but nothing on the memory side goes through registers: the node tile is
+// filled with 16-byte cp.async copies, and every thread streams the 29-31 state doubles of its NEXT particle into a
+// private shared-memory slot (8-byte cp.async) while it runs the constitutive update of the current one.  The register file only holds
+// the weights, the gather accumulators and the constitutive update, so the kernel fits 168 registers (3 x 128 or
+// 6 x 64 threads per SM) without the 60-register prefetch of k_gather_cell2<true>.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_stress_cell3(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
+               int seglen, int nseg) {
+  extern __shared__ __align__(16) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state
+  const int TLEN = seglen + 3;
+  double *tile = smem3;
+  double *state = smem3 + (size_t)16 * TLEN * 4;
+  const int tid = threadIdx.x;
+  const long long col = blockIdx.x / nseg; const int seg = (int)(blockIdx.x % nseg);
+  const int i0 = (int)(col / g.n[1]), j0 = (int)(col % g.n[1]);
+  const int kbeg = seg * seglen, kend = min(kbeg + seglen, g.n[2]);
+  const long long cellbase = col * g.n[2];
+  const int pbeg = start[cellbase + kbeg], pend = start[cellbase + kend];
+  if (pbeg == pend) return; // block-uniform
+
+  int p = pbeg + tid;
+  int ip = p < pend ? order[p] : -1;
+  int ipn = p + THREADS < pend ? order[p + THREADS] : -1;
+  // node tile: 16 rows, contiguous along k in global memory
+  const double4 *__restrict__ src0 = tp.doublemapping ? g.nv : g.nvu;
+  for (int e = tid; e < 16 * TLEN; e += THREADS) {
+    const int row = e / TLEN, t = e - row * TLEN;
+    const int ni = i0 + (row >> 2), nj = j0 + (row & 3), nk = kbeg + t;
+    double *d = tile + (size_t)e * 4;
+    if (ni < g.n[0] && nj < g.n[1] && nk < g.n[2]) {
+      const double4 *src = &src0[((long long)ni * g.n[1] + nj) * g.n[2] + nk];
+      cp_async16(d, src); cp_async16(d + 2, (const double *)src + 2);
+    } else { *(double2 *)d = make_double2(0.0, 0.0); *(double2 *)(d + 2) = make_double2(0.0, 0.0); }
+  }
+  double px = 0, py = 0, pz = 0;
+  if (ip >= 0) { px = s.x[0][ip]; py = s.x[1][ip]; pz = s.x[2][ip]; pstate_issue_async(state + tid, THREADS, s, mat, sp, ip); }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+
+  const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
+  const double h = g.h, ih = g.inv_cellsize;
+  double wave = 0, hr = 1.0;
+  while (ip >= 0) {
+    // next particle of this thread: position to registers now, state to shared memory once the slot is read
+    const int pn = p + THREADS;
+    double nx = 0, ny = 0, nz = 0;
+    if (ipn >= 0) { nx = s.x[0][ipn]; ny = s.x[1][ipn]; nz = s.x[2][ipn]; }
+    const int ipnn = pn + THREADS < pend ? order[pn + THREADS] : -1;
+
+    const int k0 = cell_axis(pz, g.lo[2], ih, g.n[2], 0);
+    const int koff = k0 - kbeg;
+    const bool int_z = cubic_interior(k0, g.n[2], 0, g.n[2]);
+    double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    {
+      double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
+      cubic_axis4<true>(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dwx);
+      cubic_axis4<true>(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dwy);
+      cubic_axis4<true>(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, wz, dwz);
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0}, B1[3] = {0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const double *row = tile + ((size_t)(a * 4 + b) * TLEN + koff) * 4;
+          double A[3] = {0, 0, 0}, B[3] = {0, 0, 0};
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const double2 vxy = *(const double2 *)(row + 4 * c); const double vz = row[4 * c + 2];
+            A[0] = fma(wz[c], vxy.x, A[0]); A[1] = fma(wz[c], vxy.y, A[1]); A[2] = fma(wz[c], vz, A[2]);
+            B[0] = fma(dwz[c], vxy.x, B[0]); B[1] = fma(dwz[c], vxy.y, B[1]); B[2] = fma(dwz[c], vz, B[2]);
+          }
+#pragma unroll
+          for (int d = 0; d < 3; d++) { A1[d] = fma(wy[b], A[d], A1[d]); A2[d] = fma(dwy[b], A[d], A2[d]); B1[d] = fma(wy[b], B[d], B1[d]); }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) { L[3 * d] = fma(dwx[a], A1[d], L[3 * d]); L[3 * d + 1] = fma(wx[a], A2[d], L[3 * d + 1]); L[3 * d + 2] = fma(wx[a], B1[d], L[3 * d + 2]); }
+      }
+    }
+    PState ps;
+    pstate_from_smem(ps, state + tid, THREADS, mat, sp);
+    if (ipn >= 0) pstate_issue_async(state + tid, THREADS, s, mat, sp, ipn); // the slot is free again: stream the next particle's state
+    cp_async_commit();
+    const double qv[3] = {0, 0, 0};
+    particle_stress<false>(s, g, sp, mat, ip, ps, L, qv, wave, hr);
+    cp_async_wait_all(); // the next particle's state has had the constitutive update to arrive
+    p = pn; ip = ipn; ipn = ipnn; px = nx; py = ny; pz = nz;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wave = fmax(wave, __shfl_xor_sync(0xffffffffu, wave, o));
+  if ((threadIdx.x & 31) == 0 && wave > 0) atomic_max_pos(tp.max_wave, wave);
+}
+
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
-struct GatherTune { int seg_target = 32, threads = 64, stress_blocks = 2; };
+struct GatherTune { int seg_target = 32, threads = 64, stress_blocks = 3, stress_version = 3; };
 inline int cell_gather2_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
                                const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
   if (sp.axisymmetric || sp.temp || !cl.valid) return -1;
@@ -143,6 +238,19 @@ inline int cell_gather2_launch(bool stress, const SolidDev &s, const GridDev &g,
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
     kern<<<(unsigned)nblocks, THREADS, smem, st>>>(s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);                           \
   } while (0)
+  if (stress && tune.stress_version == 3) {
+    const size_t smem3 = sizeof(double) * (16 * (size_t)(seglen + 3) * 4 + PSTATE_SLOTS * (size_t)tune.threads);
+#define KML_STRESS3_LAUNCH(THREADS, MINB)                                                                                          \
+  do {                                                                                                                             \
+    auto kern = k_stress_cell3<THREADS, MINB>;                                                                                     \
+    if (smem3 > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) != cudaSuccess) return 1; \
+    kern<<<(unsigned)nblocks, THREADS, smem3, st>>>(s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);                          \
+  } while (0)
+    if (tune.threads == 64) { if (tune.stress_blocks == 4) KML_STRESS3_LAUNCH(64, 8); else if (tune.stress_blocks == 3) KML_STRESS3_LAUNCH(64, 6); else KML_STRESS3_LAUNCH(64, 4); }
+    else { if (tune.stress_blocks == 4) KML_STRESS3_LAUNCH(128, 4); else if (tune.stress_blocks == 3) KML_STRESS3_LAUNCH(128, 3); else KML_STRESS3_LAUNCH(128, 2); }
+#undef KML_STRESS3_LAUNCH
+    return cudaGetLastError() != cudaSuccess;
+  }
   if (tune.threads == 64) {
     if (stress && tune.stress_blocks == 3) KML_GATHER2_LAUNCH(true, 64, 6);
     else if (stress) KML_GATHER2_LAUNCH(true, 64, 4);

@@ -255,6 +255,54 @@ struct PState {
     }
   }
 };
+// cp.async (LDGSTS): global -> shared copies that bypass the register file and complete asynchronously
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// PState staged through shared memory: slot f of thread t lives at buf[f * stride + t] (conflict-free LDS.64)
+constexpr int PSTATE_SLOTS = 32;
+__device__ __forceinline__ void pstate_issue_async(double *buf, int stride, const SolidDev &s, const kml_material &mat, const StepParams &sp, long long ip) {
+  int f = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) cp_async8(buf + (f++) * stride, s.F[i] + ip);
+#pragma unroll
+  for (int i = 0; i < 6; i++) cp_async8(buf + (f++) * stride, s.sig[i] + ip);
+#pragma unroll
+  for (int i = 0; i < 6; i++) cp_async8(buf + (f++) * stride, s.eel[i] + ip);
+  cp_async8(buf + (f++) * stride, s.vol0 + ip); cp_async8(buf + (f++) * stride, s.rho0 + ip); cp_async8(buf + (f++) * stride, s.dmg + ip);
+#pragma unroll
+  for (int i = 0; i < 3; i++) cp_async8(buf + (f++) * stride, s.v[i] + ip);
+  if (mat.type == KML_MAT_EOS_STRENGTH) {
+    cp_async8(buf + 27 * stride, s.eps + ip); cp_async8(buf + 28 * stride, s.epsdot + ip);
+    if (mat.damage_type != KML_DAMAGE_NONE) cp_async8(buf + 29 * stride, s.dmgi + ip);
+    if (mat.cp != 0 || sp.temp) cp_async8(buf + 30 * stride, s.T + ip);
+  }
+}
+__device__ __forceinline__ void pstate_from_smem(PState &ps, const double *buf, int stride, const kml_material &mat, const StepParams &sp) {
+  int f = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) ps.F[i] = buf[(f++) * stride];
+#pragma unroll
+  for (int i = 0; i < 6; i++) ps.sig[i] = buf[(f++) * stride];
+#pragma unroll
+  for (int i = 0; i < 6; i++) ps.eel[i] = buf[(f++) * stride];
+  ps.vol0 = buf[(f++) * stride]; ps.rho0 = buf[(f++) * stride]; ps.dmg = buf[(f++) * stride];
+#pragma unroll
+  for (int i = 0; i < 3; i++) ps.v[i] = buf[(f++) * stride];
+  ps.eps = ps.epsdot = ps.dmgi = ps.T = 0.0;
+  if (mat.type == KML_MAT_EOS_STRENGTH) {
+    ps.eps = buf[27 * stride]; ps.epsdot = buf[28 * stride];
+    if (mat.damage_type != KML_DAMAGE_NONE) ps.dmgi = buf[29 * stride];
+    if (mat.cp != 0 || sp.temp) ps.T = buf[30 * stride];
+  }
+}
+
 __device__ __forceinline__ void sym_to_full(const double *a, double *m) { // (xx,yy,zz,xy,xz,yz) -> row-major 3x3
   m[0] = a[0]; m[1] = a[3]; m[2] = a[4]; m[3] = a[3]; m[4] = a[1]; m[5] = a[5]; m[6] = a[4]; m[7] = a[5]; m[8] = a[2];
 }

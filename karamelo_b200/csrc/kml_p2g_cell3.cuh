@@ -50,8 +50,8 @@ __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) 
 //                                    !FULL: [0..3] x w  [4..7] y w  [8..11] z w  [12..14] m*v  [15] cell plane k
 template <bool FULL> struct Rec3 { static constexpr int N = FULL ? 36 : 16; static constexpr int K = FULL ? 34 : 15; };
 
-template <bool FULL, bool MASS, int NB>
-__global__ void __launch_bounds__(128, FULL ? (NB == 2 ? 2 : 3) : (NB == 4 ? 3 : 4))
+template <bool FULL, bool MASS, int NB, bool PIPE>
+__global__ void __launch_bounds__(128, FULL ? ((NB == 2 || PIPE) ? 2 : 3) : (NB == 4 ? 2 : 4))
 k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
   constexpr int Q = FULL ? 7 : 3;
   constexpr int GL = 16 / NB;          // lanes per group = particles per staging round
@@ -61,7 +61,8 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
   __shared__ __align__(16) double stage[GPB * GSTRIDE];
 
   const int lg = threadIdx.x % GL;
-  const int a = lg / (4 / NB), b0 = (lg % (4 / NB)) * NB;
+  int a = lg / (4 / NB), b0 = (lg % (4 / NB)) * NB;
+  asm volatile("" : "+r"(a), "+r"(b0)); // lane constants stay in registers (no S2R + shifts inside the particle loop)
   const unsigned gmask = (GL == 32 ? 0xFFFFFFFFu : ((1u << GL) - 1u)) << ((threadIdx.x & 31) / GL * GL);
   double *rec0 = stage + (threadIdx.x / GL) * GSTRIDE;
   const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GL;
@@ -126,7 +127,7 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
       for (int e = 0; e < 6; e++) rs[e] = s.sig[e][ip];
     }
   };
-  auto stage_raw = [&]() { // weights + products of the lane's particle -> its record
+  auto stage_raw = [&]() -> int { // weights + products of the lane's particle -> its record; returns the particle's cell plane
     double *r = rec0 + lg * REC;
     const int k0 = cell_axis(rz, g.lo[2], ih, g.n[2], 0);
     const bool int_z = cubic_interior(k0, g.n[2], 0, g.n[2]);
@@ -154,61 +155,94 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
       *(double2 *)(r + 12) = make_double2(rm * rv0, rm * rv1);
       *(double2 *)(r + 14) = make_double2(rm * rv2, __longlong_as_double((long long)k0));
     }
+    return k0;
   };
 
+  // register copy of one staged record, as this lane needs it
+  struct RecR { double2 X, Y[NB], Z01, Z23, D01, D23, MM, MV, A01, A23, A45; };
+  auto rec_load = [&](RecR &R, const double *r) {
+    if (FULL) {
+      R.X = *(const double2 *)(r + 2 * a);
+#pragma unroll
+      for (int e = 0; e < NB; e++) R.Y[e] = *(const double2 *)(r + 8 + 2 * (b0 + e));
+      R.Z01 = *(const double2 *)(r + 16); R.Z23 = *(const double2 *)(r + 18); R.D01 = *(const double2 *)(r + 20); R.D23 = *(const double2 *)(r + 22);
+      R.MM = *(const double2 *)(r + 24); R.MV = *(const double2 *)(r + 26);
+      R.A01 = *(const double2 *)(r + 28); R.A23 = *(const double2 *)(r + 30); R.A45 = *(const double2 *)(r + 32);
+    } else {
+      R.X.x = r[a];
+#pragma unroll
+      for (int e = 0; e < NB; e++) R.Y[e].x = r[4 + b0 + e];
+      R.Z01 = *(const double2 *)(r + 8); R.Z23 = *(const double2 *)(r + 10);
+      R.MM = *(const double2 *)(r + 12); R.MV.x = r[14];
+    }
+  };
+  auto rec_accumulate = [&](const RecR &R) {
+    const double wz[4] = {R.Z01.x, R.Z01.y, R.Z23.x, R.Z23.y};
+    if (FULL) {
+      const double dwz[4] = {R.D01.x, R.D01.y, R.D23.x, R.D23.y};
+#pragma unroll
+      for (int e = 0; e < NB; e++) {
+        const double gxy = R.X.x * R.Y[e].x, gx = R.X.y * R.Y[e].x, gy = R.X.x * R.Y[e].y;
+        const double mm = gxy * R.MM.x, M0 = gxy * R.MM.y, M1 = gxy * R.MV.x, M2 = gxy * R.MV.y;
+        // A = (xx,yy,zz,xy,xz,yz): f_x = -(xx gx + xy gy) wz - xz gxy dwz, ...
+        const double P0 = -(R.A01.x * gx + R.A23.y * gy), P1 = -(R.A23.y * gx + R.A01.y * gy), P2 = -(R.A45.x * gx + R.A45.y * gy);
+        const double Q0 = -(R.A45.x * gxy), Q1 = -(R.A45.y * gxy), Q2 = -(R.A23.x * gxy);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          double *ac = acc[e][c];
+          ac[0] += mm * wz[c];
+          ac[1] += M0 * wz[c]; ac[2] += M1 * wz[c]; ac[3] += M2 * wz[c];
+          ac[4] = fma(Q0, dwz[c], fma(P0, wz[c], ac[4])); // two FMAs per component (a sum of products would cost three FP64 instructions)
+          ac[5] = fma(Q1, dwz[c], fma(P1, wz[c], ac[5])); ac[6] = fma(Q2, dwz[c], fma(P2, wz[c], ac[6]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NB; e++) {
+        const double gxy = R.X.x * R.Y[e].x;
+        const double M0 = gxy * R.MM.x, M1 = gxy * R.MM.y, M2 = gxy * R.MV.x;
+#pragma unroll
+        for (int c = 0; c < 4; c++) { double *ac = acc[e][c]; ac[0] += M0 * wz[c]; ac[1] += M1 * wz[c]; ac[2] += M2 * wz[c]; }
+      }
+    }
+  };
+
+  const int gshift = (threadIdx.x & 31) / GL * GL;
   int kcur = kbeg, dirty = 0;
   int p = pbeg;
   if (p + lg < pend) load_raw(p + lg);
   while (p < pend) {
     const int n = min(GL, pend - p);
-    if (lg < n) stage_raw();
+    const int k0 = lg < n ? stage_raw() : 0x7fffffff;
+    // bit q of bm: particle q of this round lies in another cell plane than its predecessor (no per-particle lookup in the loop)
+    int kprev = __shfl_up_sync(gmask, k0, 1, GL);
+    if (lg == 0) kprev = kcur;
+    const unsigned bm = __ballot_sync(gmask, lg < n && k0 != kprev) >> gshift;
     __syncwarp(gmask);
     const int pn = p + n;
     if (pn + lg < pend) load_raw(pn + lg); // in flight while this round is accumulated
-    for (int q = 0; q < n; q++) {
-      const double *r = rec0 + q * REC;
-      const int kq = (int)__double_as_longlong(r[Rec3<FULL>::K]);
-      if (kq != kcur) { // group-uniform: slide the window up to the particle's cell, emitting completed planes
+    auto boundary = [&](int q) { // group-uniform: slide the window up to the particle's cell, emitting completed planes
+      if ((bm >> q) & 1) {
+        const int kq = (int)__double_as_longlong(rec0[q * REC + Rec3<FULL>::K]);
         while (kcur < kq && dirty) { if (dirty & 1) emit0(kcur); slide(); dirty >>= 1; kcur++; }
         kcur = kq;
       }
       dirty = 0xF;
-      if (FULL) {
-        const double2 X = *(const double2 *)(r + 2 * a);
-        const double2 Z01 = *(const double2 *)(r + 16), Z23 = *(const double2 *)(r + 18);
-        const double2 D01 = *(const double2 *)(r + 20), D23 = *(const double2 *)(r + 22);
-        const double2 MM = *(const double2 *)(r + 24), MV = *(const double2 *)(r + 26);
-        const double2 A01 = *(const double2 *)(r + 28), A23 = *(const double2 *)(r + 30), A45 = *(const double2 *)(r + 32);
-        const double wz[4] = {Z01.x, Z01.y, Z23.x, Z23.y}, dwz[4] = {D01.x, D01.y, D23.x, D23.y};
-#pragma unroll
-        for (int e = 0; e < NB; e++) {
-          const double2 Y = *(const double2 *)(r + 8 + 2 * (b0 + e));
-          const double gxy = X.x * Y.x, gx = X.y * Y.x, gy = X.x * Y.y;
-          const double mm = gxy * MM.x, M0 = gxy * MM.y, M1 = gxy * MV.x, M2 = gxy * MV.y;
-          // A = (xx,yy,zz,xy,xz,yz): f_x = -(xx gx + xy gy) wz - xz gxy dwz, ...
-          const double P0 = -(A01.x * gx + A23.y * gy), P1 = -(A23.y * gx + A01.y * gy), P2 = -(A45.x * gx + A45.y * gy);
-          const double Q0 = -(A45.x * gxy), Q1 = -(A45.y * gxy), Q2 = -(A23.x * gxy);
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            double *ac = acc[e][c];
-            ac[0] += mm * wz[c];
-            ac[1] += M0 * wz[c]; ac[2] += M1 * wz[c]; ac[3] += M2 * wz[c];
-            ac[4] = fma(Q0, dwz[c], fma(P0, wz[c], ac[4])); // two FMAs per component (a sum of products would cost three FP64 instructions)
-            ac[5] = fma(Q1, dwz[c], fma(P1, wz[c], ac[5])); ac[6] = fma(Q2, dwz[c], fma(P2, wz[c], ac[6]));
-          }
+    };
+    if (PIPE) { // two records in flight, unrolled by two so that no register copies are needed
+      RecR r0, r1; rec_load(r0, rec0);
+      for (int q = 0; q < n; q += 2) {
+        if (q + 1 < n) rec_load(r1, rec0 + (q + 1) * REC);
+        boundary(q); rec_accumulate(r0);
+        if (q + 1 < n) {
+          if (q + 2 < n) rec_load(r0, rec0 + (q + 2) * REC);
+          boundary(q + 1); rec_accumulate(r1);
         }
-      } else {
-        const double X = r[a];
-        const double2 Z01 = *(const double2 *)(r + 8), Z23 = *(const double2 *)(r + 10);
-        const double2 V01 = *(const double2 *)(r + 12); const double V2 = r[14];
-        const double wz[4] = {Z01.x, Z01.y, Z23.x, Z23.y};
-#pragma unroll
-        for (int e = 0; e < NB; e++) {
-          const double gxy = X * r[4 + b0 + e];
-          const double M0 = gxy * V01.x, M1 = gxy * V01.y, M2 = gxy * V2;
-#pragma unroll
-          for (int c = 0; c < 4; c++) { double *ac = acc[e][c]; ac[0] += M0 * wz[c]; ac[1] += M1 * wz[c]; ac[2] += M2 * wz[c]; }
-        }
+      }
+    } else {
+      for (int q = 0; q < n; q++) {
+        RecR cur; rec_load(cur, rec0 + q * REC);
+        boundary(q); rec_accumulate(cur);
       }
     }
     __syncwarp(gmask);
@@ -225,7 +259,7 @@ inline void cell_segments(int n2, int target, int *seglen, int *nseg) {
 }
 
 // returns 0 = launched, -1 = combination not covered (caller uses the atomic kernel), 1 = CUDA error
-template <int NB>
+template <int NB, bool PIPE>
 inline int cell_p2g3_launch_nb(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int seg_target, cudaStream_t st) {
   const bool full = (what & P2G_FORCE) != 0;
   constexpr int GL = 16 / NB;
@@ -235,14 +269,14 @@ inline int cell_p2g3_launch_nb(const SolidDev &s, const GridDev &g, const CellLi
   if (nb >= (1ll << 31)) return -1;
   if (full) {
     if (NB == 4) return -1;
-    if (what & P2G_MASS) k_p2g_cell3<true, true, NB == 4 ? 1 : NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
-    else k_p2g_cell3<true, false, NB == 4 ? 1 : NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
-  } else k_p2g_cell3<false, false, NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+    if (what & P2G_MASS) k_p2g_cell3<true, true, NB == 4 ? 1 : NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+    else k_p2g_cell3<true, false, NB == 4 ? 1 : NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+  } else k_p2g_cell3<false, false, NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
   return cudaGetLastError() != cudaSuccess;
 }
 
-// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4)
-inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int seg_target, cudaStream_t st, int *nlaunch) {
+// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4); pipe: software-pipelined record loads
+inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int pipe, int seg_target, cudaStream_t st, int *nlaunch) {
   *nlaunch = 0;
   const bool full = (what & P2G_FORCE) != 0;
   if (what & (P2G_MB | P2G_TEMP | P2G_HEAT)) return -1;
@@ -250,9 +284,16 @@ inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists
   if (!full && (what & P2G_MASS)) return -1; // mass-only / mass+momentum passes (USF) use the atomic kernel
   if (!full && !(what & P2G_MOM)) return -1;
   int rc;
-  if (full) rc = nb_full == 2 ? cell_p2g3_launch_nb<2>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1>(s, g, cl, what, seg_target, st);
-  else rc = nb_mom == 4 ? cell_p2g3_launch_nb<4>(s, g, cl, what, seg_target, st)
-          : (nb_mom == 2 ? cell_p2g3_launch_nb<2>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1>(s, g, cl, what, seg_target, st));
+  if (full) {
+    if (pipe) rc = nb_full == 2 ? cell_p2g3_launch_nb<2, true>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, true>(s, g, cl, what, seg_target, st);
+    else rc = nb_full == 2 ? cell_p2g3_launch_nb<2, false>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, false>(s, g, cl, what, seg_target, st);
+  } else if (pipe) {
+    rc = nb_mom == 4 ? cell_p2g3_launch_nb<4, true>(s, g, cl, what, seg_target, st)
+       : (nb_mom == 2 ? cell_p2g3_launch_nb<2, true>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, true>(s, g, cl, what, seg_target, st));
+  } else {
+    rc = nb_mom == 4 ? cell_p2g3_launch_nb<4, false>(s, g, cl, what, seg_target, st)
+       : (nb_mom == 2 ? cell_p2g3_launch_nb<2, false>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, false>(s, g, cl, what, seg_target, st));
+  }
   if (rc == 0) *nlaunch = 1;
   return rc;
 }
