@@ -3,16 +3,17 @@
 (BASELINE.json configs[4]: cubic B-splines, MUSL, 8 particles per cell, 248x250x202 cells = 100 192 000
 particles), through the host driver + C ABI of include/kml.h.
 
-    python bench.py --gpus N --steps K --warmup W            our arm (CUDA engine)
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA engine); N > 1 under torchrun
     python bench.py --impl reference ...                      the reference's own CPU path (oracle/_ref)
 
-Prints ONE JSON line (see the keys at the bottom).  A "step" is one full MUSL step
-(re-bin, P2G, grid update, G2P+advance, MUSL re-projection, gradient+F+stress, dt reduction).
+Prints ONE JSON line.  A "step" is one full MUSL step (re-bin, P2G, grid update, G2P+advance, MUSL
+re-projection, gradient+F+stress, dt reduction; at N > 1 also the halo sums and the particle migration).
+At N > 1 the same block is slab-decomposed along x (strong scaling): one process per GPU, NCCL inside libkml.so.
 """
 import argparse
+import ctypes as C
 import json
 import os
-import re
 import subprocess
 import sys
 import threading
@@ -27,7 +28,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 FULL_CELLS = (248, 250, 202)  # 100 192 000 particles in a 256 x 258 x 210 box
 # algorithmic bytes per particle-step (fp64 SoA, every array once per kernel)
 ALGO_BYTES = {"rebin": 80, "p2g": 158, "grid": 18, "g2p": 103, "v2g": 64, "stress": 436}
+# minimal FP64 instructions per particle and stage: the second roof of the fp64 stencil kernels
+FP64_INSTR = {"p2g": 1000, "g2p": 580, "v2g": 340, "stress": 1300}
+FP64_LANES_PER_SM_CLK = 64   # B200: 64 DFMA / clk / SM (ncu sm__inst_executed_pipe_fp64 peak = 0.5 warp-inst / clk / sub-partition)
+N_SM = 148
 A_SQUEEZE = 2.5e-4
+WORKLOAD = "synthetic 3-D ULMPM elastoplastic block (configs[4]): cubic B-splines, MUSL, FLIP 0.99, linear EOS + plastic strength, adaptive dt"
 
 
 def block_script(cells, velocity_fix):
@@ -50,32 +56,62 @@ def squeeze_velocity(x, cells):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): NVML every
+    20 ms, nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.sm_max, self.stop_flag, self.how = index, [], set(), None, False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.how = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                                  ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+                    if r & bit:
+                        self.reasons.add(name)
+                return
+            except Exception:
+                self.nvml = None
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            if out:
+                c = [x.strip() for x in out.split(",")]
+                self.sm.append(float(c[0]))
+                self.sm_max = float(c[1])
+                self.how = "nvidia-smi"
+                for i, name in enumerate(self.NAMES):
+                    if c[2 + i].lower().startswith("active"):
+                        self.reasons.add(name)
+        except Exception:
+            pass
 
     def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+            self.sample()
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi on this box"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
 
 
 def measured_peak():
@@ -84,6 +120,15 @@ def measured_peak():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(stage):
+    """dram bytes per particle of the stage's kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(stage)
+    except Exception:
+        return None
 
 
 def cpu_baseline(sample_cells=(24, 24, 24), nsteps=6):
@@ -114,7 +159,8 @@ def cpu_baseline(sample_cells=(24, 24, 24), nsteps=6):
         e.close()
         kind = "port"
     return {"value": npart / per_step, "unit": "particle-steps/s", "cores": 1, "kind": kind,
-            "sample": "same script at %dx%dx%d cells (%d particles), %d MUSL steps, 1 MPI-less rank" % (sample_cells + (npart, nsteps))}
+            "sample": "same script at %dx%dx%d cells (%d particles), %d MUSL steps; 1 rank (the reference is MPI-only and the image has no MPI: "
+                      "built with a single-rank mpi.h shim), %d host cores present" % (sample_cells + (npart, nsteps, os.cpu_count() or 0))}
 
 
 def run_reference_arm(args):
@@ -122,9 +168,135 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "particle_steps_per_sec", "value": cb["value"], "unit": "particle-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 3-D ULMPM elastoplastic block, cubic B-splines, MUSL, 8 ppc (bounded sample for the CPU)", "sample": cb["sample"]},
+            "config": {"workload": WORKLOAD + " (bounded sample for the CPU)", "sample": cb["sample"]},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    from karamelo_b200 import slab
+    from karamelo_b200.api import P
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU fallback"
+    rank, world, local, dist = slab.init_distributed()
+    cells = tuple(args.cells)
+    W, K = max(args.warmup, 3), args.steps
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = slab.make_engine(None)
+    t0 = time.perf_counter()
+    eng.script(block_script(cells, velocity_fix=False))
+    x = eng.download(0, P.X)
+    eng.upload(0, P.V, squeeze_velocity(x, cells))
+    np_local = len(x)
+    del x
+    setup_s = time.perf_counter() - t0
+    npart = eng.slab_info(0)["np_global"] if world > 1 else np_local
+
+    eng.line("run(%d)" % W)           # warm-up (>= 3 steps); includes step 1 with dt = 1e-16 like the reference
+    eng.stage_times(reset=True)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.sample()
+        sampler.start()
+    eng.timer_start()                 # CUDA events on the engine's stream
+    eng.line("run(%d)" % K)           # K full steps; the state (52 GB at 100M particles) is far larger than the 126 MB L2
+    ms = eng.timer_stop()
+    barrier()
+    if rank == 0:
+        sampler.sample()
+    clocks = sampler.summary()
+    ms = max_over_ranks(ms)
+    counts = eng.stage_times(reset=True)
+    launches = int(sum(v[1] for v in counts.values()))
+    value = npart * K / (ms * 1e-3)
+
+    # per-stage device time (events around every stage, a few extra steps) -> rooflines of the stage kernels
+    eng.profile(True)
+    eng.line("run(3)")
+    st = eng.stage_times(reset=True)
+    eng.profile(False)
+    stage_ms = {k: max_over_ranks(v[0] / 3) for k, v in st.items()}
+    np_max = int(max_over_ranks(np_local))
+    peak, peak_src = measured_peak()
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    per_stage = {}
+    for k, b in ALGO_BYTES.items():
+        if stage_ms.get(k, 0) > 0:
+            gbs = b * np_max / (stage_ms[k] * 1e-3) / 1e9   # per GPU: the slab with the most particles
+            per_stage[k] = {"ms": round(stage_ms[k], 4), "algo_GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+            if k in FP64_INSTR:
+                per_stage[k]["fp64_frac"] = round(FP64_INSTR[k] * np_max / (stage_ms[k] * 1e-3) / (FP64_LANES_PER_SM_CLK * N_SM * sm_hz), 4)
+    dom = max(per_stage, key=lambda k: per_stage[k]["ms"])
+    tr = profiled_traffic(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_stage[dom]["algo_GBps"], "peak": peak, "unit": "GB/s", "frac": per_stage[dom]["frac"],
+                "traffic": (tr["dram_bytes_per_particle"] * np_max if tr else None), "traffic_source": (tr or {}).get("source"),
+                "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "particles_per_launch": np_max,
+                "second_roof": "FP64 pipe (64 DFMA/clk/SM): fp64_frac = minimal FP64 instructions / (time x pipe rate), DESIGN.md section 3",
+                "per_stage": per_stage}
+
+    # end to end through the public API with HOST buffers: every step uploads the step's particle inputs from pinned
+    # host memory (kml_solid_upload), runs one step, downloads the results (kml_solid_download)
+    e2e = None
+    if not args.no_e2e:
+        fields_in = [P.X, P.V, P.SIGMA, P.FDEF, P.VOL, P.EFF_PLASTIC_STRAIN, P.EFF_PLASTIC_STRAIN_RATE]
+        fields_out = [P.X, P.V, P.SIGMA, P.EFF_PLASTIC_STRAIN]
+        host = {}
+        for f in fields_in:
+            a = eng.download(0, f)
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            host[f[0]] = t
+        bi = sum(host[f[0]].numel() * 8 for f in fields_in)
+        bo = sum(host[f[0]].numel() * 8 for f in fields_out)
+        info = eng.solid_info(0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            for f in fields_in:
+                eng._ckk(eng.lib.kml_solid_upload(eng.ctx, info["solid"], f[0], C.c_void_p(host[f[0]].data_ptr())))
+            eng.line("run(1)")
+            for f in fields_out:
+                eng._ckk(eng.lib.kml_solid_download(eng.ctx, info["solid"], f[0], C.c_void_p(host[f[0]].data_ptr())))
+        eng.synchronize()
+        dt_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": npart * args.e2e_steps / dt_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": int(max_over_ranks(bi)),
+               "d2h_bytes_per_step": int(max_over_ranks(bo)), "steps": args.e2e_steps,
+               "note": "per-rank bytes (largest slab); one step per upload/download round trip through kml_solid_upload/_download"}
+        del host
+
+    flags = eng.error_flags()
+    nps = [np_local]
+    if world > 1:
+        nps = [None] * world
+        dist.all_gather_object(nps, np_local)
+    eng.close()
+    if rank == 0:
+        cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(tuple(args.ref_cells))
+        cfg = {"workload": WORKLOAD, "cells": list(cells), "particles": npart, "particles_per_cell": 8, "l2": "inputs >> L2 (no flush needed)",
+               "setup_s": round(setup_s, 1)}
+        if world > 1:
+            cfg["parallelism"] = "x-slab x%d, NCCL halo sums + particle migration + dt all-reduce" % world
+            cfg["particles_per_rank"] = nps
+        line = {"metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks, "gpu_launches": launches, "error_flags": flags}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -140,98 +312,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
         if rank == 0:
             run_reference_arm(args)
         return
-
-    if world > 1 or args.gpus > 1:
-        from karamelo_b200.slab import bench_multi_gpu
-        bench_multi_gpu(args)
-        return
-
-    import torch
-    from karamelo_b200.api import Engine, P
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU fallback"
-    cells = tuple(args.cells)
-    W, K = max(args.warmup, 3), args.steps
-    eng = Engine(device=0)
-    t0 = time.perf_counter()
-    eng.script(block_script(cells, velocity_fix=False))
-    npart = eng.solid_info(0)["np"]
-    x = eng.download(0, P.X)
-    eng.upload(0, P.V, squeeze_velocity(x, cells))
-    del x
-    setup_s = time.perf_counter() - t0
-
-    eng.line("run(%d)" % W)           # warm-up (>= 3 steps); includes step 1 with dt = 1e-16 like the reference
-    eng.stage_times(reset=True)
-    sampler = ClockSampler(0)
-    sampler.start()
-    eng.synchronize()
-    eng.timer_start()                 # CUDA events on the engine's stream
-    eng.line("run(%d)" % K)           # K full steps; state (~45 GB at 100M particles) is far larger than the 126 MB L2
-    ms = eng.timer_stop()
-    clocks = sampler.summary()
-    counts = eng.stage_times(reset=True)
-    launches = int(sum(v[1] for v in counts.values()))
-    value = npart * K / (ms * 1e-3)
-
-    # per-stage device time (events around every stage, a few extra steps) -> roofline of the dominant kernel
-    eng.profile(True)
-    eng.line("run(3)")
-    st = eng.stage_times(reset=True)
-    eng.profile(False)
-    stage_ms = {k: v[0] / 3 for k, v in st.items()}
-    peak, peak_src = measured_peak()
-    per_stage = {}
-    for k, b in ALGO_BYTES.items():
-        if stage_ms.get(k, 0) > 0:
-            per_stage[k] = {"ms": round(stage_ms[k], 4), "algo_GBps": round(b * npart / (stage_ms[k] * 1e-3) / 1e9, 1), "frac": round(b * npart / (stage_ms[k] * 1e-3) / 1e9 / peak, 4)}
-    dom = max((k for k in ALGO_BYTES if stage_ms.get(k, 0) > 0), key=lambda k: stage_ms[k])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_stage[dom]["algo_GBps"], "peak": peak, "unit": "GB/s", "frac": per_stage[dom]["frac"],
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "per_stage": per_stage}
-
-    # end to end through the public API with HOST buffers: every step uploads the step's particle inputs from pinned
-    # host memory, runs one step, downloads the results
-    e2e = None
-    if not args.no_e2e:
-        fields_in = [P.X, P.V, P.SIGMA, P.FDEF, P.VOL, P.EFF_PLASTIC_STRAIN, P.EFF_PLASTIC_STRAIN_RATE]
-        fields_out = [P.X, P.V, P.SIGMA, P.EFF_PLASTIC_STRAIN]
-        host = {}
-        for f in fields_in:
-            a = eng.download(0, f)
-            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
-            t.numpy()[...] = a
-            host[f[0]] = t
-        bi = sum(host[f[0]].numel() * 8 for f in fields_in)
-        bo = sum(host[f[0]].numel() * 8 for f in fields_out)
-        import ctypes as C
-        info = eng.solid_info(0)
-        eng.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            for f in fields_in:
-                eng._ckk(eng.lib.kml_solid_upload(eng.ctx, info["solid"], f[0], C.c_void_p(host[f[0]].data_ptr())))
-            eng.line("run(1)")
-            for f in fields_out:
-                eng._ckk(eng.lib.kml_solid_download(eng.ctx, info["solid"], f[0], C.c_void_p(host[f[0]].data_ptr())))
-        eng.synchronize()
-        dt_e2e = time.perf_counter() - t0
-        e2e = {"value": npart * args.e2e_steps / dt_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "steps": args.e2e_steps}
-        del host
-
-    flags = eng.error_flags()
-    eng.close()
-    cb = None if args.no_cpu_baseline else cpu_baseline(tuple(args.ref_cells))
-    line = {"metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 3-D ULMPM elastoplastic block (configs[4]): cubic B-splines, MUSL, FLIP 0.99, linear EOS + plastic strength, adaptive dt",
-                       "cells": list(cells), "particles": npart, "particles_per_cell": 8, "l2": "inputs >> L2 (no flush needed)", "setup_s": round(setup_s, 1)},
-            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks, "gpu_launches": launches, "error_flags": flags}
-    print(json.dumps(line))
+    run_ours(args)
 
 
 if __name__ == "__main__":
