@@ -42,7 +42,7 @@ struct kml_ctx {
   void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
   bool tl_mass_done = false;
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
-  bool use_cell_p2g = true; int p2g_version = 3, p2g_nb = 1, v2g_nb = 2, p2g_pipe = 0, gather_version = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic|v2|v3, KML_P2G_NB, KML_V2G_NB, KML_GATHER=v1|v2, KML_SEGLEN, KML_GATHER_THREADS, KML_STRESS_BLOCKS
+  bool use_cell_p2g = true; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
   bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
@@ -59,7 +59,7 @@ struct StageTimer {
 StepParams step_params(kml_ctx *c) {
   StepParams sp; sp.dt = c->dt; sp.alpha = c->c.PIC_FLIP;
   for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
-  sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.flags = c->d_flags; return sp;
+  sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.inv_tav = 0.0; sp.flags = c->d_flags; return sp;
 }
 
 // kernel dispatch on (dimension, TL); the shape function is switched inside each launcher (kml_launch.h)
@@ -125,16 +125,11 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
   const char *e = getenv("KML_P2G");
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
-  if (e && !strcmp(e, "v2")) c->p2g_version = 2;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
-  c->p2g_pipe = env_int("KML_P2G_PIPE", 0) ? 1 : 0;
-  e = getenv("KML_GATHER"); if (e && !strcmp(e, "v1")) c->gather_version = 1;
   c->gtune.seg_target = std::min(std::max(env_int("KML_SEGLEN", 32), 8), 96);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;
-  { const int v = env_int("KML_STRESS_BLOCKS", 3); c->gtune.stress_blocks = (v == 2 || v == 4) ? v : 3; }
-  c->gtune.stress_version = env_int("KML_STRESS", 3) == 2 ? 2 : 3;
   *out = c; return 0;
 }
 
@@ -500,8 +495,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (!TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      const int rc = c->p2g_version == 2 ? cell_p2g_launch(S->s, g, G->cl, what, c->stream, &nl)   // -1: combination not covered -> atomic kernel
-                                         : cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->p2g_pipe, c->gtune.seg_target, c->stream, &nl);
+      const int rc = cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
@@ -556,9 +550,7 @@ int kml_advance_particles(kml_ctx *c) {
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
     if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
-      StressParams none{};
-      rc = c->gather_version == 1 ? cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream)
-                                  : cell_gather2_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
+      StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
     if (rc < 0) KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
@@ -610,12 +602,12 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
+    sp.inv_tav = S->d.mat.signal_velocity / (1000 * G->d.cellsize);
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
     if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
-      rc = c->gather_version == 1 ? cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream)
-                                  : cell_gather2_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
+      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
     }
     if (rc < 0) KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);

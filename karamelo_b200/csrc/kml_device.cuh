@@ -159,12 +159,13 @@ __device__ __forceinline__ void axis_weights(double xp, double lo, double h, dou
 __device__ __forceinline__ double det3(const double *m) {
   return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
-__device__ __forceinline__ void inv3(const double *m, double *r) {
+__device__ __forceinline__ double inv3(const double *m, double *r) { // returns 1 / det(m)
   double c00 = m[4] * m[8] - m[5] * m[7], c10 = m[5] * m[6] - m[3] * m[8], c20 = m[3] * m[7] - m[4] * m[6];
   double id = 1.0 / (m[0] * c00 + m[1] * c10 + m[2] * c20);
   r[0] = c00 * id; r[3] = c10 * id; r[6] = c20 * id;
   r[1] = (m[2] * m[7] - m[1] * m[8]) * id; r[4] = (m[0] * m[8] - m[2] * m[6]) * id; r[7] = (m[1] * m[6] - m[0] * m[7]) * id;
   r[2] = (m[1] * m[5] - m[2] * m[4]) * id; r[5] = (m[2] * m[3] - m[0] * m[5]) * id; r[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return id;
 }
 __device__ __forceinline__ void mul3(const double *a, const double *b, double *c) {
 #pragma unroll
@@ -191,7 +192,7 @@ __device__ __forceinline__ double frob3(const double *m) {
   return sqrt(s);
 }
 __device__ __forceinline__ void deviator3(const double *m, double *d) { // MPM_Math::Deviator, src/mpm_math.h:28-33
-  double t = (m[0] + m[4] + m[8]) / 3.0;
+  double t = (m[0] + m[4] + m[8]) * (1.0 / 3.0); // a multiplication, not an FP64 division (<= 1 ulp from the reference's / 3.0)
 #pragma unroll
   for (int i = 0; i < 9; i++) d[i] = m[i];
   d[0] -= t; d[4] -= t; d[8] -= t;

@@ -1,29 +1,29 @@
-// kml_gather_cell2.cuh - cell-run gather kernels, second generation (3-D cubic B-splines, ULMPM):
-// grid-to-particle (+advance) and velocity gradient + F + stress.
+// kml_gather_cell2.cuh - cell-run gather kernels (3-D cubic B-splines, ULMPM): grid-to-particle (+advance) and
+// velocity gradient + F + stress.
 //
-// Decomposition as in kml_gather_cell.cuh (a block owns a column segment of cells, its 4 x 4 x (len+3) node
-// tile lives in shared memory, one thread per particle), rebuilt around the FP64 instruction budget
+// A block owns one column segment of cells (i0, j0, [kbeg,kend)).  The 4 x 4 x (len+3) node records its particles can
+// touch are staged once in shared memory (the rows are contiguous along k in global memory); the particles of the
+// segment (contiguous in the cell-sorted order) are then processed one per thread and every one of their 64 node
+// reads is a shared-memory load instead of an L1/L2 round trip.  Built around the FP64 instruction budget
 // (DESIGN.md section 3):
 //   * interior columns evaluate the B-spline pieces branch-free (cubic_axis4);
 //   * the velocity gradient is sum-factorised: contract the node values along k with (wz, dwz), then along
 //     j with (wy, dwy), then along i with (wx, dwx) - 564 FP64 instructions per particle instead of 816;
 //   * G2P reads packed 48-byte tile records {v_update, v_update - v}: three LDS.128 per node, and the
 //     subtraction is done once per node when the tile is filled instead of once per (particle, node);
-//   * the first particle's index and position are fetched before the tile is staged, the next particle's
-//     while the current one is processed, and the stress kernel puts its 30 state loads in flight before
-//     the gather.
+//   * the first particle's index and position are fetched before the tile is staged and the next particle's
+//     while the current one is processed.
 // Arithmetic: src/solid.cpp:576-635,786-796 (G2P + advance), :860-936 (gradient), :1155-1438 (F, stress).
 #pragma once
-#include "kml_gather_cell.cuh"
+#include "kml_p2g_cell3.cuh"
 
 namespace kml {
 
-template <bool STRESS, int THREADS, int MINB>
+// ---- G2P + advance ------------------------------------------------------------------------------------------------
+template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-k_gather_cell2(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
-               int seglen, int nseg) {
-  extern __shared__ __align__(16) double tile2[]; // STRESS: [16][TLEN] double4 {v, -}; G2P: [16][TLEN] x 6 doubles {v_update, v_update - v}
-  constexpr int RECD = STRESS ? 4 : 6;
+k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
+  extern __shared__ __align__(16) double tile2[]; // [16][TLEN] x 6 doubles {v_update, v_update - v}
   const int TLEN = seglen + 3;
   const long long col = blockIdx.x / nseg; const int seg = (int)(blockIdx.x % nseg);
   const int i0 = (int)(col / g.n[1]), j0 = (int)(col % g.n[1]);
@@ -38,105 +38,66 @@ k_gather_cell2(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materi
   double px = 0, py = 0, pz = 0;
   if (ip >= 0) { px = s.x[0][ip]; py = s.x[1][ip]; pz = s.x[2][ip]; }
 
-  const double4 *__restrict__ src0 = STRESS ? (tp.doublemapping ? g.nv : g.nvu) : g.nvu;
-  for (int e = threadIdx.x; e < 16 * TLEN; e += blockDim.x) {
+  for (int e = threadIdx.x; e < 16 * TLEN; e += THREADS) {
     const int row = e / TLEN, t = e - row * TLEN;
     const int ni = i0 + (row >> 2), nj = j0 + (row & 3), nk = kbeg + t;
     double4 r0 = make_double4(0, 0, 0, 0), r1 = r0;
     if (ni < g.n[0] && nj < g.n[1] && nk < g.n[2]) {
       const long long node = ((long long)ni * g.n[1] + nj) * g.n[2] + nk;
-      r0 = ldg4(&src0[node]);
-      if (!STRESS) r1 = ldg4(&g.nv[node]);
+      r0 = ldg4(&g.nvu[node]); r1 = ldg4(&g.nv[node]);
     }
-    double *d = tile2 + (size_t)e * RECD;
-    if (STRESS) { *(double2 *)d = make_double2(r0.x, r0.y); *(double2 *)(d + 2) = make_double2(r0.z, 0.0); }
-    else {
-      *(double2 *)d = make_double2(r0.x, r0.y); *(double2 *)(d + 2) = make_double2(r0.z, r0.x - r1.x);
-      *(double2 *)(d + 4) = make_double2(r0.y - r1.y, r0.z - r1.z);
-    }
+    double *d = tile2 + (size_t)e * 6;
+    *(double2 *)d = make_double2(r0.x, r0.y); *(double2 *)(d + 2) = make_double2(r0.z, r0.x - r1.x);
+    *(double2 *)(d + 4) = make_double2(r0.y - r1.y, r0.z - r1.z);
   }
   __syncthreads();
 
   const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
   const double h = g.h, ih = g.inv_cellsize;
-  double wave = 0, hr = 1.0;
   while (ip >= 0) {
     // next particle of this thread
-    const int pn = p + blockDim.x;
+    const int pn = p + THREADS;
     const int ipn = pn < pend ? order[pn] : -1;
     double nx = 0, ny = 0, nz = 0;
     if (ipn >= 0) { nx = s.x[0][ipn]; ny = s.x[1][ipn]; nz = s.x[2][ipn]; }
-    PState ps;
-    if (STRESS) ps.load(s, mat, sp, ip);
-    double vold[3] = {0, 0, 0};
-    if (!STRESS) { vold[0] = s.v[0][ip]; vold[1] = s.v[1][ip]; vold[2] = s.v[2][ip]; } // in flight during the gather
+    double vold[3]; // in flight during the gather
+    vold[0] = s.v[0][ip]; vold[1] = s.v[1][ip]; vold[2] = s.v[2][ip];
 
     const int k0 = cell_axis(pz, g.lo[2], ih, g.n[2], 0);
     const int koff = k0 - kbeg; // the particle's cell inside the segment
-    const bool int_z = cubic_interior(k0, g.n[2], 0, g.n[2]);
-    double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
-    cubic_axis4<true>(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dwx);
-    cubic_axis4<true>(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dwy);
-    cubic_axis4<true>(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, wz, dwz);
-    if (STRESS) {
-      double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      const double qv[3] = {0, 0, 0};
+    double wx[4], wy[4], wz[4], dw_[4];
+    cubic_axis4(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dw_);
+    cubic_axis4(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dw_);
+    cubic_axis4(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], cubic_interior(k0, g.n[2], 0, g.n[2]), wz, dw_);
+    double vu[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0}, B1[3] = {0, 0, 0};
+    for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const double *row = tile2 + ((size_t)(a * 4 + b) * TLEN + koff) * 4;
-          double A[3] = {0, 0, 0}, B[3] = {0, 0, 0};
+      for (int b = 0; b < 4; b++) {
+        const double gxy = wx[a] * wy[b];
+        const double *row = tile2 + ((size_t)(a * 4 + b) * TLEN + koff) * 6;
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const double2 vxy = *(const double2 *)(row + 4 * c); const double vz = row[4 * c + 2];
-            A[0] = fma(wz[c], vxy.x, A[0]); A[1] = fma(wz[c], vxy.y, A[1]); A[2] = fma(wz[c], vz, A[2]);
-            B[0] = fma(dwz[c], vxy.x, B[0]); B[1] = fma(dwz[c], vxy.y, B[1]); B[2] = fma(dwz[c], vz, B[2]);
-          }
-#pragma unroll
-          for (int d = 0; d < 3; d++) { A1[d] = fma(wy[b], A[d], A1[d]); A2[d] = fma(dwy[b], A[d], A2[d]); B1[d] = fma(wy[b], B[d], B1[d]); }
+        for (int c = 0; c < 4; c++) {
+          const double2 r01 = *(const double2 *)(row + 6 * c), r23 = *(const double2 *)(row + 6 * c + 2), r45 = *(const double2 *)(row + 6 * c + 4);
+          const double wf = gxy * wz[c];
+          vu[0] = fma(wf, r01.x, vu[0]); vu[1] = fma(wf, r01.y, vu[1]); vu[2] = fma(wf, r23.x, vu[2]);
+          acc[0] = fma(wf, r23.y, acc[0]); acc[1] = fma(wf, r45.x, acc[1]); acc[2] = fma(wf, r45.y, acc[2]);
         }
-#pragma unroll
-        for (int d = 0; d < 3; d++) { L[3 * d] = fma(dwx[a], A1[d], L[3 * d]); L[3 * d + 1] = fma(wx[a], A2[d], L[3 * d + 1]); L[3 * d + 2] = fma(wx[a], B1[d], L[3 * d + 2]); }
       }
-      particle_stress<false>(s, g, sp, mat, ip, ps, L, qv, wave, hr);
-    } else {
-      double vu[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
-#pragma unroll
-      for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const double gxy = wx[a] * wy[b];
-          const double *row = tile2 + ((size_t)(a * 4 + b) * TLEN + koff) * 6;
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const double2 r01 = *(const double2 *)(row + 6 * c), r23 = *(const double2 *)(row + 6 * c + 2), r45 = *(const double2 *)(row + 6 * c + 4);
-            const double wf = gxy * wz[c];
-            vu[0] = fma(wf, r01.x, vu[0]); vu[1] = fma(wf, r01.y, vu[1]); vu[2] = fma(wf, r23.x, vu[2]);
-            acc[0] = fma(wf, r23.y, acc[0]); acc[1] = fma(wf, r45.x, acc[1]); acc[2] = fma(wf, r45.y, acc[2]);
-          }
-        }
-      particle_advance<false>(s, sp, ip, vu, acc, 0.0, vold);
-    }
+    particle_advance<false>(s, sp, ip, vu, acc, 0.0, vold);
     p = pn; ip = ipn; px = nx; py = ny; pz = nz;
-  }
-  if (STRESS) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wave = fmax(wave, __shfl_xor_sync(0xffffffffu, wave, o));
-    if ((threadIdx.x & 31) == 0 && wave > 0) atomic_max_pos(tp.max_wave, wave);
   }
 }
 
-// ---- velocity gradient + F + stress, third generation: asynchronous staging ----------------------------------
+// ---- velocity gradient + F + stress: asynchronous staging ------------------------------------------------------
 // Same tile / thread-per-particle scheme, but nothing on the memory side goes through registers: the node tile is
 // filled with 16-byte cp.async copies, and every thread streams the 29-31 state doubles of its NEXT particle into a
 // private shared-memory slot (8-byte cp.async) while it runs the constitutive update of the current one.  The register file only holds
 // the weights, the gather accumulators and the constitutive update, so the kernel fits 168 registers (3 x 128 or
-// 6 x 64 threads per SM) without the 60-register prefetch of k_gather_cell2<true>.
+// 6 x 64 threads per SM); prefetching the state into registers instead costs 60 more and halves the occupancy.
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-k_stress_cell3(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
+k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
                int seglen, int nseg) {
   extern __shared__ __align__(16) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state
   const int TLEN = seglen + 3;
@@ -186,11 +147,13 @@ k_stress_cell3(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materi
     double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     {
       double wx[4], dwx[4], wy[4], dwy[4], wz[4], dwz[4];
-      cubic_axis4<true>(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dwx);
-      cubic_axis4<true>(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dwy);
-      cubic_axis4<true>(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, wz, dwz);
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
+      cubic_axis4(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dwx);
+      cubic_axis4(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dwy);
+      cubic_axis4(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, wz, dwz);
+#pragma unroll 1
+      for (int a = 0; a < 4; a++) { // rolled: the hot loop body stays small (instruction cache)
+        const double wxa = a == 0 ? wx[0] : (a == 1 ? wx[1] : (a == 2 ? wx[2] : wx[3]));
+        const double dwxa = a == 0 ? dwx[0] : (a == 1 ? dwx[1] : (a == 2 ? dwx[2] : dwx[3]));
         double A1[3] = {0, 0, 0}, A2[3] = {0, 0, 0}, B1[3] = {0, 0, 0};
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -206,7 +169,7 @@ k_stress_cell3(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materi
           for (int d = 0; d < 3; d++) { A1[d] = fma(wy[b], A[d], A1[d]); A2[d] = fma(dwy[b], A[d], A2[d]); B1[d] = fma(wy[b], B[d], B1[d]); }
         }
 #pragma unroll
-        for (int d = 0; d < 3; d++) { L[3 * d] = fma(dwx[a], A1[d], L[3 * d]); L[3 * d + 1] = fma(wx[a], A2[d], L[3 * d + 1]); L[3 * d + 2] = fma(wx[a], B1[d], L[3 * d + 2]); }
+        for (int d = 0; d < 3; d++) { L[3 * d] = fma(dwxa, A1[d], L[3 * d]); L[3 * d + 1] = fma(wxa, A2[d], L[3 * d + 1]); L[3 * d + 2] = fma(wxa, B1[d], L[3 * d + 2]); }
       }
     }
     PState ps;
@@ -223,44 +186,32 @@ k_stress_cell3(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materi
   if ((threadIdx.x & 31) == 0 && wave > 0) atomic_max_pos(tp.max_wave, wave);
 }
 
+// measurement knobs (environment, see kml.cu): cells per segment and threads per block
+struct GatherTune { int seg_target = 32, threads = 64; };
+
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
-struct GatherTune { int seg_target = 32, threads = 64, stress_blocks = 3, stress_version = 3; };
-inline int cell_gather2_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
-                               const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
+inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
+                              const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
   if (sp.axisymmetric || sp.temp || !cl.valid) return -1;
   int seglen, nseg; cell_segments(g.n[2], tune.seg_target, &seglen, &nseg);
   const long long nblocks = (long long)g.n[0] * g.n[1] * nseg;
   if (nblocks >= (1ll << 31)) return -1;
-  const size_t smem = sizeof(double) * 16 * (seglen + 3) * (stress ? 4 : 6);
-#define KML_GATHER2_LAUNCH(STRESS, THREADS, MINB)                                                                                  \
+  const size_t tile = sizeof(double) * 16 * (size_t)(seglen + 3) * (stress ? 4 : 6);
+  const size_t smem = tile + (stress ? sizeof(double) * PSTATE_SLOTS * (size_t)tune.threads : 0);
+#define KML_GATHER_LAUNCH(KERN, THREADS, ...)                                                                                       \
   do {                                                                                                                             \
-    auto kern = k_gather_cell2<STRESS, THREADS, MINB>;                                                                             \
+    auto kern = KERN;                                                                                                              \
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-    kern<<<(unsigned)nblocks, THREADS, smem, st>>>(s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);                           \
+    kern<<<(unsigned)nblocks, THREADS, smem, st>>>(__VA_ARGS__);                                                                   \
   } while (0)
-  if (stress && tune.stress_version == 3) {
-    const size_t smem3 = sizeof(double) * (16 * (size_t)(seglen + 3) * 4 + PSTATE_SLOTS * (size_t)tune.threads);
-#define KML_STRESS3_LAUNCH(THREADS, MINB)                                                                                          \
-  do {                                                                                                                             \
-    auto kern = k_stress_cell3<THREADS, MINB>;                                                                                     \
-    if (smem3 > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3) != cudaSuccess) return 1; \
-    kern<<<(unsigned)nblocks, THREADS, smem3, st>>>(s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);                          \
-  } while (0)
-    if (tune.threads == 64) { if (tune.stress_blocks == 4) KML_STRESS3_LAUNCH(64, 8); else if (tune.stress_blocks == 3) KML_STRESS3_LAUNCH(64, 6); else KML_STRESS3_LAUNCH(64, 4); }
-    else { if (tune.stress_blocks == 4) KML_STRESS3_LAUNCH(128, 4); else if (tune.stress_blocks == 3) KML_STRESS3_LAUNCH(128, 3); else KML_STRESS3_LAUNCH(128, 2); }
-#undef KML_STRESS3_LAUNCH
-    return cudaGetLastError() != cudaSuccess;
-  }
-  if (tune.threads == 64) {
-    if (stress && tune.stress_blocks == 3) KML_GATHER2_LAUNCH(true, 64, 6);
-    else if (stress) KML_GATHER2_LAUNCH(true, 64, 4);
-    else KML_GATHER2_LAUNCH(false, 64, 8);
+  if (stress) {
+    if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
+    else KML_GATHER_LAUNCH((k_stress_cell<128, 3>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
   } else {
-    if (stress && tune.stress_blocks == 3) KML_GATHER2_LAUNCH(true, 128, 3);
-    else if (stress) KML_GATHER2_LAUNCH(true, 128, 2);
-    else KML_GATHER2_LAUNCH(false, 128, 4);
+    if (tune.threads == 64) KML_GATHER_LAUNCH((k_g2p_cell<64, 8>), 64, s, g, sp, cl.start, cl.order, seglen, nseg);
+    else KML_GATHER_LAUNCH((k_g2p_cell<128, 4>), 128, s, g, sp, cl.start, cl.order, seglen, nseg);
   }
-#undef KML_GATHER2_LAUNCH
+#undef KML_GATHER_LAUNCH
   return cudaGetLastError() != cudaSuccess;
 }
 

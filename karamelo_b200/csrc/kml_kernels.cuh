@@ -21,6 +21,7 @@ struct StepParams {
   double dt, alpha;        // alpha = PIC_FLIP
   double boxlo[3], boxhi[3];
   int axisymmetric, temp;
+  double inv_tav;          // stress update: signal_velocity / (1000 cellsize) of the solid being updated
   unsigned *flags;         // device error word
 };
 
@@ -326,14 +327,14 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
   }
 #pragma unroll
   for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
-  double Finv[9]; inv3(Fn, Finv);
+  double Finv[9]; const double iJ = inv3(Fn, Finv);
   const double J = det3(Fn);
   const double vol0 = ps.vol0;
   const double vol = J * vol0;
   s.vol[ip] = vol;
   const double damage_old = ps.dmg;
   if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);
-  const double rho = ps.rho0 / J;
+  const double rho = ps.rho0 * iJ; // 1/J from the inverse: one FP64 division less per particle
   double D[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   if (mat.type != KML_MAT_NEO_HOOKEAN) {
     if (TL) {
@@ -376,7 +377,6 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
       for (int i = 0; i < 9; i++) s.pk1[i][ip] = vol0 * PK1[i];
     }
     double FP[9]; mul3_bt(Fn, PK1, FP);
-    const double iJ = 1.0 / J;
 #pragma unroll
     for (int i = 0; i < 9; i++) sig[i] = iJ * FP[i];
     double C[9]; mul3_at(Fn, Fn, C);
@@ -395,9 +395,9 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
     double eps = ps.eps, epsdot = ps.epsdot;
     strength_dev(mat, dt, sig, D, sdev, dep, eps, epsdot, damage, T);
     eps += dep;
-    const double tav = 1000 * g.cellsize / mat.signal_velocity;
-    epsdot -= epsdot * dt / tav;
-    epsdot += dep / tav;
+    const double itav = sp.inv_tav; // 1 / (1000 cellsize / signal_velocity), src/solid.cpp:1323-1327, uniform per launch
+    epsdot -= epsdot * dt * itav;
+    epsdot += dep * itav;
     epsdot = (0.0 > epsdot) ? 0.0 : epsdot;
     s.eps[ip] = eps; s.epsdot[ip] = epsdot;
     if (mat.damage_type != KML_DAMAGE_NONE) {
@@ -412,7 +412,7 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
       s.gamma[ip] = gam;
     }
     const double pf = (damage == 0 || pH >= 0) ? -pH : -pH * (1.0 - damage);
-    const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) / 3.0;
+    const double te = (dt * trD + (eel[0] + eel[4] + eel[8])) * (1.0 / 3.0);
     const double iGd = 1.0 / ((damage > 1e-10) ? mat.G * (1 - damage) : mat.G); // one reciprocal instead of nine FP64 divisions
 #pragma unroll
     for (int i = 0; i < 9; i++) { sig[i] = sdev[i]; eel[i] = sdev[i] * iGd; }

@@ -7,6 +7,7 @@
 //   * interior columns evaluate the cubic B-spline pieces branch-free (node a of the stencil always lies in
 //     the same interval of src/basis_functions.h:40-104); boundary columns keep the reference's branches;
 //   * the raw data of the next round is loaded before the current round is accumulated (register prefetch);
+//   * a ballot marks the particles that open a new cell plane, so the inner loop has no per-particle lookup;
 //   * a lane may own NB = 2 node columns (8-lane groups): half the shared-memory traffic per FP64 FMA;
 //   * no FP64 compares in the emit path (an integer dirty mask tracks non-empty planes).
 // Arithmetic per (particle, node) is that of src/solid.cpp:317-335, :337-390, :482-522; the summation
@@ -25,7 +26,6 @@ __device__ __forceinline__ void cubic_piece(int a, double r, double ih, double &
 }
 
 // (w, dw) of the 4 stencil nodes i0..i0+3 (LOCAL indices) of one axis; interior = all four nodes exist and have ntype 0
-template <bool DERIV>
 __device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, double ih, int i0, int n, int goff, int gn, bool interior, double (&w)[4], double (&dw)[4]) {
   if (interior) {
 #pragma unroll
@@ -38,7 +38,6 @@ __device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, doub
 #pragma unroll
     for (int a = 0; a < 4; a++) cubic_node(xp, lo, h, ih, i0 + a, n, goff, gn, w[a], dw[a]);
   }
-  (void)DERIV;
 }
 __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) {
   const int ig = i0 + goff;
@@ -48,10 +47,13 @@ __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) 
 // Staged particle record (doubles).  FULL:  [0..7] x (w,dw)x4  [8..15] y (w,dw)x4  [16..19] z w  [20..23] z dw
 //                                           [24..27] m, m*vx, m*vy, m*vz  [28..33] vol*sigma (xx,yy,zz,xy,xz,yz)  [34] cell plane k
 //                                    !FULL: [0..3] x w  [4..7] y w  [8..11] z w  [12..14] m*v  [15] cell plane k
-template <bool FULL> struct Rec3 { static constexpr int N = FULL ? 36 : 16; static constexpr int K = FULL ? 34 : 15; };
+// The record stride is chosen so that the 16-byte stores of consecutive lanes fall into different banks (stride mod 128 B = 48 / 16):
+// with a power-of-two stride every STS of the staging pass is a 16-way bank conflict (ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st
+// 42 % of peak in the momentum pass with a 128-byte stride; the padding took that pass from 0.54 to 0.42 ms at 7 M particles).
+template <bool FULL> struct Rec3 { static constexpr int N = FULL ? 38 : 18; static constexpr int K = FULL ? 34 : 15; };
 
-template <bool FULL, bool MASS, int NB, bool PIPE>
-__global__ void __launch_bounds__(128, FULL ? ((NB == 2 || PIPE) ? 2 : 3) : (NB == 4 ? 2 : 4))
+template <bool FULL, bool MASS, int NB>
+__global__ void __launch_bounds__(128, FULL ? (NB == 2 ? 2 : 3) : (NB == 4 ? 3 : 4))
 k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
   constexpr int Q = FULL ? 7 : 3;
   constexpr int GL = 16 / NB;          // lanes per group = particles per staging round
@@ -132,17 +134,17 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
     const int k0 = cell_axis(rz, g.lo[2], ih, g.n[2], 0);
     const bool int_z = cubic_interior(k0, g.n[2], 0, g.n[2]);
     double w[4], dw[4];
-    cubic_axis4<FULL>(rx, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, w, dw);
+    cubic_axis4(rx, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, w, dw);
     if (FULL) {
 #pragma unroll
       for (int t = 0; t < 4; t++) *(double2 *)(r + 2 * t) = make_double2(w[t], dw[t]);
     } else { *(double2 *)(r + 0) = make_double2(w[0], w[1]); *(double2 *)(r + 2) = make_double2(w[2], w[3]); }
-    cubic_axis4<FULL>(ry, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, w, dw);
+    cubic_axis4(ry, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, w, dw);
     if (FULL) {
 #pragma unroll
       for (int t = 0; t < 4; t++) *(double2 *)(r + 8 + 2 * t) = make_double2(w[t], dw[t]);
     } else { *(double2 *)(r + 4) = make_double2(w[0], w[1]); *(double2 *)(r + 6) = make_double2(w[2], w[3]); }
-    cubic_axis4<FULL>(rz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, w, dw);
+    cubic_axis4(rz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], int_z, w, dw);
     if (FULL) {
       *(double2 *)(r + 16) = make_double2(w[0], w[1]); *(double2 *)(r + 18) = make_double2(w[2], w[3]);
       *(double2 *)(r + 20) = make_double2(dw[0], dw[1]); *(double2 *)(r + 22) = make_double2(dw[2], dw[3]);
@@ -229,21 +231,9 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
       }
       dirty = 0xF;
     };
-    if (PIPE) { // two records in flight, unrolled by two so that no register copies are needed
-      RecR r0, r1; rec_load(r0, rec0);
-      for (int q = 0; q < n; q += 2) {
-        if (q + 1 < n) rec_load(r1, rec0 + (q + 1) * REC);
-        boundary(q); rec_accumulate(r0);
-        if (q + 1 < n) {
-          if (q + 2 < n) rec_load(r0, rec0 + (q + 2) * REC);
-          boundary(q + 1); rec_accumulate(r1);
-        }
-      }
-    } else {
-      for (int q = 0; q < n; q++) {
-        RecR cur; rec_load(cur, rec0 + q * REC);
-        boundary(q); rec_accumulate(cur);
-      }
+    for (int q = 0; q < n; q++) {
+      RecR cur; rec_load(cur, rec0 + q * REC);
+      boundary(q); rec_accumulate(cur);
     }
     __syncwarp(gmask);
     p = pn;
@@ -259,24 +249,19 @@ inline void cell_segments(int n2, int target, int *seglen, int *nseg) {
 }
 
 // returns 0 = launched, -1 = combination not covered (caller uses the atomic kernel), 1 = CUDA error
-template <int NB, bool PIPE>
-inline int cell_p2g3_launch_nb(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int seg_target, cudaStream_t st) {
-  const bool full = (what & P2G_FORCE) != 0;
+template <bool FULL, bool MASS, int NB>
+inline int cell_p2g3_launch_one(const SolidDev &s, const GridDev &g, const CellLists &cl, int seg_target, cudaStream_t st) {
   constexpr int GL = 16 / NB;
   int seglen, nseg; cell_segments(g.n[2], seg_target, &seglen, &nseg);
   const long long ngroups = (long long)g.n[0] * g.n[1] * nseg;
   const long long nb = (ngroups * GL + 127) / 128;
   if (nb >= (1ll << 31)) return -1;
-  if (full) {
-    if (NB == 4) return -1;
-    if (what & P2G_MASS) k_p2g_cell3<true, true, NB == 4 ? 1 : NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
-    else k_p2g_cell3<true, false, NB == 4 ? 1 : NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
-  } else k_p2g_cell3<false, false, NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+  k_p2g_cell3<FULL, MASS, NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
   return cudaGetLastError() != cudaSuccess;
 }
 
-// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4); pipe: software-pipelined record loads
-inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int pipe, int seg_target, cudaStream_t st, int *nlaunch) {
+// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4)
+inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int seg_target, cudaStream_t st, int *nlaunch) {
   *nlaunch = 0;
   const bool full = (what & P2G_FORCE) != 0;
   if (what & (P2G_MB | P2G_TEMP | P2G_HEAT)) return -1;
@@ -285,14 +270,11 @@ inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists
   if (!full && !(what & P2G_MOM)) return -1;
   int rc;
   if (full) {
-    if (pipe) rc = nb_full == 2 ? cell_p2g3_launch_nb<2, true>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, true>(s, g, cl, what, seg_target, st);
-    else rc = nb_full == 2 ? cell_p2g3_launch_nb<2, false>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, false>(s, g, cl, what, seg_target, st);
-  } else if (pipe) {
-    rc = nb_mom == 4 ? cell_p2g3_launch_nb<4, true>(s, g, cl, what, seg_target, st)
-       : (nb_mom == 2 ? cell_p2g3_launch_nb<2, true>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, true>(s, g, cl, what, seg_target, st));
+    if (what & P2G_MASS) rc = nb_full == 2 ? cell_p2g3_launch_one<true, true, 2>(s, g, cl, seg_target, st) : cell_p2g3_launch_one<true, true, 1>(s, g, cl, seg_target, st);
+    else rc = nb_full == 2 ? cell_p2g3_launch_one<true, false, 2>(s, g, cl, seg_target, st) : cell_p2g3_launch_one<true, false, 1>(s, g, cl, seg_target, st);
   } else {
-    rc = nb_mom == 4 ? cell_p2g3_launch_nb<4, false>(s, g, cl, what, seg_target, st)
-       : (nb_mom == 2 ? cell_p2g3_launch_nb<2, false>(s, g, cl, what, seg_target, st) : cell_p2g3_launch_nb<1, false>(s, g, cl, what, seg_target, st));
+    rc = nb_mom == 4 ? cell_p2g3_launch_one<false, false, 4>(s, g, cl, seg_target, st)
+       : (nb_mom == 2 ? cell_p2g3_launch_one<false, false, 2>(s, g, cl, seg_target, st) : cell_p2g3_launch_one<false, false, 1>(s, g, cl, seg_target, st));
   }
   if (rc == 0) *nlaunch = 1;
   return rc;
