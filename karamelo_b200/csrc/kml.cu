@@ -140,7 +140,7 @@ int kml_destroy(kml_ctx *c) {
   for (auto s : c->solids) { cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
-    cudaFree(c->comm.halo_recv); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
+    cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
     cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
   }
   cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage);
@@ -430,43 +430,27 @@ static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
   const int span = c->c.shape_function == KML_SHAPE_LINEAR ? 2 : 4;
   const int nsh = span - 1;
   const long long plane = (long long)g.n[1] * g.n[2], cnt = plane * nsh;
-  struct Field { double *ptr; int width; };
-  std::vector<Field> fields;
-  if (what & P2G_MOM) fields.push_back({(double *)g.nv, 4});
-  if (what & P2G_FORCE) for (int d = 0; d < 3; d++) fields.push_back({g.f[d], 1});
-  if (what & P2G_MB) for (int d = 0; d < 3; d++) fields.push_back({g.mb[d], 1});
-  if (what & P2G_TEMP) fields.push_back({g.T, 1});
-  if (what & P2G_HEAT) { fields.push_back({g.Qext, 1}); fields.push_back({g.Qint, 1}); }
-  size_t total = 0; for (auto &f : fields) total += (size_t)cnt * f.width;
-  const size_t need = total * 2 * sizeof(double);
-  if (need > cm.halo_bytes) { cudaFree(cm.halo_recv); CU(cudaMalloc(&cm.halo_recv, need)); cm.halo_bytes = need; }
-  const bool left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
-  double *rl = cm.halo_recv, *rr = cm.halo_recv + total;
+  HaloFields hf; hf.n = 0;
+  auto add = [&](double *p, int w, int skip_w) { hf.ptr[hf.n] = p; hf.width[hf.n] = w; hf.skip_w[hf.n] = skip_w; hf.n++; };
+  if (what & P2G_MOM) add((double *)g.nv, 4, (what & P2G_MASS) ? 0 : 1);
+  if (what & P2G_FORCE) for (int d = 0; d < 3; d++) add(g.f[d], 1, 0);
+  if (what & P2G_MB) for (int d = 0; d < 3; d++) add(g.mb[d], 1, 0);
+  if (what & P2G_TEMP) add(g.T, 1, 0);
+  if (what & P2G_HEAT) { add(g.Qext, 1, 0); add(g.Qint, 1, 0); }
+  if (hf.n == 0) return 0;
+  size_t total = 0; for (int f = 0; f < hf.n; f++) total += (size_t)cnt * hf.width[f];
+  const size_t need = total * 4 * sizeof(double);
+  if (need > cm.halo_bytes) { cudaFree(cm.halo_buf); cm.halo_buf = nullptr; CU(cudaMalloc(&cm.halo_buf, need)); cm.halo_bytes = need; }
+  const int left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+  double *sl = cm.halo_buf, *sr = sl + total, *rl = sr + total, *rr = rl + total;
+  const long long top = (long long)(g.n[0] - nsh) * plane;
+  k_halo_pack<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top, sl, sr, left, right);
   NC(nccl().GroupStart());
-  size_t off = 0;
-  for (auto &f : fields) {
-    const size_t n = (size_t)cnt * f.width;
-    if (left) { NC(nccl().Send(f.ptr, n, ncclDouble, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(rl + off, n, ncclDouble, cm.rank - 1, cm.comm, c->stream)); }
-    if (right) {
-      double *top = f.ptr + (size_t)(g.n[0] - nsh) * plane * f.width;
-      NC(nccl().Send(top, n, ncclDouble, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(rr + off, n, ncclDouble, cm.rank + 1, cm.comm, c->stream));
-    }
-    off += n;
-  }
+  if (left) { NC(nccl().Send(sl, total, ncclDouble, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(rl, total, ncclDouble, cm.rank - 1, cm.comm, c->stream)); }
+  if (right) { NC(nccl().Send(sr, total, ncclDouble, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(rr, total, ncclDouble, cm.rank + 1, cm.comm, c->stream)); }
   NC(nccl().GroupEnd());
-  off = 0;
-  for (auto &f : fields) {
-    const size_t n = (size_t)cnt * f.width;
-    for (int side = 0; side < 2; side++) {
-      if (!(side == 0 ? left : right)) continue;
-      double *dst = side == 0 ? f.ptr : f.ptr + (size_t)(g.n[0] - nsh) * plane * f.width;
-      const double *src = (side == 0 ? rl : rr) + off;
-      if (f.width == 4) k_halo_add_nv<<<nblocks(cnt, 256), 256, 0, c->stream>>>((double4 *)dst, (const double4 *)src, cnt, (what & P2G_MASS) ? 1 : 0);
-      else k_halo_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(dst, src, cnt);
-      c->launches[stage]++;
-    }
-    off += n;
-  }
+  k_halo_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top, rl, rr, left, right);
+  c->launches[stage] += 2;
   return check_launch("halo_sum");
 }
 

@@ -4,10 +4,12 @@
 // (src/ulmpm.cpp:565-667) + Solid::pack/unpack_particle (src/solid.cpp:1612-1808).
 //
 // The grid is cut along x (the slowest node index), so the planes shared with a neighbour are one
-// contiguous range of every node array: no pack kernel is needed for the halo - the partial sums are
-// sent straight from the arrays, received into scratch and added.  Both neighbours send their partial
-// sums and add what they receive (a + b == b + a in IEEE arithmetic), so both hold identical totals
-// after ONE exchange, where the reference needs a reduce and a broadcast-back.
+// contiguous range of every node array.  All exchanged fields are packed into ONE message per side
+// (one pack kernel, one grouped send/recv pair per neighbour, one add kernel): the exchange is latency-
+// bound (9 MB per side at 100 M particles), so the number of NCCL operations matters more than the two
+// extra passes over the planes.  Both neighbours send their partial sums and add what they receive
+// (a + b == b + a in IEEE arithmetic), so both hold identical totals after ONE exchange, where the
+// reference needs a reduce and a broadcast-back.
 #pragma once
 #include "kml_kernels.cuh"
 #include "kml_nccl.h"
@@ -17,7 +19,7 @@ namespace kml {
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  double *halo_recv = nullptr; size_t halo_bytes = 0;      // scratch for the received planes
+  double *halo_buf = nullptr; size_t halo_bytes = 0;       // scratch: [sendL | sendR | recvL | recvR] packed planes
   int *mig_cnt = nullptr;                                   // device: sendL, sendR, recvL, recvR, nhole, nfill
   int *mig_list = nullptr; int mig_cap = 0;                 // device: [2][mig_cap] leaving particle ids, then holes / fillers
   int *mig_flag = nullptr;                                  // device: [2 * mig_cap] leaver flags of the vacated tail
@@ -25,16 +27,36 @@ struct Comm {
   int *h_cnt = nullptr;                                     // pinned
 };
 
-__global__ void k_halo_add_nv(double4 *dst, const double4 *src, long long n, int add_mass) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 a = dst[i]; const double4 b = src[i];
-  a.x += b.x; a.y += b.y; a.z += b.z; if (add_mass) a.w += b.w;
-  dst[i] = a;
+// Shared planes of every exchanged field -> one contiguous message per side, and back (adding).  A field is `width`
+// doubles per node; the planes shared with the left neighbour start at node 0, those shared with the right one at
+// node (n0 - nsh) * plane.  Message layout: field after field, each cnt * width doubles.
+struct HaloFields { double *ptr[12]; int width[12]; int skip_w[12]; int n; }; // skip_w: do not add component 3 (the mass of a momentum-only pass)
+__global__ void k_halo_pack(HaloFields hf, long long cnt, long long top_off_nodes, double *outL, double *outR, int left, int right) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // node within the shared planes
+  if (i >= cnt) return;
+  long long off = 0;
+  for (int f = 0; f < hf.n; f++) {
+    const int w = hf.width[f];
+    for (int k = 0; k < w; k++) {
+      if (left) outL[off + i * w + k] = hf.ptr[f][i * w + k];
+      if (right) outR[off + i * w + k] = hf.ptr[f][(top_off_nodes + i) * w + k];
+    }
+    off += cnt * w;
+  }
 }
-__global__ void k_halo_add(double *dst, const double *src, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] += src[i];
+__global__ void k_halo_add(HaloFields hf, long long cnt, long long top_off_nodes, const double *inL, const double *inR, int left, int right) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  long long off = 0;
+  for (int f = 0; f < hf.n; f++) {
+    const int w = hf.width[f];
+    for (int k = 0; k < w; k++) {
+      if (k == 3 && hf.skip_w[f]) continue;
+      if (left) hf.ptr[f][i * w + k] += inL[off + i * w + k];
+      if (right) hf.ptr[f][(top_off_nodes + i) * w + k] += inR[off + i * w + k];
+    }
+    off += cnt * w;
+  }
 }
 
 // ---- migration ---------------------------------------------------------------------------------

@@ -76,7 +76,7 @@ def step(args):
     rank, world, _, dist = slab.init_distributed()
     assert torch.cuda.is_available()
     cells = tuple(args.cells)
-    script = block(cells, args.scheme, args.shape, a=2.5e-3, drift=args.drift)
+    script = block(cells, args.scheme, args.shape, a=args.a, drift=args.drift)
     fields = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "VOL")
     eng = slab.make_engine(None)
     eng.script(script)
@@ -115,5 +115,12 @@ if __name__ == "__main__":
     ap.add_argument("--scheme", default="musl")
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--drift", type=float, default=0.0)
+    ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
     a = ap.parse_args()
-    {"partition": partition, "step": step}[a.mode](a)
+    try:
+        {"partition": partition, "step": step}[a.mode](a)
+    except BaseException as exc:  # one line the launching test can show, whatever the launcher then does to the other ranks
+        import traceback
+        print("SLAB-FAIL rank %s: %s: %s | %s" % (os.environ.get("RANK", "0"), type(exc).__name__, str(exc)[:1500],
+                                                 traceback.format_exc().strip().splitlines()[-3][:200]), flush=True)
+        raise
