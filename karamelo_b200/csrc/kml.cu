@@ -4,6 +4,7 @@
 #include "kml_launch.h"
 #include "kml_gather_cell2.cuh"
 #include "kml_comm.cuh"
+#include "kml_cpdi.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,7 @@ struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
   bool moved = false;     // xn holds the positions after grid_to_points (UL)
   bool mbp_nonzero = false;
+  CpdiDev cp{}; double *cpbuf = nullptr; int *cpibuf = nullptr; // CPDI neighbour lists and particle domains
   double *red = nullptr;  // device: [0] max wave speed, [1] min_h_ratio
   double dtCFL = 1.0e22;
 };
@@ -40,7 +42,7 @@ struct kml_ctx {
   unsigned *d_flags = nullptr; double *d_scratch = nullptr; // scratch: small reduction outputs
   double *h_pinned = nullptr;                                // pinned readback buffer
   void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
-  bool tl_mass_done = false;
+  bool tl_mass_done = false, tl_wf_done = false;
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
@@ -110,7 +112,8 @@ const char *kml_last_error(void) { return g_err.c_str(); }
 const char *kml_backend(void) { return "cuda-sm_100a"; }
 
 int kml_create(const kml_config *cfg, kml_ctx **out) {
-  if (cfg->is_CPDI) return fail("kml: CPDI (ulcpdi/tlcpdi) is not implemented in the CUDA engine yet");
+  if (cfg->is_CPDI && cfg->dimension != 2) return fail("Error: ULCPDI is only 2D....\n"); // src/ulcpdi.cpp:115-118, src/tlcpdi.cpp:102-104
+  if (cfg->is_CPDI && (cfg->axisymmetric || cfg->temp)) return fail("kml: CPDI with axisymmetry / thermo-mechanical coupling is not implemented in the CUDA engine");
   if (cfg->ge) return fail("kml: gradient-enhanced mapping is not implemented in the CUDA engine yet");
   if (cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP) return fail("kml: APIC / AFLIP / ASFLIP / MLS are not implemented in the CUDA engine yet");
   int ndev = 0;
@@ -137,7 +140,7 @@ int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
-  for (auto s : c->solids) { cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
+  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
@@ -291,6 +294,18 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   }
   CU(cudaMemcpyAsync(s.rho0, rho.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(s.mask, m1.data(), sizeof(int) * d->np, cudaMemcpyHostToDevice, c->stream));
+  if (c->c.is_CPDI) {
+    CpdiDev &cp = S->cp; cp.style = c->c.cpdi_style; cp.cap = cap; cp.maxn = c->c.shape_function == KML_SHAPE_LINEAR ? 16 : CPDI_MAXN;
+    const size_t per = (size_t)cp.maxn * cap;
+    CU(cudaMalloc(&S->cpibuf, sizeof(int) * (cap + per))); CU(cudaMemsetAsync(S->cpibuf, 0, sizeof(int) * (cap + per), c->stream));
+    CU(cudaMalloc(&S->cpbuf, sizeof(double) * (7 * per + 24 * cap))); CU(cudaMemsetAsync(S->cpbuf, 0, sizeof(double) * (7 * per + 24 * cap), c->stream));
+    cp.n = S->cpibuf; cp.node = S->cpibuf + cap;
+    double *q = S->cpbuf; auto takep = [&](size_t n) { double *r = q; q += n; return r; };
+    cp.wf = takep(per); cp.wfd[0] = takep(per); cp.wfd[1] = takep(per);
+    for (int k = 0; k < 4; k++) cp.wfc[k] = takep(per);
+    for (int k = 0; k < 2; k++) for (int d2 = 0; d2 < 2; d2++) { cp.rp[k][d2] = takep(cap); cp.rp0[k][d2] = takep(cap); }
+    for (int k = 0; k < 4; k++) for (int d2 = 0; d2 < 2; d2++) { cp.xpc[k][d2] = takep(cap); cp.xpc0[k][d2] = takep(cap); }
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->solids.push_back(S); *sid = (int)c->solids.size() - 1; return 0;
 }
@@ -320,6 +335,19 @@ static int solid_field(kml_ctx *c, Solid *S, int field, double **comp, int *ncom
 }
 static const int SYM_OF[9] = {0, 3, 4, 3, 1, 5, 4, 5, 2}; // row-major (a,b) -> (xx,yy,zz,xy,xz,yz)
 
+// CPDI domain fields: host rows [np][2][3] (RP, RP0) / [np][4][3] (XPC, XPC0); the device keeps the x, y components
+static bool cpdi_rowmap(Solid *S, int field, RowMap &rm) {
+  CpdiDev &cp = S->cp; if (!S->cpbuf) return false;
+  const bool r = field == KML_P_RP || field == KML_P_RP0, x = field == KML_P_XPC || field == KML_P_XPC0;
+  if (!r && !x) return false;
+  const int nv = r ? 2 : 4; rm.ncols = 3 * nv; rm.ncomp = 2 * nv;
+  for (int k = 0; k < nv; k++) for (int d = 0; d < 2; d++) {
+    rm.comp[2 * k + d] = field == KML_P_RP ? cp.rp[k][d] : (field == KML_P_RP0 ? cp.rp0[k][d] : (field == KML_P_XPC ? cp.xpc[k][d] : cp.xpc0[k][d]));
+    rm.col[2 * k + d] = 3 * k + d;
+  }
+  return true;
+}
+
 int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   CU(cudaSetDevice(c->dev));
   Solid *S = c->solids[sid]; const long long np = S->s.np;
@@ -327,6 +355,14 @@ int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   if (field == KML_P_MASK) { CU(cudaMemcpyAsync(S->s.mask, src, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_P_X && !c->c.is_TL) S->moved = false;
   if (field == KML_P_MBP) S->mbp_nonzero = true;
+  { RowMap rm;
+    if (cpdi_rowmap(S, field, rm)) {
+      if (stage_reserve(c, sizeof(double) * np * rm.ncols)) return 1;
+      CU(cudaMemcpyAsync(c->d_stage, src, sizeof(double) * np * rm.ncols, cudaMemcpyHostToDevice, c->stream));
+      k_rows_to_soa<<<nblocks(np, 256), 256, 0, c->stream>>>((const double *)c->d_stage, rm, np);
+      if (check_launch("k_rows_to_soa")) return 1;
+      CU(cudaStreamSynchronize(c->stream)); return 0;
+    } }
   double *comp[9]; int nc; bool sym;
   if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
   // rows [np][ncols] on the host -> SoA components on the device: one H2D copy + a transposition kernel
@@ -357,6 +393,15 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
     }
     return 0;
   }
+  { RowMap rm;
+    if (cpdi_rowmap(S, field, rm)) {
+      if (stage_reserve(c, sizeof(double) * np * rm.ncols)) return 1;
+      CU(cudaMemsetAsync(c->d_stage, 0, sizeof(double) * np * rm.ncols, c->stream)); // the z components
+      k_soa_to_rows<<<nblocks(np, 256), 256, 0, c->stream>>>((double *)c->d_stage, rm, np);
+      if (check_launch("k_soa_to_rows")) return 1;
+      CU(cudaMemcpyAsync(dst, c->d_stage, sizeof(double) * np * rm.ncols, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream)); return 0;
+    } }
   double *comp[9]; int nc; bool sym;
   if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
   const int ncols = sym ? 9 : nc;
@@ -388,8 +433,30 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   // Weights are functions of the step-start positions: make the positions advanced by
   // the previous step current.  UL re-bins the particles by cell for the cell-centric P2G.
-  if (!c->c.is_TL) {
+  if (!c->c.is_TL)
     for (Solid *S : c->solids) if (S->moved) { for (int k = 0; k < 3; k++) std::swap(S->s.x[k], S->s.xn[k]); S->moved = false; }
+  if (c->c.is_CPDI) { // explicit per-particle lists: every step for UL, once for TL (update_wf, src/tlcpdi.cpp:100,351)
+    if (c->c.is_TL && c->tl_wf_done) return 0;
+    StageTimer t(c, KML_STAGE_REBIN);
+    for (Solid *S : c->solids) {
+      Grid *G = c->grids[S->d.grid];
+      const unsigned nb = nblocks(S->s.np, 64);
+#define KML_CPDI_W(SH) do { if (c->c.is_TL) k_cpdi_weights<SH, true><<<nb, 64, 0, c->stream>>>(S->s, G->g, S->cp, c->c.boxlo[0], c->c.boxlo[1], c->d_flags); \
+                            else k_cpdi_weights<SH, false><<<nb, 64, 0, c->stream>>>(S->s, G->g, S->cp, c->c.boxlo[0], c->c.boxlo[1], c->d_flags); } while (0)
+      switch (c->c.shape_function) {
+      case KML_SHAPE_LINEAR: KML_CPDI_W(KML_SHAPE_LINEAR); break;
+      case KML_SHAPE_CUBIC_SPLINE: KML_CPDI_W(KML_SHAPE_CUBIC_SPLINE); break;
+      case KML_SHAPE_QUADRATIC_SPLINE: KML_CPDI_W(KML_SHAPE_QUADRATIC_SPLINE); break;
+      default: KML_CPDI_W(KML_SHAPE_BERNSTEIN); break;
+      }
+#undef KML_CPDI_W
+      c->launches[KML_STAGE_REBIN]++;
+      if (check_launch("k_cpdi_weights")) return 1;
+    }
+    c->tl_wf_done = true;
+    return 0;
+  }
+  if (!c->c.is_TL) {
     if (c->use_cell_p2g && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StageTimer t(c, KML_STAGE_REBIN);
       for (Solid *S : c->solids) {
@@ -483,6 +550,11 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
+    if (!done && c->c.is_CPDI) {
+      if (TL) k_cpdi_p2g<true><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, g, S->cp, what);
+      else k_cpdi_p2g<false><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, g, S->cp, what);
+      c->launches[stage]++; done = true;
+    }
     if (!done) {
       KML_DISPATCH(p2g, S->s, g, sp, what, c->stream);
       c->launches[stage]++;
@@ -537,7 +609,10 @@ int kml_advance_particles(kml_ctx *c) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
-    if (rc < 0) KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
+    if (c->c.is_CPDI) {
+      if (c->c.is_TL) k_cpdi_g2p<true><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp);
+      else k_cpdi_g2p<false><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp);
+    } else if (rc < 0) KML_DISPATCH(g2p, S->s, G->g, sp, c->stream);
     c->launches[KML_STAGE_G2P]++;
     if (check_launch("k_g2p")) return 1;
     if (!c->c.is_TL) S->moved = true;
@@ -594,7 +669,10 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
       rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
     }
-    if (rc < 0) KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);
+    if (c->c.is_CPDI) {
+      if (c->c.is_TL) k_cpdi_stress<true><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp, tp, S->d.mat);
+      else k_cpdi_stress<false><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp, tp, S->d.mat);
+    } else if (rc < 0) KML_DISPATCH(stress, S->s, G->g, sp, tp, S->d.mat, c->stream);
     c->launches[KML_STAGE_STRESS]++;
     if (check_launch("k_stress")) return 1;
   }
@@ -615,7 +693,7 @@ int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
   CU(cudaMemcpyAsync(c->h_pinned + 2 * ns, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   unsigned flags; memcpy(&flags, c->h_pinned + 2 * ns, sizeof flags);
-  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed)");
+  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
     Solid *S = c->solids[i]; Grid *G = c->grids[S->d.grid];

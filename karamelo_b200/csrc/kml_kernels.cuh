@@ -310,7 +310,8 @@ __device__ __forceinline__ void sym_to_full(const double *a, double *m) { // (xx
 
 template <bool TL>
 __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev &g, const StepParams &sp, const kml_material &mat, long long ip,
-                                                const PState &ps, double *L, const double *qv, double &wave, double &hr) {
+                                                const PState &ps, double *L, const double *qv, double &wave, double &hr,
+                                                double vol_cpdi = -1.0) { // vol_cpdi >= 0: CPDI-Q4 volume (area of the corner polygon)
   const double dt = sp.dt;
   double F[9], Fn[9];
 #pragma unroll
@@ -327,10 +328,11 @@ __device__ __forceinline__ void particle_stress(const SolidDev &s, const GridDev
   }
 #pragma unroll
   for (int i = 0; i < 9; i++) s.F[i][ip] = Fn[i];
-  double Finv[9]; const double iJ = inv3(Fn, Finv);
-  const double J = det3(Fn);
+  double Finv[9]; double iJ = inv3(Fn, Finv);
   const double vol0 = ps.vol0;
-  const double vol = J * vol0;
+  double J, vol;
+  if (vol_cpdi >= 0.0) { vol = vol_cpdi; J = vol / vol0; iJ = 1.0 / J; } // src/solid.cpp:1188-1201
+  else { J = det3(Fn); vol = J * vol0; }
   s.vol[ip] = vol;
   const double damage_old = ps.dmg;
   if (J <= 0.0 && damage_old < 1.0) atomicOr(sp.flags, 2u);

@@ -121,6 +121,10 @@ Var Sim::cmd_method(std::vector<std::string> &a) {
   // Method::setup: APIC/MLS force PIC_FLIP = 0 (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   if (!is_TL && (sub_method == KML_SUB_APIC || sub_method == KML_SUB_MLS)) PIC_FLIP = 0;
   if (is_TL && sub_method == KML_SUB_APIC) PIC_FLIP = 0;
+  // ULCPDI::advance_particles blends with its OWN member `FLIP` (src/ulcpdi.cpp:468, declared src/ulcpdi.h:31), which no code
+  // ever assigns: the ratio given in the script is ignored and the freshly allocated Method object holds 0.0, i.e. the
+  // reference's ULCPDI is pure PIC whatever the script says (verified against the reference build: bit-identical with 0).
+  if (method_type == "ulcpdi") PIC_FLIP = 0;
   method_set = true;
   return Var(0);
 }
@@ -476,6 +480,9 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
     for (int k = 0; k < ppc; k++) for (int i = 0; i < ppc; i++) for (int j = 0; j < ppc; j++) { ip.push_back((i + 0.5) * d - 0.5); ip.push_back((j + 0.5) * d - 0.5); ip.push_back((k + 0.5) * d - 0.5); }
   }
   mass_ /= (double)nip; vol_ /= (double)nip;
+  // CPDI half-length of the particle domain, src/solid.cpp:2025-2027 (lp = delta), :2033,2053,2067,2105 (scaled by the lattice)
+  double lp = delta;
+  if (ppc == 1) lp *= 0.5; else if (ppc == 2) lp *= 0.25; else if (ppc == 3) lp *= 1.0 / 6.0; else lp *= 1.0 / (2 * ppc);
 
   s.x0.clear();
   const int dim = dimension;
@@ -536,6 +543,21 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   check(kml_solid_upload(ctx, s.dev, KML_P_VOL0, vol.data()));
   check(kml_solid_upload(ctx, s.dev, KML_P_VOL, vol.data()));
   if (temp) check(kml_solid_upload(ctx, s.dev, KML_P_T, T.data()));
+  if (is_CPDI) { // particle domains, src/solid.cpp:2186-2247: R4 domain vectors / Q4 corner positions (2-D)
+    if (dimension != 2) fatal("Error: ULCPDI is only 2D....\n");
+    if (cpdi_style == 0) {
+      std::vector<std::array<double, 3>> rp(2 * s.np);
+      for (int64_t i = 0; i < s.np; i++) { rp[2 * i] = {lp, 0, 0}; rp[2 * i + 1] = {0, lp, 0}; }
+      check(kml_solid_upload(ctx, s.dev, KML_P_RP0, rp.data())); check(kml_solid_upload(ctx, s.dev, KML_P_RP, rp.data()));
+    } else {
+      std::vector<std::array<double, 3>> xc(4 * s.np);
+      for (int64_t i = 0; i < s.np; i++) {
+        const double x = s.x0[i][0], y = s.x0[i][1];
+        xc[4 * i] = {x - lp, y - lp, 0}; xc[4 * i + 1] = {x + lp, y - lp, 0}; xc[4 * i + 2] = {x + lp, y + lp, 0}; xc[4 * i + 3] = {x - lp, y + lp, 0};
+      }
+      check(kml_solid_upload(ctx, s.dev, KML_P_XPC0, xc.data())); check(kml_solid_upload(ctx, s.dev, KML_P_XPC, xc.data()));
+    }
+  }
   // Solid::init totals, src/solid.cpp:170-195
   s.vtot = s.mtot = 0; for (int64_t i = 0; i < s.np; i++) { s.vtot += vol[i]; s.mtot += mass[i]; }
   if (!quiet) std::cout << "Solid " << s.id << ": np=" << s.np << " total volume = " << s.vtot << " total mass = " << s.mtot << " grid " << s.grid->desc.n[0] << "x" << s.grid->desc.n[1] << "x" << s.grid->desc.n[2] << std::endl;

@@ -157,6 +157,10 @@ struct OSolid {
   std::vector<std::vector<Vec3>> wfd_pn, wfd_np;
   double dtCFL; double max_p_wave_speed;
   Mat3 Di; int np_per_cell;
+  // CPDI (reference src/solid.h: nc, rp, rp0, xpc, xpc0, wf_pn_corners): domain vectors (R4) / corner positions (Q4)
+  int nc = 0;
+  std::vector<Vec3> rp, rp0, xpc, xpc0;
+  std::vector<std::vector<double>> wf_pn_corners;
 };
 
 struct kml_ctx {
@@ -180,7 +184,7 @@ const char *kml_last_error(void) { return g_err.c_str(); }
 const char *kml_backend(void) { return "oracle-cpu"; }
 
 int kml_create(const kml_config *cfg, kml_ctx **out) {
-  if (cfg->is_CPDI) return fail("oracle: CPDI not restated");
+  if (cfg->is_CPDI && cfg->dimension != 2) return fail("Error: ULCPDI is only 2D....\n"); // src/ulcpdi.cpp:115-118, src/tlcpdi.cpp:102-104
   kml_ctx *c = new kml_ctx();
   c->c = *cfg; c->dt = 1e-16; /* reference src/update.cpp:38 */
   c->update_wf = true; c->update_mass_nodes = true; c->flags = 0; c->rigid_solids = 0; c->update_Di = true;
@@ -285,6 +289,12 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   int64_t nn = c->grids[d->grid]->nn;
   s->neigh_np.resize(nn); s->wf_np.resize(nn); s->wfd_np.resize(nn);
   s->dtCFL = 1.0e22; s->max_p_wave_speed = 0; s->Di.setIdentity(); s->np_per_cell = 2;
+  if (c->c.is_CPDI) { // src/solid.cpp:83-88 (nc = 2^dim), :249-259, :299-300
+    s->nc = 1 << c->c.dimension;
+    s->rp.assign(c->c.dimension * n, z3); s->rp0.assign(c->c.dimension * n, z3);
+    s->xpc.assign(s->nc * n, z3); s->xpc0.assign(s->nc * n, z3);
+    s->wf_pn_corners.resize(s->nc * n);
+  }
   c->solids.push_back(s); *sid = (int)c->solids.size() - 1; return 0;
 }
 int kml_solid_np(kml_ctx *c, int sid, int64_t *np) { *np = c->solids[sid]->np; return 0; }
@@ -303,6 +313,8 @@ int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   case KML_P_IENERGY: get1(s->ienergy, src); break; case KML_P_MASK: get1(s->mask, src); break;
   case KML_P_T: get1(s->T, src); break; case KML_P_GAMMA: get1(s->gamma, src); break; case KML_P_Q: get3(s->q, src); break;
   case KML_P_J: get1(s->J, src); break;
+  case KML_P_RP: get3(s->rp, src); break; case KML_P_RP0: get3(s->rp0, src); break;
+  case KML_P_XPC: get3(s->xpc, src); break; case KML_P_XPC0: get3(s->xpc0, src); break;
   default: return fail("solid_upload: bad field");
   }
   return 0;
@@ -321,6 +333,8 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
   case KML_P_DAMAGE: put1(s->damage, dst); break; case KML_P_DAMAGE_INIT: put1(s->damage_init, dst); break;
   case KML_P_IENERGY: put1(s->ienergy, dst); break; case KML_P_MASK: put1(s->mask, dst); break;
   case KML_P_T: put1(s->T, dst); break; case KML_P_GAMMA: put1(s->gamma, dst); break; case KML_P_Q: put3(s->q, dst); break;
+  case KML_P_RP: put3(s->rp, dst); break; case KML_P_RP0: put3(s->rp0, dst); break;
+  case KML_P_XPC: put3(s->xpc, dst); break; case KML_P_XPC0: put3(s->xpc0, dst); break;
   default: return fail("solid_download: bad field");
   }
   return 0;
@@ -350,7 +364,106 @@ static int compute_inertia_tensor(kml_ctx *c, OSolid *s) {
 
 // ULMPM::compute_grid_weight_functions_and_gradients, reference src/ulmpm.cpp:88-337
 // TLMPM::compute_grid_weight_functions_and_gradients, reference src/tlmpm.cpp:87-340
+// ULCPDI / TLCPDI::compute_grid_weight_functions_and_gradients, reference src/ulcpdi.cpp:111-393, src/tlcpdi.cpp:98-351.
+// The particle's domain is a parallelogram (R4: x +- r1 +- r2) or a quadrilateral with advected corners (Q4); its
+// neighbour nodes are the union of the corners' stencils, the weight is the corner average (R4) or the area-weighted
+// corner combination (Q4) of the corners' shape functions, and the gradient follows from the domain geometry.
+static int cpdi_weights(kml_ctx *c) {
+  const bool TL = c->c.is_TL;
+  if (TL && !c->update_wf) return 0;
+  const int sf = c->c.shape_function, style = c->c.cpdi_style, dim = c->c.dimension;
+  for (OSolid *s : c->solids) {
+    OGrid *g = c->grids[s->grid];
+    const int nc = s->nc; const int64_t nnodes = g->nn; const int ny = g->ny, nz = g->nz;
+    const double inv_cellsize = 1.0 / g->d.cellsize;
+    const std::vector<Vec3> &xp = TL ? s->x0 : s->x;
+    const double *boxlo = c->c.boxlo; // both methods index the candidate nodes from domain->boxlo (src/tlcpdi.cpp:200-222)
+    for (int64_t in = 0; in < nnodes; in++) { s->neigh_np[in].clear(); s->wf_np[in].clear(); s->wfd_np[in].clear(); }
+    std::vector<int> n_neigh; std::vector<Vec3> xcorner(nc); std::vector<double> wfc(nc, 0.0);
+    for (int64_t ip = 0; ip < s->np; ip++) {
+      s->neigh_pn[ip].clear(); s->wf_pn[ip].clear(); s->wfd_pn[ip].clear();
+      for (int ic = 0; ic < nc; ic++) s->wf_pn_corners[nc * ip + ic].clear();
+      n_neigh.clear();
+      if (style == 0) { // CPDI-R4 corners from the domain vectors
+        xcorner[0] = xp[ip] - s->rp[2 * ip] - s->rp[2 * ip + 1];
+        xcorner[1] = xp[ip] + s->rp[2 * ip] - s->rp[2 * ip + 1];
+        xcorner[2] = xp[ip] + s->rp[2 * ip] + s->rp[2 * ip + 1];
+        xcorner[3] = xp[ip] - s->rp[2 * ip] + s->rp[2 * ip + 1];
+      }
+      for (int ic = 0; ic < nc; ic++) {
+        if (style == 1) xcorner[ic] = s->xpc[nc * ip + ic];
+        int i0, j0, k0, m;
+        if (sf == KML_SHAPE_LINEAR) {
+          i0 = (int)((xcorner[ic][0] - boxlo[0]) * inv_cellsize); j0 = (int)((xcorner[ic][1] - boxlo[1]) * inv_cellsize);
+          k0 = (int)((xcorner[ic][2] - boxlo[2]) * inv_cellsize); m = 2;
+        } else if (sf == KML_SHAPE_BERNSTEIN) {
+          i0 = 2 * (int)((xcorner[ic][0] - boxlo[0]) * inv_cellsize); j0 = 2 * (int)((xcorner[ic][1] - boxlo[1]) * inv_cellsize);
+          k0 = 2 * (int)((xcorner[ic][2] - boxlo[2]) * inv_cellsize);
+          if ((i0 >= 1) && (i0 % 2 != 0)) i0--;
+          if ((j0 >= 1) && (j0 % 2 != 0)) j0--;
+          if (nz > 1) if ((k0 >= 1) && (k0 % 2 != 0)) k0--;
+          m = 3;
+        } else {
+          i0 = (int)((xcorner[ic][0] - boxlo[0]) * inv_cellsize - 1); j0 = (int)((xcorner[ic][1] - boxlo[1]) * inv_cellsize - 1);
+          k0 = (int)((xcorner[ic][2] - boxlo[2]) * inv_cellsize - 1); m = 4;
+        }
+        for (int i = i0; i < i0 + m; i++) {
+          if (ny > 1) {
+            for (int j = j0; j < j0 + m; j++) {
+              if (nz > 1) { for (int k = k0; k < k0 + m; k++) { int64_t n = (int64_t)nz * ny * i + (int64_t)nz * j + k; if (n >= 0 && n < nnodes) n_neigh.push_back((int)n); } }
+              else { int64_t n = (int64_t)ny * i + j; if (n >= 0 && n < nnodes) n_neigh.push_back((int)n); }
+            }
+          } else if (i >= 0 && i < nnodes) n_neigh.push_back(i);
+        }
+      }
+      std::sort(n_neigh.begin(), n_neigh.end());
+      n_neigh.erase(std::unique(n_neigh.begin(), n_neigh.end()), n_neigh.end());
+      const double inv_Vp = 1.0 / s->vol[ip];
+      double a = 0, b = 0, alpha_over_Vp = 0, sixVp = 0;
+      if (style == 1) {
+        a = (xcorner[3][0] - xcorner[0][0]) * (xcorner[1][1] - xcorner[2][1]) - (xcorner[1][0] - xcorner[2][0]) * (xcorner[3][1] - xcorner[0][1]);
+        b = (xcorner[2][0] - xcorner[3][0]) * (xcorner[0][1] - xcorner[1][1]) - (xcorner[0][0] - xcorner[1][0]) * (xcorner[2][1] - xcorner[3][1]);
+        alpha_over_Vp = 0.0417 * inv_Vp; sixVp = 6 * s->vol[ip];
+      }
+      for (int in : n_neigh) {
+        double wf = 0;
+        for (int ic = 0; ic < nc; ic++) {
+          Vec3 r = (xcorner[ic] - g->x0[in]) * inv_cellsize;
+          double p0 = c->bf(r[0], g->ntype[in][0]), p1 = c->bf(r[1], g->ntype[in][1]);
+          double p2 = dim == 3 ? c->bf(r[2], g->ntype[in][2]) : 1;
+          wfc[ic] = p0 * p1 * p2;
+          if (style == 0 && wfc[ic] > 1.0e-12) wf += wfc[ic];
+        }
+        if (style == 0) wf *= 0.25;
+        if (style == 1) wf = alpha_over_Vp * ((sixVp - a - b) * wfc[0] + (sixVp - a + b) * wfc[1] + (sixVp + a + b) * wfc[2] + (sixVp + a - b) * wfc[3]);
+        if (!(wf > 1.0e-12)) continue;
+        Vec3 wfd;
+        if (style == 0) {
+          const Vec3 &r1 = s->rp[dim * ip], &r2 = s->rp[dim * ip + 1];
+          wfd[0] = (wfc[0] - wfc[2]) * (r1[1] - r2[1]) + (wfc[1] - wfc[3]) * (r1[1] + r2[1]);
+          wfd[1] = (wfc[0] - wfc[2]) * (r2[0] - r1[0]) - (wfc[1] - wfc[3]) * (r1[0] + r2[0]);
+          wfd[2] = 0;
+          wfd = wfd * inv_Vp;
+        } else {
+          wfd[0] = wfc[0] * (xcorner[1][1] - xcorner[3][1]) + wfc[1] * (xcorner[2][1] - xcorner[0][1]) + wfc[2] * (xcorner[3][1] - xcorner[1][1]) + wfc[3] * (xcorner[0][1] - xcorner[2][1]);
+          wfd[1] = wfc[0] * (xcorner[3][0] - xcorner[1][0]) + wfc[1] * (xcorner[0][0] - xcorner[2][0]) + wfc[2] * (xcorner[1][0] - xcorner[3][0]) + wfc[3] * (xcorner[2][0] - xcorner[0][0]);
+          wfd[2] = 0;
+          wfd = wfd * (0.5 * inv_Vp);
+          for (int ic = 0; ic < nc; ic++) s->wf_pn_corners[nc * ip + ic].push_back(wfc[ic]);
+        }
+        s->neigh_pn[ip].push_back(in); s->neigh_np[in].push_back((int)ip);
+        s->wf_pn[ip].push_back(wf); s->wf_np[in].push_back(wf);
+        s->wfd_pn[ip].push_back(wfd); s->wfd_np[in].push_back(wfd);
+      }
+    }
+    if (c->c.sub_method == KML_SUB_APIC) if (compute_inertia_tensor(c, s)) return 1;
+  }
+  if (TL) c->update_wf = false;
+  return 0;
+}
+
 int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
+  if (c->c.is_CPDI) return cpdi_weights(c);
   const bool TL = c->c.is_TL;
   if (TL && !c->update_wf) return 0;
   const int dim = c->c.dimension; const int sf = c->c.shape_function;
@@ -679,6 +792,33 @@ static bool inside_box(const kml_config &cf, const Vec3 &x) { // Domain::inside,
 //  ASFLIP: compute_particle_accelerations_velocities, src/solid.cpp:637-694) ; update_particle_temperature src/solid.cpp:2798-2808
 int kml_grid_to_points(kml_ctx *c) {
   double inv_dt = 1.0 / c->dt;
+  if (c->c.is_CPDI) { // ULCPDI/TLCPDI::grid_to_points: compute_particle_velocities_and_positions + compute_particle_acceleration (src/solid.cpp:696-784)
+    const bool corners = c->c.cpdi_style == 1;
+    for (OSolid *s : c->solids) {
+      OGrid *g = c->grids[s->grid]; const int nc = s->nc;
+      std::vector<Vec3> vc(nc);
+      for (int64_t ip = 0; ip < s->np; ip++) {
+        s->v_update[ip].setZero();
+        if (corners) for (int ic = 0; ic < nc; ic++) vc[ic].setZero();
+        for (size_t j = 0; j < s->neigh_pn[ip].size(); j++) {
+          int in = s->neigh_pn[ip][j];
+          s->v_update[ip] += s->wf_pn[ip][j] * g->v_update[in];
+          s->x[ip] += c->dt * s->wf_pn[ip][j] * g->v_update[in];
+          if (corners) for (int ic = 0; ic < nc; ic++) vc[ic] += s->wf_pn_corners[nc * ip + ic][j] * g->v_update[in];
+        }
+        if (!c->c.is_TL && !inside_box(c->c, s->x[ip])) { c->flags |= 1; return fail("Particle left the domain"); }
+        if (corners) for (int ic = 0; ic < nc; ic++) s->xpc[nc * ip + ic] += c->dt * vc[ic];
+      }
+      for (int64_t ip = 0; ip < s->np; ip++) {
+        s->a[ip].setZero();
+        if (s->mat.rigid) continue;
+        for (size_t j = 0; j < s->neigh_pn[ip].size(); j++) { int in = s->neigh_pn[ip][j]; s->a[ip] += s->wf_pn[ip][j] * (g->v_update[in] - g->v[in]); }
+        s->a[ip] *= inv_dt;
+        s->f[ip] = s->a[ip] * s->mass[ip];
+      }
+    }
+    return 0;
+  }
   for (OSolid *s : c->solids) {
     OGrid *g = c->grids[s->grid];
     if (s->mat.rigid) {
@@ -787,8 +927,15 @@ int kml_update_deformation_gradient(kml_ctx *c) {
       if (c->c.is_TL) s->F[ip] += c->dt * s->Fdot[ip];
       else s->F[ip] = (eye + c->dt * s->L[ip]) * s->F[ip];
       s->Finv[ip] = s->F[ip].inverse();
-      s->J[ip] = s->F[ip].determinant();
-      s->vol[ip] = s->J[ip] * s->vol0[ip];
+      if (c->c.is_CPDI && c->c.cpdi_style == 1) { // CPDI-Q4: the volume is the area of the corner polygon, src/solid.cpp:1188-1201
+        const Vec3 *q = &s->xpc[s->nc * ip];
+        s->vol[ip] = 0.5 * (q[0][0] * q[1][1] - q[1][0] * q[0][1] + q[1][0] * q[2][1] - q[2][0] * q[1][1] + q[2][0] * q[3][1] - q[3][0] * q[2][1] +
+                            q[3][0] * q[0][1] - q[0][0] * q[3][1]);
+        s->J[ip] = s->vol[ip] / s->vol0[ip];
+      } else {
+        s->J[ip] = s->F[ip].determinant();
+        s->vol[ip] = s->J[ip] * s->vol0[ip];
+      }
       if (s->J[ip] <= 0.0 && s->damage[ip] < 1.0) { c->flags |= 2; return fail("J<=0"); }
       s->rho[ip] = s->rho0[ip] / s->J[ip];
       if (!nh) {
@@ -800,6 +947,8 @@ int kml_update_deformation_gradient(kml_ctx *c) {
         } else s->D[ip] = 0.5 * (s->L[ip] + s->L[ip].transpose());
       }
     }
+    if (c->c.is_CPDI && !c->c.is_TL && c->c.cpdi_style == 0) // ULCPDI::update_deformation_gradient -> Solid::update_particle_domain, src/solid.cpp:2338-2352
+      for (int64_t ip = 0; ip < s->np; ip++) { s->rp[2 * ip] = s->F[ip] * s->rp0[2 * ip]; s->rp[2 * ip + 1] = s->F[ip] * s->rp0[2 * ip + 1]; }
   }
   return 0;
 }

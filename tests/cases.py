@@ -263,6 +263,37 @@ set_dt(1e-6)
 """
 
 
+# convected particle domain interpolation (2-D), the reference's Vertical_bar CPDI example
+# (examples/Vertical_bar/CPDI/CPDI-r4|Q4/vertical_bar.mpm) with the method() syntax the current parser accepts
+# (method, sub-method, shape, ratio, "mechanical", style - src/update.cpp:108-196; the shipped files predate it).
+def cpdi_bar(method="ulcpdi", style="R4", shape="linear"):
+    # TLCPDI indexes its candidate nodes from domain->boxlo although the TL grid starts at the solid's own corner
+    # (src/tlcpdi.cpp:200-222): the particles only find their nodes when the two coincide, so the TL variants use the
+    # box the example keeps commented out (-L..0); UL needs the room below the bar (-3L..0).
+    ylo = "-L" if method == "tlcpdi" else "-3*L"
+    return f"""
+E = 1e+6
+nu = 0.3
+rho = 1050
+L = 1
+hL = 0.5*L
+FLIP=0.99
+method({method}, FLIP, {shape}, FLIP, mechanical, {style})
+N = 5
+cellsize = L/N
+dimension(2,-hL, hL, {ylo}, 0, cellsize)
+region(box, block, -hL, hL, -L, 0)
+material(mat1, neo-hookean, rho, E, nu)
+solid(solid1, region, box, 2, mat1, cellsize, 0)
+region(rBCLX, block, INF, INF, -cellsize/4, INF)
+group(gBCLX, nodes, region, rBCLX, solid, solid1)
+fix(fBCLX, velocity_nodes, gBCLX, NULL, 0, NULL)
+gravity = -1e+3
+fix(fbody, body_force, all, 0, gravity, 0)
+dt_factor(0.2)
+"""
+
+
 # name -> (script, is_TL, thermal, steps)
 CASES = {
     "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
@@ -277,4 +308,8 @@ CASES = {
     "c5_block_usl_fixed_dt": (block((6, 6, 6), "usl", fixed_dt=True), False, False, 100),
     "x_neo_hookean_usf": (neo_hookean_bar(), False, False, 100),
     "x_fluid_column": (fluid_column(), False, False, 100),
+    "x_cpdi_ul_r4": (cpdi_bar("ulcpdi", "R4"), False, False, 100),
+    "x_cpdi_ul_q4": (cpdi_bar("ulcpdi", "Q4"), False, False, 100),
+    "x_cpdi_tl_r4": (cpdi_bar("tlcpdi", "R4"), True, False, 100),
+    "x_cpdi_tl_q4": (cpdi_bar("tlcpdi", "Q4"), True, False, 100),
 }
