@@ -43,6 +43,7 @@ struct kml_ctx {
   double *h_pinned = nullptr;                                // pinned readback buffer
   void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
   bool tl_mass_done = false, tl_wf_done = false;
+  bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
@@ -61,7 +62,19 @@ struct StageTimer {
 StepParams step_params(kml_ctx *c) {
   StepParams sp; sp.dt = c->dt; sp.alpha = c->c.PIC_FLIP;
   for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
-  sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.inv_tav = 0.0; sp.flags = c->d_flags; return sp;
+  sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.inv_tav = 0.0; sp.flags = c->d_flags;
+  sp.apic = c->apic; sp.mls = !c->c.is_TL && c->c.sub_method == KML_SUB_MLS; sp.asflip = !c->c.is_TL && c->c.sub_method == KML_SUB_ASFLIP;
+  sp.Di[0] = sp.Di[1] = sp.Di[2] = 1.0;
+  return sp;
+}
+
+// Solid::compute_inertia_tensor, src/solid.cpp:1440-1478: Di = k / cellsize^2 on the active dimensions (linear TL: the
+// reference distinguishes 1 and 2 particles per cell; the ABI carries no lattice information, 2 per cell is assumed)
+void fill_inertia(kml_ctx *c, const Grid *G, StepParams &sp) {
+  if (!c->apic) return;
+  const double cs = 1.0 / (G->d.cellsize * G->d.cellsize);
+  const double k = c->c.shape_function == KML_SHAPE_LINEAR ? 16.0 / 3.0 : (c->c.shape_function == KML_SHAPE_CUBIC_SPLINE ? 3.0 : 4.0);
+  for (int d = 0; d < 3; d++) sp.Di[d] = d < c->c.dimension ? k * cs : 1.0;
 }
 
 // kernel dispatch on (dimension, TL); the shape function is switched inside each launcher (kml_launch.h)
@@ -115,10 +128,19 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (cfg->is_CPDI && cfg->dimension != 2) return fail("Error: ULCPDI is only 2D....\n"); // src/ulcpdi.cpp:115-118, src/tlcpdi.cpp:102-104
   if (cfg->is_CPDI && (cfg->axisymmetric || cfg->temp)) return fail("kml: CPDI with axisymmetry / thermo-mechanical coupling is not implemented in the CUDA engine");
   if (cfg->ge) return fail("kml: gradient-enhanced mapping is not implemented in the CUDA engine yet");
-  if (cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP) return fail("kml: APIC / AFLIP / ASFLIP / MLS are not implemented in the CUDA engine yet");
+  const bool apic_ = cfg->is_TL ? cfg->sub_method == KML_SUB_APIC
+                                : (cfg->sub_method == KML_SUB_APIC || cfg->sub_method == KML_SUB_MLS || cfg->sub_method == KML_SUB_AFLIP || cfg->sub_method == KML_SUB_ASFLIP);
+  if (cfg->is_TL && cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP && cfg->sub_method != KML_SUB_APIC)
+    return fail("kml: total-Lagrangian methods take PIC, FLIP or APIC");
+  if (apic_) { // Solid::compute_inertia_tensor, src/solid.cpp:1440-1478
+    if (cfg->is_CPDI) return fail("kml: APIC with CPDI is not implemented in the CUDA engine");
+    if (cfg->shape_function == KML_SHAPE_BERNSTEIN) return fail("Shape function not supported for APIC.");
+    if (cfg->shape_function == KML_SHAPE_LINEAR && !cfg->is_TL) return fail("Shape function not supported for APIC and ULMPM.");
+    if (cfg->nranks > 1) return fail("kml: the APIC family is single-GPU in the CUDA engine (the stored velocity gradient is not migrated)");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("kml: no CUDA device available - the engine has no CPU fallback");
-  kml_ctx *c = new kml_ctx(); c->c = *cfg; c->dev = cfg->device;
+  kml_ctx *c = new kml_ctx(); c->c = *cfg; c->dev = cfg->device; c->apic = apic_;
   CU(cudaSetDevice(c->dev));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
@@ -272,7 +294,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   Solid *S = new Solid(); S->d = *d; SolidDev &s = S->s;
   s.np = d->np; S->cap = std::max<long long>(d->capacity, d->np);
   const long long cap = (S->cap + 31) / 32 * 32; S->cap = cap;
-  const int nd = c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL;
+  const int nd = (c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL) + (c->apic ? 9 : 0);
   CU(cudaMalloc(&S->buf, sizeof(double) * cap * nd)); CU(cudaMemsetAsync(S->buf, 0, sizeof(double) * cap * nd, c->stream));
   CU(cudaMalloc(&S->lbuf, sizeof(long long) * cap)); CU(cudaMemsetAsync(S->lbuf, 0, sizeof(long long) * cap, c->stream));
   CU(cudaMalloc(&S->ibuf, sizeof(int) * cap));
@@ -285,6 +307,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   s.ien = take(); s.T = take(); s.gamma = take();
   if (c->c.is_TL) { for (int k = 0; k < 9; k++) s.pk1[k] = take(); for (int k = 0; k < 9; k++) s.R[k] = take(); }
   else { for (int k = 0; k < 9; k++) { s.pk1[k] = nullptr; s.R[k] = nullptr; } }
+  for (int k = 0; k < 9; k++) s.Lst[k] = c->apic ? take() : nullptr;
   s.ptag = S->lbuf; s.mask = S->ibuf;
   // initial values of Solid::populate, src/solid.cpp:2283-2321: F = R = I, rho0 = mat.rho0, mask = 1
   std::vector<double> ones(d->np, 1.0), rho(d->np, d->mat.rho0); std::vector<int> m1(d->np, 1);
@@ -457,7 +480,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
     return 0;
   }
   if (!c->c.is_TL) {
-    if (c->use_cell_p2g && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (c->use_cell_p2g && !c->apic && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StageTimer t(c, KML_STAGE_REBIN);
       for (Solid *S : c->solids) {
         Grid *G = c->grids[S->d.grid];
@@ -543,7 +566,8 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     }
     if (what == 0) continue;
     bool done = false;
-    if (!TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
+    fill_inertia(c, G, sp);
+    if (!TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
       const int rc = cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
@@ -605,7 +629,8 @@ int kml_advance_particles(kml_ctx *c) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
-    if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    fill_inertia(c, G, sp);
+    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
@@ -623,7 +648,7 @@ int kml_advance_particles(kml_ctx *c) {
 int kml_velocities_to_grid(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   if (c->pending_g2p) return fail("velocities_to_grid called between grid_to_points and advance_particles");
-  if (p2g_launch(c, P2G_MOM | (c->c.temp ? P2G_TEMP : 0), KML_STAGE_V2G)) return 1;
+  if (p2g_launch(c, P2G_MOM | P2G_POSMOVED | (c->c.temp ? P2G_TEMP : 0), KML_STAGE_V2G)) return 1;
   // the reference divides by the node mass inside compute_velocity_nodes; fixes that follow
   // (post_velocities_to_grid) and the gradient gather need velocities, so normalise now
   StageTimer t(c, KML_STAGE_V2G);
@@ -665,7 +690,8 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
-    if (!c->c.is_TL && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    fill_inertia(c, G, sp);
+    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
     }

@@ -14,6 +14,7 @@ struct SolidDev {
   double *sig[6], *eel[6], *F[9];
   double *vol0, *vol, *rho0, *mass, *eps, *epsdot, *dmg, *dmgi, *ien, *T, *gamma;
   double *pk1[9], *R[9]; // TL only
+  double *Lst[9];        // APIC family only: the velocity gradient of the previous step (UL: L, TL: Fdot), src/solid.cpp:392-426
   long long *ptag; int *mask;
 };
 
@@ -22,10 +23,15 @@ struct StepParams {
   double boxlo[3], boxhi[3];
   int axisymmetric, temp;
   double inv_tav;          // stress update: signal_velocity / (1000 cellsize) of the solid being updated
+  // APIC family (Update::SubMethodType APIC / MLS / AFLIP / ASFLIP): affine momentum transfer with the diagonal inertia
+  // tensor Di of Solid::compute_inertia_tensor (src/solid.cpp:1440-1478)
+  int apic, mls, asflip;
+  double Di[3];
   unsigned *flags;         // device error word
 };
 
-enum { P2G_MASS = 1, P2G_MOM = 2, P2G_FORCE = 4, P2G_MB = 8, P2G_TEMP = 16, P2G_HEAT = 32 };
+enum { P2G_MASS = 1, P2G_MOM = 2, P2G_FORCE = 4, P2G_MB = 8, P2G_TEMP = 16, P2G_HEAT = 32,
+       P2G_POSMOVED = 64 /* UL: explicit particle positions are the ones advanced by G2P (MUSL re-projection) */ };
 
 // symmetric index helper: (xx,yy,zz,xy,xz,yz)
 __device__ __forceinline__ void load_sym(double *const *a, long long i, double *m) {
@@ -100,18 +106,43 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
     }
   }
   if (what & P2G_MB) { mbp[0] = s.mbp[0][ip]; mbp[1] = s.mbp[1][ip]; mbp[2] = s.mbp[2][ip]; }
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, pp[3] = {px, py, pz};
+  if (sp.apic) { // compute_velocity_nodes_APIC / compute_external_and_internal_forces_nodes_UL_MLS use the particle position explicitly
+    if ((what & P2G_MOM) && s.Lst[0]) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) C[i] = s.Lst[i][ip];
+    }
+    if (!TL && (what & P2G_POSMOVED)) { pp[0] = s.xn[0][ip]; pp[1] = s.xn[1][ip]; pp[2] = s.xn[2][ip]; }
+  }
   if (what & P2G_TEMP) mT = m * s.T[ip];
   if (what & P2G_HEAT) { gam = s.gamma[ip]; qv[0] = s.q[0][ip]; qv[1] = s.q[1][ip]; qv[2] = s.q[2][ip]; }
 
   KML_FOR_STENCIL(st, g, {
     if (what & P2G_MASS) atomicAdd(&g.nv[node].w, wf * m);
+    double dxn[3] = {0, 0, 0}; // x_I - x_p (APIC family)
+    if (sp.apic) {
+      dxn[0] = __dadd_rn(g.lo[0], __dmul_rn((double)(st.i0[0] + sa_ + g.goff0), g.h)) - pp[0];
+      if (DIM >= 2) dxn[1] = __dadd_rn(g.lo[1], __dmul_rn((double)(st.i0[1] + sb_), g.h)) - pp[1];
+      if (DIM == 3) dxn[2] = __dadd_rn(g.lo[2], __dmul_rn((double)(st.i0[2] + sc_), g.h)) - pp[2];
+    }
     if (what & P2G_MOM) {
       const double wm = wf * m;
-      atomicAdd(&g.nv[node].x, wm * mv[0]);
-      if (DIM >= 2) atomicAdd(&g.nv[node].y, wm * mv[1]);
-      if (DIM == 3) atomicAdd(&g.nv[node].z, wm * mv[2]);
+      if (sp.apic) { // src/solid.cpp:392-426: (w m) (v + C (x_I - x_p))
+        atomicAdd(&g.nv[node].x, wm * (mv[0] + (C[0] * dxn[0] + C[1] * dxn[1] + C[2] * dxn[2])));
+        if (DIM >= 2) atomicAdd(&g.nv[node].y, wm * (mv[1] + (C[3] * dxn[0] + C[4] * dxn[1] + C[5] * dxn[2])));
+        if (DIM == 3) atomicAdd(&g.nv[node].z, wm * (mv[2] + (C[6] * dxn[0] + C[7] * dxn[1] + C[8] * dxn[2])));
+      } else {
+        atomicAdd(&g.nv[node].x, wm * mv[0]);
+        if (DIM >= 2) atomicAdd(&g.nv[node].y, wm * mv[1]);
+        if (DIM == 3) atomicAdd(&g.nv[node].z, wm * mv[2]);
+      }
     }
-    if (what & P2G_FORCE) {
+    if ((what & P2G_FORCE) && sp.mls && !TL) { // src/solid.cpp:524-574: f_I -= vol w (sigma Di (x_I - x_p))
+      const double e0 = sp.Di[0] * dxn[0], e1 = sp.Di[1] * dxn[1], e2 = sp.Di[2] * dxn[2];
+      atomicAdd(&g.f[0][node], -(wf * (A[0] * e0 + A[1] * e1 + A[2] * e2)));
+      if (DIM >= 2) atomicAdd(&g.f[1][node], -(wf * (A[3] * e0 + A[4] * e1 + A[5] * e2)));
+      if (DIM == 3) atomicAdd(&g.f[2][node], -(wf * (A[6] * e0 + A[7] * e1 + A[8] * e2)));
+    } else if (what & P2G_FORCE) {
       double f0 = -(A[0] * wfd0 + A[1] * wfd1 + A[2] * wfd2);
       if (sp.axisymmetric) f0 -= hoop * wf;
       atomicAdd(&g.f[0][node], f0);
@@ -189,8 +220,10 @@ __device__ __forceinline__ void particle_advance(const SolidDev &s, const StepPa
   for (int d = 0; d < 3; d++) {
     const double ad = a[d] * inv_dt;
     const double xo = s.x[d][ip];
-    xnew[d] = xo + sp.dt * vu[d];
-    s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * ((vold ? vold[d] : s.v[d][ip]) + sp.dt * ad);
+    const double vnew = (1 - sp.alpha) * vu[d] + sp.alpha * ((vold ? vold[d] : s.v[d][ip]) + sp.dt * ad);
+    // ASFLIP (UL): the position is advanced with the blended particle velocity, not with v~ (src/solid.cpp:637-694, :786-796)
+    xnew[d] = (!TL && sp.asflip) ? xo + sp.dt * vnew : xo + sp.dt * vu[d];
+    s.v[d][ip] = vnew;
     if (TL) s.x[d][ip] = xnew[d]; else s.xn[d][ip] = xnew[d];
   }
   if (sp.temp) s.T[ip] = Tp;
@@ -451,8 +484,15 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
     Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
     const double4 *__restrict__ gv = tp.doublemapping ? g.nv : g.nvu;
     double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, hoop = 0, qv[3] = {0, 0, 0};
+    double pp[3] = {px, py, pz}; // explicit particle position of the APIC gradient (src/solid.cpp:1006-1153)
+    if (sp.apic && !TL && tp.moved) { pp[0] = s.xn[0][ip]; pp[1] = s.xn[1][ip]; pp[2] = s.xn[2][ip]; }
     KML_FOR_STENCIL(st, g, {
-      const double wfd[3] = {wfd0, wfd1, wfd2};
+      double wfd[3] = {wfd0, wfd1, wfd2};
+      if (sp.apic) { // L += v_I (x) (x_I - x_p) w, scaled by Di afterwards
+        wfd[0] = (__dadd_rn(g.lo[0], __dmul_rn((double)(st.i0[0] + sa_ + g.goff0), g.h)) - pp[0]) * wf;
+        wfd[1] = DIM >= 2 ? (__dadd_rn(g.lo[1], __dmul_rn((double)(st.i0[1] + sb_), g.h)) - pp[1]) * wf : 0.0;
+        wfd[2] = DIM == 3 ? (__dadd_rn(g.lo[2], __dmul_rn((double)(st.i0[2] + sc_), g.h)) - pp[2]) * wf : 0.0;
+      }
       const double4 rec = ldg4(&gv[node]);
       const double vn[3] = {rec.x, rec.y, rec.z};
 #pragma unroll
@@ -470,6 +510,16 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
     if (DIM == 2 && sp.axisymmetric) {
       const double xr = TL ? s.x0[0][ip] : (tp.moved ? s.xn[0][ip] : s.x[0][ip]);
       L[8] += hoop / xr; // the reference divides term by term; same value up to rounding
+    }
+    if (sp.apic) { // L *= Di (src/solid.cpp:1077,1151), kept for the next step's affine momentum transfer
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) L[3 * a + b] *= sp.Di[b];
+      if (s.Lst[0]) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.Lst[i][ip] = L[i];
+      }
     }
     PState ps; ps.load(s, mat, sp, ip);
     particle_stress<TL>(s, g, sp, mat, ip, ps, L, qv, wave, hr);

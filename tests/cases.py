@@ -9,7 +9,7 @@ variant of C2, thermo-mechanical variant of C3, both contact fixes for C4).
 
 # C1: examples/two-disks.mpm - 2-D ULMPM, two elastic disks colliding, linear shape functions.
 # The disks start closer together so that they collide within the first 100 steps.
-def two_disks(scheme="usl", v=0.1, c=0.2):
+def two_disks(scheme="usl", v=0.1, c=0.2, method="method(ulmpm, FLIP, linear, FLIP)"):
     return f"""
 E   = 1e+3
 nu  = 0.3
@@ -17,7 +17,7 @@ rho = 1000
 L   = 1
 hL  = 0.5*L
 FLIP=1.0
-method(ulmpm, FLIP, linear, FLIP)
+{method}
 scheme({scheme})
 N        = 20
 cellsize = L/N
@@ -146,7 +146,7 @@ fix(BC_right, velocity_nodes, groupn2, v, NULL, NULL)
 
 
 # C4: examples/Bouncing_balls/TLMPM/FLIP - TLMPM, two solids on private grids, contact fix.
-def bouncing_balls(contact="minimize_penetration", v=0.5):
+def bouncing_balls(contact="minimize_penetration", v=0.5, method="method(tlmpm, FLIP, linear, alphaFLIP)"):
     fix = "fix(contact, contact/minimize_penetration, sBall1, sBall2, 0.3)" if contact == "minimize_penetration" else "fix(contact, contact/hertz, sBall1, sBall2)"
     return f"""
 E   = 1e+3
@@ -155,7 +155,7 @@ rho = 1000
 L    = 1
 hL   = 0.5*L
 alphaFLIP=1
-method(tlmpm, FLIP, linear, alphaFLIP)
+{method}
 N        = 40
 cellsize = L/N
 dimension(2,-hL, hL, -hL, hL, cellsize)
@@ -308,6 +308,12 @@ CASES = {
     "c5_block_usl_fixed_dt": (block((6, 6, 6), "usl", fixed_dt=True), False, False, 100),
     "x_neo_hookean_usf": (neo_hookean_bar(), False, False, 100),
     "x_fluid_column": (fluid_column(), False, False, 100),
+    # affine sub-methods (rows a7 _APIC, a8 _MLS, a12 ASFLIP, a15 _APIC of SURVEY section 8)
+    "x_apic_ul_cubic": (two_disks("musl", method="method(ulmpm, APIC, cubic-spline)"), False, False, 100),
+    "x_mls_ul_cubic": (two_disks("usl", method="method(ulmpm, MLS, cubic-spline)"), False, False, 100),
+    "x_asflip_ul_quadratic": (two_disks("musl", method="method(ulmpm, ASFLIP, quadratic-spline, 0.99)"), False, False, 100),
+    "x_aflip_ul_cubic_usf": (two_disks("usf", method="method(ulmpm, AFLIP, cubic-spline, 0.95)"), False, False, 100),
+    "x_apic_tl_linear": (bouncing_balls("minimize_penetration", method="method(tlmpm, APIC, linear)"), True, False, 100),
     "x_cpdi_ul_r4": (cpdi_bar("ulcpdi", "R4"), False, False, 100),
     "x_cpdi_ul_q4": (cpdi_bar("ulcpdi", "Q4"), False, False, 100),
     "x_cpdi_tl_r4": (cpdi_bar("tlcpdi", "R4"), True, False, 100),
