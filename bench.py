@@ -29,7 +29,7 @@ FULL_CELLS = (248, 250, 202)  # 100 192 000 particles in a 256 x 258 
 # algorithmic bytes per particle-step (fp64 SoA, every array once per kernel)
 ALGO_BYTES = {"rebin": 80, "p2g": 158, "grid": 18, "g2p": 103, "v2g": 64, "stress": 436}
 # minimal FP64 instructions per particle and stage: the second roof of the fp64 stencil kernels
-FP64_INSTR = {"p2g": 1000, "g2p": 580, "v2g": 340, "stress": 1300}
+FP64_INSTR = {"p2g": 1000, "g2p": 580, "v2g": 340, "stress": 960}
 FP64_LANES_PER_SM_CLK = 64   # B200: 64 DFMA / clk / SM (ncu sm__inst_executed_pipe_fp64 peak = 0.5 warp-inst / clk / sub-partition)
 N_SM = 148
 A_SQUEEZE = 2.5e-4

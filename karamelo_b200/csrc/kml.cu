@@ -45,7 +45,7 @@ struct kml_ctx {
   bool tl_mass_done = false, tl_wf_done = false;
   bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
-  bool use_cell_p2g = true; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
+  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
   bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
@@ -152,6 +152,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
+  c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   c->gtune.seg_target = std::min(std::max(env_int("KML_SEGLEN", 32), 8), 96);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;
@@ -567,7 +568,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (what == 0) continue;
     bool done = false;
     fill_inertia(c, G, sp);
-    if (!TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
+    if (!TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
       const int rc = cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
@@ -630,7 +631,7 @@ int kml_advance_particles(kml_ctx *c) {
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
     fill_inertia(c, G, sp);
-    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
@@ -691,7 +692,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
     fill_inertia(c, G, sp);
-    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 4) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
     }

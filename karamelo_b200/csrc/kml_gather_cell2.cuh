@@ -177,7 +177,9 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
     if (ipn >= 0) pstate_issue_async(state + tid, THREADS, s, mat, sp, ipn); // the slot is free again: stream the next particle's state
     cp_async_commit();
     const double qv[3] = {0, 0, 0};
-    particle_stress<false>(s, g, sp, mat, ip, ps, L, qv, wave, hr);
+    double wave_p = 0; // particle_stress ASSIGNS the particle's wave speed: keep the maximum over this thread's particles
+    particle_stress<false>(s, g, sp, mat, ip, ps, L, qv, wave_p, hr);
+    wave = fmax(wave, wave_p);
     cp_async_wait_all(); // the next particle's state has had the constitutive update to arrive
     p = pn; ip = ipn; ipn = ipnn; px = nx; py = ny; pz = nz;
   }

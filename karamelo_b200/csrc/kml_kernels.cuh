@@ -290,11 +290,13 @@ struct PState {
   }
 };
 // cp.async (LDGSTS): global -> shared copies that bypass the register file and complete asynchronously
+// (the "memory" clobbers matter: without them the compiler may sink ordinary shared-memory loads of a slot below the
+//  cp.async that refills it)
 __device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

@@ -178,8 +178,10 @@ set_dt(0.001)
 
 
 # C5: synthetic 3-D ULMPM elastoplastic block, cubic B-splines, at test size.
-def block(n=(8, 8, 8), scheme="musl", shape="cubic-spline", fixed_dt=False, a=2.5e-3, ppc=2, strength="plastic", drift=0.0):
-    """drift: uniform x velocity added to the squeeze (moves particles across slab cuts in the multi-GPU tests)"""
+def block(n=(8, 8, 8), scheme="musl", shape="cubic-spline", fixed_dt=False, a=2.5e-3, ppc=2, strength="plastic", drift=0.0, margin=4):
+    """drift: uniform x velocity added to the squeeze (moves particles across slab cuts in the multi-GPU tests);
+    margin: empty cells between the block and the box (4 keeps every stencil on interior nodes; 1 puts the outer
+    particles on the boundary-modified splines, ntype -2/-1/1/2 of src/grid.cpp:236-240)"""
     nx, ny, nz = n
     a_m, a_e = ("%e" % a).split("e")
     a_txt = "%s%s%+d" % (a_m.rstrip("0").rstrip("."), "e", int(a_e))  # e.g. 2.5e-3: the parser needs a signed exponent
@@ -195,17 +197,17 @@ sigmay = 3
 h = 1
 method(ulmpm, FLIP, {shape}, 0.99)
 scheme({scheme})
-dimension(3, 0, {nx + 8}, 0, {ny + 8}, 0, {nz + 8}, h)
-region(box, block, 4, {nx + 4}, 4, {ny + 4}, 4, {nz + 4})
+dimension(3, 0, {nx + 2 * margin}, 0, {ny + 2 * margin}, 0, {nz + 2 * margin}, h)
+region(box, block, {margin}, {nx + margin}, {margin}, {ny + margin}, {margin}, {nz + margin})
 eos(e, linear, rho, K)
 {strength_cmd}
 material(m, eos-strength, e, s)
 solid(blk, region, box, {ppc}, m, h, 0)
 group(gall, particles, region, box, solid, blk)
 a = {a_txt}
-cx = {4 + nx / 2}
-cy = {4 + ny / 2}
-cz = {4 + nz / 2}
+cx = {margin + nx / 2}
+cy = {margin + ny / 2}
+cz = {margin + nz / 2}
 fix(v0, initial_velocity_particles, gall, {drift}-a*(x-cx), 0.5*a*(y-cy), 0.5*a*(z-cz))
 {"set_dt(0.2)" if fixed_dt else "dt_factor(0.5)"}
 """
@@ -308,6 +310,13 @@ CASES = {
     "c5_block_usl_fixed_dt": (block((6, 6, 6), "usl", fixed_dt=True), False, False, 100),
     "x_neo_hookean_usf": (neo_hookean_bar(), False, False, 100),
     "x_fluid_column": (fluid_column(), False, False, 100),
+    # edge cases of the cell-centric kernels: boundary-modified splines on every face (margin 1, pure compression so that no
+    # particle leaves the box), one and 27 particles per cell (staging rounds that start and end inside a cell), a segment
+    # boundary inside the block (40 cells along z > 32)
+    "e_block_boundary_splines": (block((6, 6, 6), "musl", a=2.5e-3, margin=1).replace("0.5*a*(y-cy), 0.5*a*(z-cz)", "-0.5*a*(y-cy), -0.5*a*(z-cz)"), False, False, 100),
+    "e_block_ppc1": (block((8, 8, 8), "musl", ppc=1), False, False, 100),
+    "e_block_ppc3": (block((5, 5, 5), "usl", ppc=3), False, False, 100),
+    "e_block_two_segments": (block((3, 3, 40), "musl"), False, False, 60),
     # affine sub-methods (rows a7 _APIC, a8 _MLS, a12 ASFLIP, a15 _APIC of SURVEY section 8)
     "x_apic_ul_cubic": (two_disks("musl", method="method(ulmpm, APIC, cubic-spline)"), False, False, 100),
     "x_mls_ul_cubic": (two_disks("usl", method="method(ulmpm, MLS, cubic-spline)"), False, False, 100),

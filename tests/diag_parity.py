@@ -1,44 +1,25 @@
-#!/usr/bin/env python
-"""Diagnostic (not a test): error growth of the CUDA engine against the oracle, step by step.
-
-    python tests/diag_parity.py <case> [checkpoints...]
-"""
+"""Diagnostic (not a test): which cell kernel disagrees with the oracle on a case, and where.
+    python tests/diag_parity.py <case> [steps]     (GPU box)"""
 import os
 import sys
 
 import numpy as np
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
-sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from cases import CASES  # noqa: E402
-from common import FIELDS, rel  # noqa: E402
-from karamelo_b200.api import Engine, load_host_library  # noqa: E402
+from common import rel, run_case  # noqa: E402
+from conftest import ORACLE_HOST_LIB  # noqa: E402
+from karamelo_b200.api import load_host_library  # noqa: E402
 
-
-def main():
-    name = sys.argv[1]
-    cps = [int(x) for x in sys.argv[2:]] or [1, 2, 3, 5, 10, 20, 30, 40, 50, 60, 70, 80, 90, 100]
-    script, is_tl, thermal, _ = CASES[name]
-    cuda = load_host_library(None)
-    oracle = load_host_library(os.path.join(os.path.dirname(HERE), "oracle", "_build", "libkml_host_oracle.so"))
-    a, b = Engine(cuda), Engine(oracle)
-    a.script(script)
-    b.script(script)
-    done = 0
-    fields = FIELDS + (("T",) if thermal else ())
-    print("%5s %12s " % ("step", "dt_rel") + " ".join("%10s" % f[:10] for f in fields[1:]))
-    for cp in cps:
-        a.line("run(%d)" % (cp - done))
-        b.line("run(%d)" % (cp - done))
-        done = cp
-        sa, sb = a.snapshot(fields), b.snapshot(fields)
-        row = []
-        for f in fields[1:]:
-            row.append(max(rel(x[f], y[f]) for x, y in zip(sa, sb)))
-        da, db = a.state()["dt"], b.state()["dt"]
-        print("%5d %12.3e " % (cp, abs(da - db) / abs(db)) + " ".join("%10.2e" % r for r in row), flush=True)
-
-
-if __name__ == "__main__":
-    main()
+name = sys.argv[1]
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+script = CASES[name][0]
+ref, _ = run_case(load_host_library(ORACLE_HOST_LIB), script, steps)
+for mask in (0, 1, 2, 4, 7):
+    os.environ["KML_CELL_MASK"] = str(mask)
+    got, _ = run_case(load_host_library(None), script, steps)
+    w = {k: rel(got[0][k], ref[0][k]) for k in ("X", "V", "SIGMA", "FDEF")}
+    d = np.abs(got[0]["V"] - ref[0]["V"]).max(1)
+    bad = np.argsort(d)[-3:]
+    print("mask", mask, {k: "%.1e" % v for k, v in w.items()}, "worst particles (x0):", [tuple(np.round(ref[0]["X"][i], 2)) for i in bad])
