@@ -312,6 +312,9 @@ Var Sim::cmd_run(std::vector<std::string> &a, int kind) {
   if (a.size() < 1) fatal("Illegal run command.\n");
   if (!method_set || !ctx) fatal("Error: no method was defined!\n");
   check(kml_set_dt(ctx, dt));
+  // Run::command calls scheme->setup() (-> Output::setup) BEFORE it updates laststep (src/run.cpp:41-53): the log interval of a
+  // second run is therefore clipped by the PREVIOUS run's last step, which is why the reference repeats that step's row
+  output_setup();
   maxtime = -1;
   firststep = ntimestep;
   Var cond;
@@ -328,7 +331,6 @@ Var Sim::cmd_run(std::vector<std::string> &a, int kind) {
     Var c = input.parsev(a[0]);
     cond = kind == 2 ? Var("!(" + c.str() + ")", !c.result(), false) : Var(c.str(), c.result(), false);
   }
-  output_setup();
   run(cond);
   return Var(0);
 }

@@ -73,6 +73,36 @@ void Sim::register_commands() {
   c["run_time"] = [this](std::vector<std::string> &a) { return cmd_run(a, 1); };
   c["run_until"] = [this](std::vector<std::string> &a) { return cmd_run(a, 2); };
   c["run_while"] = [this](std::vector<std::string> &a) { return cmd_run(a, 3); };
+  // CentreOfMass / InternalForce commands (src/centre_of_mass.cpp, src/internal_force.cpp -> Group::xcm / internal_force,
+  // src/group.cpp:262-408): lazy variables - the returned Var carries the call as its equation and is re-evaluated,
+  // i.e. the state is downloaded again, every time a log line or an expression needs it.
+  auto group_sum = [this](std::vector<std::string> &a, bool com) -> Var {
+    if (a.size() < 2) fatal("Illegal run command");
+    const int ig = find_group(a[0]);
+    if (ig == -1) fatal("Error: could not find group named: " + a[0] + "\n");
+    int dir; if (a[1] == "x") dir = 0; else if (a[1] == "y") dir = 1; else if (a[1] == "z") dir = 2;
+    else fatal("Error: directions should be either x,y or z: " + a[1] + " not understood.\n");
+    if (gsolid[ig] == -1) fatal("Error: " + std::string(com ? "xcm" : "internal_force") + " needs a group restricted to one solid (the reference indexes solids[-1] for \"all\").\n");
+    SolidH &s = *solids[gsolid[ig]]; const int bit = gbitmask[ig];
+    double num = 0, den = 0;
+    if (gpon[ig] == "particles") {
+      int64_t np = 0; check(kml_solid_np(ctx, s.dev, &np));
+      std::vector<double> v(3 * np), m(np); std::vector<int> mask(np);
+      check(kml_solid_download(ctx, s.dev, com ? KML_P_X : KML_P_F, v.data()));
+      check(kml_solid_download(ctx, s.dev, KML_P_MASK, mask.data()));
+      if (com) check(kml_solid_download(ctx, s.dev, KML_P_MASS, m.data()));
+      for (int64_t i = 0; i < np; i++) if (mask[i] & bit) { if (com) { num += v[3 * i + dir] * m[i]; den += m[i]; } else num += v[3 * i + dir]; }
+    } else {
+      GridH &g = *s.grid; std::vector<double> v(3 * g.nnodes), m(g.nnodes);
+      check(kml_grid_download(ctx, g.id, com ? KML_N_X : KML_N_F, v.data()));
+      if (com) check(kml_grid_download(ctx, g.id, KML_N_MASS, m.data()));
+      for (int64_t i = 0; i < g.nnodes; i++) if (g.mask[i] & bit) { if (com) { num += v[3 * i + dir] * m[i]; den += m[i]; } else num += v[3 * i + dir]; }
+    }
+    const double val = com ? (den ? num / den : 0.0) : num;
+    return Var(std::string(com ? "xcm(" : "internal_force(") + a[0] + "," + a[1] + ")", val);
+  };
+  c["xcm"] = [group_sum](std::vector<std::string> &a) { return group_sum(a, true); };
+  c["internal_force"] = [group_sum](std::vector<std::string> &a) { return group_sum(a, false); };
   c["plot"] = [](std::vector<std::string> &) { return Var(0); };
   c["save_plot"] = [](std::vector<std::string> &) { return Var(0); };
 }

@@ -113,7 +113,7 @@ public:
   std::vector<std::unique_ptr<Fix>> fixes; std::vector<std::unique_ptr<Compute>> computes;
 
   // ---- Output ----
-  int every_log = 0; std::vector<std::string> log_fields{"step", "dt", "time"}; int64_t next_log = 0;
+  int every_log = 1 /* src/output.cpp:48 */; std::vector<std::string> log_fields{"step", "dt", "time"}; int64_t next_log = 0;
   std::vector<Dump> dumps; std::ofstream logfile; bool quiet = false;
   int restart_every = 0; std::string restart_name; // accepted and ignored
 
