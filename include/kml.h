@@ -228,6 +228,9 @@ int kml_fix_velocity_nodes(kml_ctx *ctx, int solid, int groupbit, int set_mask, 
                            const double vprev[3], int which, double ftot[3]);
 /* FixBodyforce::post_particles_to_grid with a constant force, src/fix_body_force.cpp:106-180 */
 int kml_fix_body_force(kml_ctx *ctx, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]);
+/* FixForceNodes::post_particles_to_grid, src/fix_force_nodes.cpp:96-193: the force f is shared equally by the n nodes of the
+ * group that carry mass (mb_I += f / n). solid = -1: every solid's grid, n counted per grid. */
+int kml_fix_force_nodes(kml_ctx *ctx, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]);
 /* FixContactHertz::initial_integrate, src/fix_contact_hertz.cpp:84-201 */
 int kml_fix_contact_hertz(kml_ctx *ctx, int solid1, int solid2, double ftot[3]);
 /* FixContactMinPenetration::initial_integrate, src/fix_contact_min_penetration.cpp:88-258 */

@@ -837,6 +837,25 @@ int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const 
   return 0;
 }
 
+int kml_fix_force_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]) {
+  CU(cudaSetDevice(c->dev));
+  if (c->comm.nranks > 1) return fail("kml: fix force_nodes is single-GPU in the CUDA engine (the node count of the group is not reduced across slabs)");
+  StageTimer t(c, KML_STAGE_GRID);
+  CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
+  std::vector<Grid *> gs;
+  if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
+  int *cnt = (int *)(c->d_scratch + 16);
+  for (Grid *G : gs) {
+    CU(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+    k_fix_force_count<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, cnt);
+    k_fix_force_apply<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, f[0], f[1], f[2], cnt, c->d_scratch);
+    c->launches[KML_STAGE_GRID] += 2;
+  }
+  if (check_launch("k_fix_force_nodes")) return 1;
+  if (ftot) return read_scratch3(c, ftot);
+  return 0;
+}
+
 static int contact(kml_ctx *c, int s1, int s2, int hertz, double mu, double ftot[3]) {
   CU(cudaSetDevice(c->dev));
   StageTimer t(c, KML_STAGE_CONTACT);

@@ -589,6 +589,32 @@ __global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f
   }
 }
 
+// FixForceNodes, src/fix_force_nodes.cpp:96-193: count the massive nodes of the group, then share the force among them
+__global__ void k_fix_force_count(GridDev g, int groupbit, int *count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < g.nn && g.nv[i].w > 0 && (g.mask[i] & groupbit);
+  const unsigned b = __ballot_sync(0xffffffffu, in);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
+__global__ void k_fix_force_apply(GridDev g, int groupbit, int set_mask, double f0, double f1, double f2, const int *count, double *ftot) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double f[3] = {0, 0, 0};
+  if (i < g.nn && g.nv[i].w > 0 && (g.mask[i] & groupbit)) {
+    const double n = (double)*count; const double fv[3] = {f0, f1, f2};
+#pragma unroll
+    for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { f[d] = fv[d] / n; g.mb[d][i] += f[d]; }
+  }
+  const int plane = (int)(min(i, g.nn - 1) / ((long long)g.n[1] * g.n[2]));
+  const bool own = plane >= g.own_lo && plane < g.own_hi;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double x = own ? f[d] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
+  }
+}
+
 // FixContactHertz / FixContactMinPenetration, src/fix_contact_hertz.cpp:84-201,
 // src/fix_contact_min_penetration.cpp:88-258.  All-pairs like the reference, tiled through shared
 // memory: block = 128 particles of solid 1, loops over solid 2 in tiles.  The three screens of the

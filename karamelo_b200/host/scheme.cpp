@@ -66,6 +66,32 @@ struct FixBodyForce : Fix {
   }
 };
 
+// FixForceNodes, reference src/fix_force_nodes.cpp:32-193
+struct FixForceNodes : Fix {
+  bool set[3] = {false, false, false}; Var val[3];
+  void post_particles_to_grid(Sim &s) override {
+    double f[3] = {0, 0, 0}, ftot[3]; int m = 0;
+    for (int d = 0; d < 3; d++) if (set[d]) { m |= 1 << d; f[d] = val[d].result(&s.input); }
+    s.check(kml_fix_force_nodes(s.ctx, s.gsolid[igroup], groupbit, m, f, ftot));
+    const char *sfx[3] = {"_x", "_y", "_z"};
+    for (int d = 0; d < 3; d++) if (set[d]) s.input.vars[id + sfx[d]] = Var(id + sfx[d], ftot[d]);
+  }
+};
+
+// FixKineticEnergy / FixStrainEnergy, reference src/fix_kinetic_energy.cpp:66-110, src/fix_strain_energy.cpp: the energy of the
+// group on output steps, published as <id>_s
+struct FixEnergy : Fix {
+  bool kinetic = true;
+  void final_integrate(Sim &s) override {
+    bool due = s.ntimestep == s.next_log || s.ntimestep == s.nsteps;
+    for (auto &d : s.dumps) due = due || d.next == s.ntimestep;
+    if (!due) return;
+    double e = 0; const int solid = s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev;
+    if (kinetic) s.check(kml_compute_kinetic_energy(s.ctx, solid, groupbit, &e)); else s.check(kml_compute_strain_energy(s.ctx, solid, groupbit, &e));
+    s.input.vars[id + "_s"] = Var(id + "_s", e);
+  }
+};
+
 // FixContactHertz / FixContactMinPenetration, reference src/fix_contact_hertz.cpp, src/fix_contact_min_penetration.cpp
 struct FixContact : Fix {
   int solid1 = -1, solid2 = -1; double mu = 0; bool hertz = true;
@@ -128,6 +154,18 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
         fatal("fix body_force: position-dependent body forces are not supported by this build.\n");
     }
     f->mask = POST_PARTICLES_TO_GRID;
+  } else if (style == "force_nodes") {
+    auto f = new FixForceNodes(); fix.reset(f); group_of(*f);
+    if (a.size() < 6) fatal("Error: too few arguments for fix_force_nodes: requires at least 6 arguments. " + std::to_string(a.size()) + " received.\n");
+    if (gpon[f->igroup] != "nodes") fatal("fix_force_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    for (int d = 0; d < 3; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
+    f->mask = POST_PARTICLES_TO_GRID;
+  } else if (style == "kinetic_energy" || style == "strain_energy") {
+    auto f = new FixEnergy(); fix.reset(f); group_of(*f);
+    f->kinetic = style == "kinetic_energy";
+    if (gpon[f->igroup] != "particles" && gpon[f->igroup] != "all") fatal("fix_" + style + " needs to be given a group of particles" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    input.vars[a[0] + "_s"] = Var(a[0] + "_s", 0.0);
+    f->mask = FINAL_INTEGRATE;
   } else if (style == "contact/hertz" || style == "contact/minimize_penetration") {
     auto f = new FixContact(); fix.reset(f);
     f->hertz = style == "contact/hertz";
@@ -138,6 +176,8 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
     f->mask = INITIAL_INTEGRATE;
   } else fatal("fix style " + style + " is outside the hot path covered by this build (see DESIGN.md).\n");
   fix->id = a[0]; fix->style = style;
+  for (const char *sfx : {"_x", "_y", "_z", "_s"}) // Fix::Fix publishes the fix's outputs as variables from the start, src/fix.cpp:41-44
+    if (!input.vars.count(a[0] + sfx)) input.vars[a[0] + sfx] = Var(a[0] + sfx, 0.0);
   fixes.push_back(std::move(fix));
   return Var(0);
 }
@@ -161,6 +201,7 @@ void Sim::hooks(int which) {
     case POST_PARTICLES_TO_GRID: f->post_particles_to_grid(*this); break;
     case POST_UPDATE_GRID_STATE: f->post_update_grid_state(*this); break;
     case POST_VELOCITIES_TO_GRID: f->post_velocities_to_grid(*this); break;
+    case FINAL_INTEGRATE: f->final_integrate(*this); break;
     default: break;
     }
   }

@@ -71,6 +71,7 @@ struct Fix {
   virtual void post_particles_to_grid(Sim &) {}
   virtual void post_update_grid_state(Sim &) {}
   virtual void post_velocities_to_grid(Sim &) {}
+  virtual void final_integrate(Sim &) {}
 };
 struct Compute {
   std::string id, style;

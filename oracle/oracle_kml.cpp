@@ -1162,6 +1162,20 @@ int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const 
   if (ftot) { ftot[0] = ft[0]; ftot[1] = ft[1]; ftot[2] = ft[2]; }
   return 0;
 }
+// FixForceNodes::post_particles_to_grid, reference src/fix_force_nodes.cpp:96-193
+int kml_fix_force_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const double fv[3], double ftot[3]) {
+  Vec3 ft; ft.setZero();
+  auto apply = [&](OGrid *g) {
+    int n = 0;
+    for (int64_t in = 0; in < g->nn; in++) if (g->mass[in] > 0 && (g->mask[in] & groupbit)) n++;
+    for (int64_t in = 0; in < g->nn; in++)
+      if (g->mass[in] > 0 && (g->mask[in] & groupbit))
+        for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { g->mb[in][d] += fv[d] / ((double)n); ft[d] += fv[d] / ((double)n); }
+  };
+  if (solid == -1) { for (OSolid *s : c->solids) apply(c->grids[s->grid]); } else apply(c->grids[c->solids[solid]->grid]);
+  if (ftot) { ftot[0] = ft[0]; ftot[1] = ft[1]; ftot[2] = ft[2]; }
+  return 0;
+}
 // FixContactHertz::initial_integrate, reference src/fix_contact_hertz.cpp:84-201
 int kml_fix_contact_hertz(kml_ctx *c, int solid1, int solid2, double ftot[3]) {
   OSolid *s1 = c->solids[solid1], *s2 = c->solids[solid2];
