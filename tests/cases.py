@@ -296,6 +296,36 @@ dt_factor(0.2)
 """
 
 
+# examples/Cantilever/2D/cantilever_force_tip.mpm at test size: TLMPM neo-Hookean beam, clamped nodes, tip load through
+# fix force_nodes (shared by the massive nodes of the group), energies through the energy fixes.
+def cantilever(shape="linear"):
+    return f"""
+E = 1e+6
+nu = 0.3
+rho = 1050
+L = 1
+alpha=0.99
+N = 8
+cellsize = L/N
+method(tlmpm, FLIP, {shape}, alpha)
+dimension(2, 0, 4*L, 0, L, cellsize)
+region(box, block, 0, 4*L, 0, L)
+material(mat1, neo-hookean, rho, E, nu)
+solid(solid1, region, box, 2, mat1, cellsize, 0)
+region(rBCLX, block, INF, cellsize/4, INF, INF)
+group(gBCLX, nodes, region, rBCLX, solid, solid1)
+fix(fBCLX, velocity_nodes, gBCLX, 0, 0)
+region(rEND, block, 4*L-cellsize/4, INF, L-5*cellsize/4, INF)
+group(gEND, nodes, region, rEND, solid, solid1)
+F = -20000
+fix(fEnd, force_nodes, gEND, 0, F, 0)
+group(gAll, particles, region, box, solid, solid1)
+fix(Ek, kinetic_energy, gAll)
+fix(Es, strain_energy, gAll)
+dt_factor(0.5)
+"""
+
+
 # name -> (script, is_TL, thermal, steps)
 CASES = {
     "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
@@ -317,6 +347,7 @@ CASES = {
     "e_block_ppc1": (block((8, 8, 8), "musl", ppc=1), False, False, 100),
     "e_block_ppc3": (block((5, 5, 5), "usl", ppc=3), False, False, 100),
     "e_block_two_segments": (block((3, 3, 40), "musl"), False, False, 60),
+    "x_cantilever_force_nodes": (cantilever(), True, False, 100),
     # affine sub-methods (rows a7 _APIC, a8 _MLS, a12 ASFLIP, a15 _APIC of SURVEY section 8)
     "x_apic_ul_cubic": (two_disks("musl", method="method(ulmpm, APIC, cubic-spline)"), False, False, 100),
     "x_mls_ul_cubic": (two_disks("usl", method="method(ulmpm, MLS, cubic-spline)"), False, False, 100),
