@@ -1,5 +1,6 @@
 // scheme.cpp - the per-step stage order (host-side orchestration, as in the reference),
 // the fix / compute commands that sit between stages, run commands and log/dump output.
+#include <algorithm>
 #include "sim.h"
 #include <climits>
 #include <cmath>
@@ -264,6 +265,45 @@ static void write_particle_dump(Sim &s, const Dump &d) { // DumpParticle::write,
   }
 }
 
+static void write_grid_dump(Sim &s, const Dump &d) { // DumpGrid::write, reference src/dump_grid.cpp:50-150
+  std::string fn = d.filename; size_t star = fn.find('*');
+  if (star != std::string::npos) fn = fn.substr(0, star) + (s.nranks > 1 ? "proc-" + std::to_string(s.rank) + "." : "") + std::to_string(s.ntimestep) + fn.substr(star + 1);
+  std::ofstream os(fn);
+  if (!os) fatal("Error: cannot write in file: " + fn + ".\n");
+  std::vector<GridH *> grids;
+  for (auto &S : s.solids) if (std::find(grids.begin(), grids.end(), S->grid) == grids.end()) grids.push_back(S->grid);
+  int64_t total = 0; for (auto g : grids) total += g->nnodes;
+  os << "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n" << total << "\nITEM: BOX BOUNDS sm sm sm\n";
+  for (int k = 0; k < 3; k++) os << s.boxlo[k] << " " << s.boxhi[k] << "\n";
+  os << "ITEM: ATOMS id type tag ";
+  for (auto &f : d.fields) os << f << " ";
+  os << "\n";
+  int igrid = 0;
+  for (auto g : grids) {
+    const int64_t n = g->nnodes; const kml_grid_desc &gd = g->desc;
+    std::vector<double> x(3 * n), v(3 * n), mb(3 * n), mass(n), T(n); std::vector<int> ntype(3 * n), rigid(n);
+    s.check(kml_grid_download(s.ctx, g->id, KML_N_X, x.data())); s.check(kml_grid_download(s.ctx, g->id, KML_N_V, v.data()));
+    s.check(kml_grid_download(s.ctx, g->id, KML_N_MB, mb.data())); s.check(kml_grid_download(s.ctx, g->id, KML_N_MASS, mass.data()));
+    s.check(kml_grid_download(s.ctx, g->id, KML_N_NTYPE, ntype.data())); s.check(kml_grid_download(s.ctx, g->id, KML_N_RIGID, rigid.data()));
+    if (s.temp) s.check(kml_grid_download(s.ctx, g->id, KML_N_T, T.data()));
+    for (int64_t i = 0; i < n; i++) {
+      const int64_t tag = i + (int64_t)gd.goff * gd.n[1] * gd.n[2]; // ntag = nz ny i + nz j + k of the global grid, src/grid.cpp:251
+      os << tag << " " << igrid + 1 << " " << tag << " ";
+      for (auto &f : d.fields) {
+        if (f == "x") os << x[3 * i]; else if (f == "y") os << x[3 * i + 1]; else if (f == "z") os << x[3 * i + 2];
+        else if (f == "vx") os << v[3 * i]; else if (f == "vy") os << v[3 * i + 1]; else if (f == "vz") os << v[3 * i + 2];
+        else if (f == "bx") os << mb[3 * i]; else if (f == "by") os << mb[3 * i + 1]; else if (f == "bz") os << mb[3 * i + 2];
+        else if (f == "mass") os << mass[i]; else if (f == "mask") os << g->mask[i];
+        else if (f == "ntypex") os << ntype[3 * i]; else if (f == "ntypey") os << ntype[3 * i + 1]; else if (f == "ntypez") os << ntype[3 * i + 2];
+        else if (f == "rigid") os << rigid[i]; else if (f == "T") os << T[i];
+        os << " ";
+      }
+      os << "\n";
+    }
+    igrid++;
+  }
+}
+
 void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
   for (auto &d : dumps) d.next = (ntimestep / d.every) * d.every + d.every;
   if (!quiet) {
@@ -278,7 +318,7 @@ void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
 
 void Sim::output_write(int64_t step) { // Output::write, src/output.cpp:128-199
   for (auto &d : dumps)
-    if (d.next == step) { if (d.style == "particle") write_particle_dump(*this, d); d.next += d.every; }
+    if (d.next == step) { if (d.style == "particle") write_particle_dump(*this, d); else if (d.style == "grid") write_grid_dump(*this, d); d.next += d.every; }
   if (next_log == step || step == 0) {
     for (auto &c : computes) c->compute_value(*this); // Modify::run_computes
     if (!quiet) {

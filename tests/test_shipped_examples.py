@@ -39,7 +39,7 @@ def log_rows(text):
     return rows
 
 
-def run(exe, src, text):
+def run(exe, src, text, keep_dumps=None):
     d = tempfile.mkdtemp(prefix="kmlship_")
     try:
         for aux in os.listdir(os.path.dirname(src)):  # meshes etc. next to the script
@@ -48,6 +48,9 @@ def run(exe, src, text):
                 os.symlink(p, os.path.join(d, aux))
         open(os.path.join(d, "in.mpm"), "w").write(text)
         p = subprocess.run([exe, "-i", "in.mpm"], cwd=d, capture_output=True, text=True, timeout=600)
+        if keep_dumps is not None:
+            for f in sorted(glob.glob(os.path.join(d, "dump*"))):
+                keep_dumps[os.path.basename(f)] = open(f, "rb").read()
         return p.returncode, p.stdout + p.stderr
     finally:
         shutil.rmtree(d, ignore_errors=True)
@@ -64,8 +67,9 @@ def test_shipped_script_behaves_like_the_reference(oracle_lib, rel):
     text = re.sub(r"(?m)^run(_time|_until|_while)?\(.*$", "run(%d)" % n, open(src, errors="replace").read())
     if rel in LONG:
         text = re.sub(r"(?m)^(log|set_output)\(.*$", r"\1(%d)" % max(n // 4, 1), text)
-    rc_ref, out_ref = run(REF_BIN, src, text)
-    rc_our, out_our = run(OUR_CLI, src, text)
+    dumps_ref, dumps_our = {}, {}
+    rc_ref, out_ref = run(REF_BIN, src, text, dumps_ref)
+    rc_our, out_our = run(OUR_CLI, src, text, dumps_our)
     if rc_ref != 0:
         assert rc_our != 0, "the reference rejects this file, we accept it:\n" + out_ref[-400:]
         return
@@ -76,3 +80,8 @@ def test_shipped_script_behaves_like_the_reference(oracle_lib, rel):
         assert len(a) == len(b), (a, b)
         for x, y in zip(a, b):
             assert abs(x - y) <= 2e-5 * max(abs(x), abs(y)) + 1e-30, (a, b)  # the log prints 6 significant digits
+    # the dump files (LAMMPS text, what users' OVITO scripts read) are the same files, byte for byte
+    lammps = {k: v for k, v in dumps_ref.items() if k.endswith(".LAMMPS")}
+    assert set(lammps) == {k for k in dumps_our if k.endswith(".LAMMPS")}, (sorted(lammps), sorted(dumps_our))
+    for k, v in lammps.items():
+        assert dumps_our[k] == v, "dump file %s differs from the reference's" % k
