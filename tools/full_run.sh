@@ -7,4 +7,4 @@ python bench.py > gpurun_out/bench_full_$TAG.log 2>&1; tail -1 gpurun_out/bench_
 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; tail -1 gpurun_out/bench_ref_$TAG.log
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1; tail -1 gpurun_out/ncu_launches_$TAG.log | cut -c1-300
-bash tools/ncu_full.sh $TAG "k_p2g_cell3|k_gather_cell2|k_stress_cell3"
+bash tools/ncu_full.sh $TAG "k_p2g_cell3|k_g2p_cell|k_stress_cell"
