@@ -30,6 +30,7 @@ struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
   bool moved = false;     // xn holds the positions after grid_to_points (UL)
   bool mbp_nonzero = false;
+  bool rigid = false;     // Mat::rigid (src/material.h:49)
   CpdiDev cp{}; double *cpbuf = nullptr; int *cpibuf = nullptr; // CPDI neighbour lists and particle domains
   double *red = nullptr;  // device: [0] max wave speed, [1] min_h_ratio
   double dtCFL = 1.0e22;
@@ -43,6 +44,7 @@ struct kml_ctx {
   double *h_pinned = nullptr;                                // pinned readback buffer
   void *d_stage = nullptr; size_t stage_bytes = 0;           // upload / download staging (rows <-> SoA)
   bool tl_mass_done = false, tl_wf_done = false;
+  bool has_rigid = false; // some solid is rigid (ULMPM::rigid_solids, src/ulmpm.cpp:98-99)
   bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
@@ -64,7 +66,7 @@ StepParams step_params(kml_ctx *c) {
   for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
   sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.inv_tav = 0.0; sp.flags = c->d_flags;
   sp.apic = c->apic; sp.mls = !c->c.is_TL && c->c.sub_method == KML_SUB_MLS; sp.asflip = !c->c.is_TL && c->c.sub_method == KML_SUB_ASFLIP;
-  sp.Di[0] = sp.Di[1] = sp.Di[2] = 1.0;
+  sp.Di[0] = sp.Di[1] = sp.Di[2] = 1.0; sp.rigid_mode = 0; sp.ge = c->c.ge;
   return sp;
 }
 
@@ -127,7 +129,8 @@ const char *kml_backend(void) { return "cuda-sm_100a"; }
 int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (cfg->is_CPDI && cfg->dimension != 2) return fail("Error: ULCPDI is only 2D....\n"); // src/ulcpdi.cpp:115-118, src/tlcpdi.cpp:102-104
   if (cfg->is_CPDI && (cfg->axisymmetric || cfg->temp)) return fail("kml: CPDI with axisymmetry / thermo-mechanical coupling is not implemented in the CUDA engine");
-  if (cfg->ge) return fail("kml: gradient-enhanced mapping is not implemented in the CUDA engine yet");
+  if (cfg->ge && (cfg->is_TL || cfg->is_CPDI)) return fail("kml: gradient-enhanced projection is implemented for ulmpm only in the CUDA engine");
+  if (cfg->ge && cfg->nranks > 1) return fail("kml: gradient-enhanced projection is single-GPU in the CUDA engine (the stored velocity gradient is not migrated)");
   const bool apic_ = cfg->is_TL ? cfg->sub_method == KML_SUB_APIC
                                 : (cfg->sub_method == KML_SUB_APIC || cfg->sub_method == KML_SUB_MLS || cfg->sub_method == KML_SUB_AFLIP || cfg->sub_method == KML_SUB_ASFLIP);
   if (cfg->is_TL && cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP && cfg->sub_method != KML_SUB_APIC)
@@ -215,7 +218,7 @@ int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.n
 
 static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
   if (!G->v_is_momentum && !G->T_is_weighted) return 0;
-  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted);
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0);
   G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
   return check_launch("k_grid_update(normalize)");
 }
@@ -291,11 +294,15 @@ static const int SOLID_NDBL_TL = SOLID_NDBL_UL + 18;
 
 int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaSetDevice(c->dev));
-  if (d->mat.rigid || d->mat.type == KML_MAT_RIGID) return fail("kml: rigid materials are not implemented in the CUDA engine yet");
-  Solid *S = new Solid(); S->d = *d; SolidDev &s = S->s;
+  const bool rigid_ = d->mat.rigid || d->mat.type == KML_MAT_RIGID;
+  if (rigid_ && c->c.is_CPDI) return fail("kml: rigid solids with CPDI are not implemented in the CUDA engine");
+  if (rigid_ && c->c.nranks > 1) return fail("kml: rigid solids are single-GPU in the CUDA engine (Grid::reduce_rigid_ghost_nodes is not reproduced)");
+  Solid *S = new Solid(); S->d = *d; S->rigid = rigid_; if (rigid_) c->has_rigid = true; SolidDev &s = S->s;
   s.np = d->np; S->cap = std::max<long long>(d->capacity, d->np);
-  const long long cap = (S->cap + 31) / 32 * 32; S->cap = cap;
-  const int nd = (c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL) + (c->apic ? 9 : 0);
+  long long cap = (S->cap + 31) / 32 * 32;
+  { const char *pad = getenv("KML_CAP_PAD"); if (pad && *pad) cap += atoll(pad) / 32 * 32; } // experiment: de-alias the SoA component stride
+  S->cap = cap;
+  const int nd = (c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL) + ((c->apic || c->c.ge) ? 9 : 0);
   CU(cudaMalloc(&S->buf, sizeof(double) * cap * nd)); CU(cudaMemsetAsync(S->buf, 0, sizeof(double) * cap * nd, c->stream));
   CU(cudaMalloc(&S->lbuf, sizeof(long long) * cap)); CU(cudaMemsetAsync(S->lbuf, 0, sizeof(long long) * cap, c->stream));
   CU(cudaMalloc(&S->ibuf, sizeof(int) * cap));
@@ -308,7 +315,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   s.ien = take(); s.T = take(); s.gamma = take();
   if (c->c.is_TL) { for (int k = 0; k < 9; k++) s.pk1[k] = take(); for (int k = 0; k < 9; k++) s.R[k] = take(); }
   else { for (int k = 0; k < 9; k++) { s.pk1[k] = nullptr; s.R[k] = nullptr; } }
-  for (int k = 0; k < 9; k++) s.Lst[k] = c->apic ? take() : nullptr;
+  for (int k = 0; k < 9; k++) s.Lst[k] = (c->apic || c->c.ge) ? take() : nullptr;
   s.ptag = S->lbuf; s.mask = S->ibuf;
   // initial values of Solid::populate, src/solid.cpp:2283-2321: F = R = I, rho0 = mat.rho0, mask = 1
   std::vector<double> ones(d->np, 1.0), rho(d->np, d->mat.rho0); std::vector<int> m1(d->np, 1);
@@ -480,8 +487,20 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
     c->tl_wf_done = true;
     return 0;
   }
+  if (c->has_rigid && !(c->c.is_TL && c->tl_wf_done)) { // Grid::rigid, set where a rigid particle's weight is non-zero (src/ulmpm.cpp:263-268, src/tlmpm.cpp:279-283)
+    StageTimer t(c, KML_STAGE_REBIN);
+    StepParams sp = step_params(c);
+    for (Solid *S : c->solids) {
+      if (!S->rigid || S->s.np == 0) continue;
+      Grid *G = c->grids[S->d.grid];
+      KML_DISPATCH(p2g, S->s, G->g, sp, P2G_MARK_RIGID, c->stream);
+      c->launches[KML_STAGE_REBIN]++;
+      if (check_launch("k_p2g(mark rigid)")) return 1;
+    }
+    if (c->c.is_TL) c->tl_wf_done = true;
+  }
   if (!c->c.is_TL) {
-    if (c->use_cell_p2g && !c->apic && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (c->use_cell_p2g && !c->apic && !c->c.ge && !c->has_rigid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StageTimer t(c, KML_STAGE_REBIN);
       for (Solid *S : c->solids) {
         Grid *G = c->grids[S->d.grid];
@@ -568,7 +587,8 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (what == 0) continue;
     bool done = false;
     fill_inertia(c, G, sp);
-    if (!TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
+    sp.rigid_mode = c->has_rigid ? (S->rigid ? 2 : 1) : 0;
+    if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
       const int rc = cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
@@ -611,7 +631,7 @@ int kml_update_grid_state(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   StageTimer t(c, KML_STAGE_GRID);
   for (Grid *G : active_grids(c)) {
-    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted);
+    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid);
     G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
     if (check_launch("k_grid_update")) return 1;
   }
@@ -631,7 +651,8 @@ int kml_advance_particles(kml_ctx *c) {
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
     fill_inertia(c, G, sp);
-    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    sp.rigid_mode = c->has_rigid ? (S->rigid ? 2 : 1) : 0;
+    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
@@ -687,12 +708,13 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
+    if (S->rigid) continue; // src/solid.cpp:799,862,1157,1248: the gradient, F and stress updates return at once for a rigid material
     sp.inv_tav = S->d.mat.signal_velocity / (1000 * G->d.cellsize);
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
     fill_inertia(c, G, sp);
-    if (!c->c.is_TL && !c->apic && c->use_cell_p2g && (c->cell_mask & 4) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
     }

@@ -26,12 +26,18 @@ struct StepParams {
   // APIC family (Update::SubMethodType APIC / MLS / AFLIP / ASFLIP): affine momentum transfer with the diagonal inertia
   // tensor Di of Solid::compute_inertia_tensor (src/solid.cpp:1440-1478)
   int apic, mls, asflip;
+  int ge;                  // gradient-enhanced momentum projection v_p + L_p (x_I - x_p) (Method::ge, src/solid.cpp:369-371)
   double Di[3];
+  // rigid bodies (material(..., rigid), src/material.h:49): 0 = no rigid solid in this run, 1 = there are rigid solids and
+  // the solid being processed is deformable, 2 = the solid being processed is rigid.  Nodes inside the stencil of a rigid
+  // particle carry Grid::rigid (src/ulmpm.cpp:267-268, src/tlmpm.cpp:283); the flag is never cleared (src/grid.cpp:248).
+  int rigid_mode;
   unsigned *flags;         // device error word
 };
 
 enum { P2G_MASS = 1, P2G_MOM = 2, P2G_FORCE = 4, P2G_MB = 8, P2G_TEMP = 16, P2G_HEAT = 32,
-       P2G_POSMOVED = 64 /* UL: explicit particle positions are the ones advanced by G2P (MUSL re-projection) */ };
+       P2G_POSMOVED = 64 /* UL: explicit particle positions are the ones advanced by G2P (MUSL re-projection) */,
+       P2G_MARK_RIGID = 128 /* only set Grid::rigid on the nodes this (rigid) solid's particles reach (wf != 0) */ };
 
 // symmetric index helper: (xx,yy,zz,xy,xz,yz)
 __device__ __forceinline__ void load_sym(double *const *a, long long i, double *m) {
@@ -89,6 +95,10 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   if (ip >= s.np) return;
   const double px = TL ? s.x0[0][ip] : s.x[0][ip], py = TL ? s.x0[1][ip] : s.x[1][ip], pz = TL ? s.x0[2][ip] : s.x[2][ip];
   Stencil<DIM, SHAPE, TL> st; st.build(g, px, py, pz);
+  if (what & P2G_MARK_RIGID) {
+    KML_FOR_STENCIL(st, g, { g.rigid[node] = 1; (void)wf; (void)wfd0; (void)wfd1; (void)wfd2; })
+    return;
+  }
   const double m = s.mass[ip];
   double mv[3] = {0, 0, 0}, A[9], mbp[3] = {0, 0, 0}, hoop = 0, mT = 0, gam = 0, qv[3] = {0, 0, 0};
   if (what & P2G_MOM) { mv[0] = s.v[0][ip]; mv[1] = s.v[1][ip]; mv[2] = s.v[2][ip]; }
@@ -107,7 +117,8 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   }
   if (what & P2G_MB) { mbp[0] = s.mbp[0][ip]; mbp[1] = s.mbp[1][ip]; mbp[2] = s.mbp[2][ip]; }
   double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, pp[3] = {px, py, pz};
-  if (sp.apic) { // compute_velocity_nodes_APIC / compute_external_and_internal_forces_nodes_UL_MLS use the particle position explicitly
+  const bool affine = sp.apic || sp.ge;
+  if (affine) { // compute_velocity_nodes_APIC / compute_external_and_internal_forces_nodes_UL_MLS use the particle position explicitly
     if ((what & P2G_MOM) && s.Lst[0]) {
 #pragma unroll
       for (int i = 0; i < 9; i++) C[i] = s.Lst[i][ip];
@@ -118,16 +129,20 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   if (what & P2G_HEAT) { gam = s.gamma[ip]; qv[0] = s.q[0][ip]; qv[1] = s.q[1][ip]; qv[2] = s.q[2][ip]; }
 
   KML_FOR_STENCIL(st, g, {
-    if (what & P2G_MASS) atomicAdd(&g.nv[node].w, wf * m);
+    // rigid nodes take mass and momentum from rigid solids only (src/solid.cpp:326,355,412), no body force (:438,:493-:512)
+    // and, TL, no internal force (:460)
+    const bool nrigid = sp.rigid_mode != 0 && g.rigid[node] != 0;
+    const bool take_mv = !(nrigid && sp.rigid_mode != 2);
+    if ((what & P2G_MASS) && take_mv) atomicAdd(&g.nv[node].w, wf * m);
     double dxn[3] = {0, 0, 0}; // x_I - x_p (APIC family)
-    if (sp.apic) {
+    if (affine) {
       dxn[0] = __dadd_rn(g.lo[0], __dmul_rn((double)(st.i0[0] + sa_ + g.goff0), g.h)) - pp[0];
       if (DIM >= 2) dxn[1] = __dadd_rn(g.lo[1], __dmul_rn((double)(st.i0[1] + sb_), g.h)) - pp[1];
       if (DIM == 3) dxn[2] = __dadd_rn(g.lo[2], __dmul_rn((double)(st.i0[2] + sc_), g.h)) - pp[2];
     }
-    if (what & P2G_MOM) {
+    if ((what & P2G_MOM) && take_mv) {
       const double wm = wf * m;
-      if (sp.apic) { // src/solid.cpp:392-426: (w m) (v + C (x_I - x_p))
+      if (affine) { // src/solid.cpp:392-426 (APIC family) and :369-371 (gradient-enhanced): (w m) (v + C (x_I - x_p))
         atomicAdd(&g.nv[node].x, wm * (mv[0] + (C[0] * dxn[0] + C[1] * dxn[1] + C[2] * dxn[2])));
         if (DIM >= 2) atomicAdd(&g.nv[node].y, wm * (mv[1] + (C[3] * dxn[0] + C[4] * dxn[1] + C[5] * dxn[2])));
         if (DIM == 3) atomicAdd(&g.nv[node].z, wm * (mv[2] + (C[6] * dxn[0] + C[7] * dxn[1] + C[8] * dxn[2])));
@@ -142,14 +157,14 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
       atomicAdd(&g.f[0][node], -(wf * (A[0] * e0 + A[1] * e1 + A[2] * e2)));
       if (DIM >= 2) atomicAdd(&g.f[1][node], -(wf * (A[3] * e0 + A[4] * e1 + A[5] * e2)));
       if (DIM == 3) atomicAdd(&g.f[2][node], -(wf * (A[6] * e0 + A[7] * e1 + A[8] * e2)));
-    } else if (what & P2G_FORCE) {
+    } else if ((what & P2G_FORCE) && !(TL && nrigid)) {
       double f0 = -(A[0] * wfd0 + A[1] * wfd1 + A[2] * wfd2);
       if (sp.axisymmetric) f0 -= hoop * wf;
       atomicAdd(&g.f[0][node], f0);
       if (DIM >= 2) atomicAdd(&g.f[1][node], -(A[3] * wfd0 + A[4] * wfd1 + A[5] * wfd2));
       if (DIM == 3) atomicAdd(&g.f[2][node], -(A[6] * wfd0 + A[7] * wfd1 + A[8] * wfd2));
     }
-    if (what & P2G_MB) {
+    if ((what & P2G_MB) && !nrigid) {
       atomicAdd(&g.mb[0][node], wf * mbp[0]);
       if (DIM >= 2) atomicAdd(&g.mb[1][node], wf * mbp[1]);
       if (DIM == 3) atomicAdd(&g.mb[2][node], wf * mbp[2]);
@@ -166,11 +181,12 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
 // ---- grid kernels ----------------------------------------------------------------------------
 // normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
 // Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
-__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T) {
+__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
   double4 rec = g.nv[i];
   const double m = rec.w;
+  const bool free_node = !(rigid_aware && g.rigid[i] != 0); // rigid nodes keep v_update = v (src/grid.cpp:455-461)
   double v[3] = {rec.x, rec.y, rec.z};
   if (normalize) {
 #pragma unroll
@@ -182,9 +198,9 @@ __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, i
   if (temp) { T = g.T[i]; if (normalize_T) { T = (m > 0) ? T / m : 0.0; g.T[i] = T; } }
   if (update) {
     double4 u;
-    u.x = (m != 0) ? v[0] + dt * (g.f[0][i] + g.mb[0][i]) / m : v[0];
-    u.y = (m != 0) ? v[1] + dt * (g.f[1][i] + g.mb[1][i]) / m : v[1];
-    u.z = (m != 0) ? v[2] + dt * (g.f[2][i] + g.mb[2][i]) / m : v[2];
+    u.x = (m != 0 && free_node) ? v[0] + dt * (g.f[0][i] + g.mb[0][i]) / m : v[0];
+    u.y = (m != 0 && free_node) ? v[1] + dt * (g.f[1][i] + g.mb[1][i]) / m : v[1];
+    u.z = (m != 0 && free_node) ? v[2] + dt * (g.f[2][i] + g.mb[2][i]) / m : v[2];
     u.w = temp ? ((m != 0) ? T + dt * (g.Qint[i] + g.Qext[i]) / m : T) : 0.0;
     g.nvu[i] = u;
   }
@@ -252,6 +268,7 @@ __global__ void __launch_bounds__(128) k_g2p(SolidDev s, GridDev g, StepParams s
     if (sp.temp) Tp += wf * ru.w;
     (void)wfd0; (void)wfd1; (void)wfd2;
   })
+  if (sp.rigid_mode == 2) a[0] = a[1] = a[2] = 0.0; // rigid particles: Solid::compute_particle_acceleration leaves a = 0 (src/solid.cpp:767-784)
   particle_advance<TL>(s, sp, ip, vu, a, Tp);
 }
 
@@ -518,10 +535,10 @@ __global__ void __launch_bounds__(128) k_stress(SolidDev s, GridDev g, StepParam
       for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int b = 0; b < 3; b++) L[3 * a + b] *= sp.Di[b];
-      if (s.Lst[0]) {
+    }
+    if (s.Lst[0]) { // APIC family and gradient-enhanced projection read it back in the next momentum pass
 #pragma unroll
-        for (int i = 0; i < 9; i++) s.Lst[i][ip] = L[i];
-      }
+      for (int i = 0; i < 9; i++) s.Lst[i][ip] = L[i];
     }
     PState ps; ps.load(s, mat, sp, ip);
     particle_stress<TL>(s, g, sp, mat, ip, ps, L, qv, wave, hr);

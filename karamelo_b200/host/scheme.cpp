@@ -42,6 +42,168 @@ struct FixInitialVelocityParticles : Fix {
   }
 };
 
+// Per-particle expressions: the reference publishes x, y, z, x0, y0, z0 of the particle before every evaluation
+// (e.g. src/fix_velocity_particles.cpp:143-148).  Constant expressions skip that.
+static inline void publish_particle(Sim &s, const double *x, const std::array<double, 3> &x0) {
+  s.input.vars["x"] = Var("x", x[0]); s.input.vars["y"] = Var("y", x[1]); s.input.vars["z"] = Var("z", x[2]);
+  s.input.vars["x0"] = Var("x0", x0[0]); s.input.vars["y0"] = Var("y0", x0[1]); s.input.vars["z0"] = Var("z0", x0[2]);
+}
+template <class F> static void for_group_solids(Sim &s, int igroup, F f) { // "solid == -1: every solid" loops of the reference's fixes
+  const int solid = s.gsolid[igroup];
+  for (size_t is = 0; is < s.solids.size(); is++) if (solid == -1 || (int)is == solid) f(*s.solids[is]);
+}
+
+// FixVelocityParticles, reference src/fix_velocity_particles.cpp:30-300: v = v(t - dt) before the step, v = v(t) and
+// x = x_old + dt v(t) after advance_particles; the reaction m (v(t) - v_advanced) / dt is published as <id>_x/_y/_z.
+// (The reference also writes v_update at initial_integrate; only Solid::compute_velocity_nodes of a rigid solid reads it,
+// into the scratch copy it keeps in grid->mb, which nothing consumes - src/solid.cpp:366-381, src/grid.cpp:455-461.)
+struct FixVelocityParticles : Fix {
+  bool set[3] = {false, false, false}; Var val[3], prev[3];
+  std::vector<std::vector<double>> xold; // per solid, rows [np][3]
+  void initial_integrate(Sim &s) override {
+    xold.assign(s.solids.size(), {});
+    const int solid = s.gsolid[igroup];
+    for (size_t is = 0; is < s.solids.size(); is++) {
+      if (solid != -1 && (int)is != solid) continue;
+      SolidH &S = *s.solids[is];
+      std::vector<double> &x = xold[is]; x.resize(3 * S.np); std::vector<double> v(3 * S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
+      bool fast = true; for (int d = 0; d < 3; d++) if (set[d] && !prev[d].is_constant()) fast = false;
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        if (!fast) publish_particle(s, &x[3 * ip], S.x0[ip]);
+        for (int d = 0; d < 3; d++) if (set[d]) v[3 * ip + d] = prev[d].result(&s.input);
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_V, v.data()));
+    }
+  }
+  void post_advance_particles(Sim &s) override {
+    double ftot[3] = {0, 0, 0}; const double inv_dt = 1.0 / s.dt;
+    const int solid = s.gsolid[igroup];
+    for (size_t is = 0; is < s.solids.size(); is++) {
+      if (solid != -1 && (int)is != solid) continue;
+      SolidH &S = *s.solids[is];
+      std::vector<double> x(3 * S.np), v(3 * S.np), mass(S.np); const std::vector<double> &xo = xold[is];
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_MASS, mass.data()));
+      bool fast = true; for (int d = 0; d < 3; d++) if (set[d] && !val[d].is_constant()) fast = false;
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        if (!fast) publish_particle(s, &xo[3 * ip], S.x0[ip]);
+        double Dv[3] = {0, 0, 0};
+        for (int d = 0; d < 3; d++) if (set[d]) {
+          const double vd = val[d].result(&s.input);
+          Dv[d] = vd - v[3 * ip + d]; v[3 * ip + d] = vd; x[3 * ip + d] = xo[3 * ip + d] + s.dt * vd;
+        }
+        for (int d = 0; d < 3; d++) ftot[d] += (inv_dt * mass[ip]) * Dv[d];
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_V, v.data()));
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_X, x.data()));
+    }
+    s.input.vars[id + "_x"] = Var(id + "_x", ftot[0]); s.input.vars[id + "_y"] = Var(id + "_y", ftot[1]); s.input.vars[id + "_z"] = Var(id + "_z", ftot[2]);
+  }
+};
+
+// FixTemperatureParticles, reference src/fix_temperature_particles.cpp:92-181: T = T(t - dt) before the step, T = T(t) after
+// advance_particles
+struct FixTemperatureParticles : Fix {
+  Var val, prev;
+  void apply(Sim &s, Var &e) {
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      std::vector<double> x(3 * S.np), T(S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_T, T.data()));
+      const bool fast = e.is_constant();
+      if (!fast) s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        if (!fast) publish_particle(s, &x[3 * ip], S.x0[ip]);
+        T[ip] = e.result(&s.input);
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_T, T.data()));
+    });
+  }
+  void initial_integrate(Sim &s) override { apply(s, prev); }
+  void post_advance_particles(Sim &s) override { apply(s, val); }
+};
+
+// FixInitialStress, reference src/fix_initial_stress.cpp:96-162: at step 1, sigma components (xx, yy, zz, yz, xz, xy) of the
+// group's particles; total-Lagrangian: vol0PK1 = vol0 sigma
+struct FixInitialStress : Fix {
+  bool set[6] = {false, false, false, false, false, false}; Var val[6];
+  void initial_integrate(Sim &s) override {
+    if (s.ntimestep != 1) return;
+    static const int A[6] = {0, 1, 2, 1, 0, 0}, B[6] = {0, 1, 2, 2, 2, 1};
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      std::vector<double> x(3 * S.np), sig(9 * S.np), pk1, vol0;
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_SIGMA, sig.data()));
+      if (s.is_TL) { pk1.resize(9 * S.np); vol0.resize(S.np); s.check(kml_solid_download(s.ctx, S.dev, KML_P_VOL0PK1, pk1.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_VOL0, vol0.data())); }
+      bool fast = true; for (int k = 0; k < 6; k++) if (set[k] && !val[k].is_constant()) fast = false;
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        if (!fast) publish_particle(s, &x[3 * ip], S.x0[ip]);
+        for (int k = 0; k < 6; k++) if (set[k]) { const double v = val[k].result(&s.input); sig[9 * ip + 3 * A[k] + B[k]] = v; sig[9 * ip + 3 * B[k] + A[k]] = v; }
+        if (s.is_TL) for (int k = 0; k < 9; k++) pk1[9 * ip + k] = vol0[ip] * sig[9 * ip + k];
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_SIGMA, sig.data()));
+      if (s.is_TL) s.check(kml_solid_upload(s.ctx, S.dev, KML_P_VOL0PK1, pk1.data()));
+    });
+  }
+};
+
+// Node fixes work on every solid's grid (TL) or on the shared background grid (UL), like the "solid == -1" loops of the reference
+template <class F> static void for_group_grids(Sim &s, int igroup, F f) {
+  if (!s.is_TL) { if (s.grid) f(*s.grid); return; }
+  for_group_solids(s, igroup, [&](SolidH &S) { f(*S.grid); });
+}
+
+// FixTemperatureNodes, reference src/fix_temperature_nodes.cpp:74-146: T_update = T(t), T = T(t - dt) after the grid update;
+// T = T(t) after the MUSL re-projection
+struct FixTemperatureNodes : Fix {
+  Var val, prev;
+  void post_update_grid_state(Sim &s) override {
+    const double T = val.result(&s.input), Told = prev.result(&s.input);
+    for_group_grids(s, igroup, [&](GridH &g) {
+      std::vector<double> Tn(g.nnodes), Tu(g.nnodes);
+      s.check(kml_grid_download(s.ctx, g.id, KML_N_T, Tn.data())); s.check(kml_grid_download(s.ctx, g.id, KML_N_T_UPDATE, Tu.data()));
+      for (int64_t i = 0; i < g.nnodes; i++) if (g.mask[i] & groupbit) { Tu[i] = T; Tn[i] = Told; }
+      s.check(kml_grid_upload(s.ctx, g.id, KML_N_T, Tn.data())); s.check(kml_grid_upload(s.ctx, g.id, KML_N_T_UPDATE, Tu.data()));
+    });
+  }
+  void post_velocities_to_grid(Sim &s) override {
+    const double T = val.result(&s.input);
+    for_group_grids(s, igroup, [&](GridH &g) {
+      std::vector<double> Tn(g.nnodes);
+      s.check(kml_grid_download(s.ctx, g.id, KML_N_T, Tn.data()));
+      for (int64_t i = 0; i < g.nnodes; i++) if (g.mask[i] & groupbit) Tn[i] = T;
+      s.check(kml_grid_upload(s.ctx, g.id, KML_N_T, Tn.data()));
+    });
+  }
+};
+
+// FixInitialVelocityNodes, reference src/fix_initial_velocity_nodes.cpp:103-226: at step 1, v_update after the grid update and v
+// after the MUSL re-projection take the given (x0, y0, z0)-dependent values on the group's nodes
+struct FixInitialVelocityNodes : Fix {
+  bool set[3] = {false, false, false}; Var val[3];
+  void apply(Sim &s, int field) {
+    if (s.ntimestep != 1) return;
+    for_group_grids(s, igroup, [&](GridH &g) {
+      std::vector<double> v(3 * g.nnodes), x0(3 * g.nnodes);
+      s.check(kml_grid_download(s.ctx, g.id, field, v.data())); s.check(kml_grid_download(s.ctx, g.id, KML_N_X0, x0.data()));
+      for (int64_t i = 0; i < g.nnodes; i++) {
+        if (!(g.mask[i] & groupbit)) continue;
+        s.input.vars["x0"] = Var("x0", x0[3 * i]); s.input.vars["y0"] = Var("y0", x0[3 * i + 1]); s.input.vars["z0"] = Var("z0", x0[3 * i + 2]);
+        for (int d = 0; d < 3; d++) if (set[d]) v[3 * i + d] = val[d].result(&s.input);
+      }
+      s.check(kml_grid_upload(s.ctx, g.id, field, v.data()));
+    });
+  }
+  void post_update_grid_state(Sim &s) override { apply(s, KML_N_V_UPDATE); }
+  void post_velocities_to_grid(Sim &s) override { apply(s, KML_N_V); }
+};
+
 // FixVelocityNodes, reference src/fix_velocity_nodes.cpp:36-268
 struct FixVelocityNodes : Fix {
   bool set[3] = {false, false, false}; Var val[3], prev[3];
@@ -126,6 +288,13 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
     if (f.igroup == -1) fatal("Error: could not find group ID " + a[2] + "\n");
     f.groupbit = gbitmask[f.igroup];
   };
+  // the value one step earlier: SpecialFunc::replace_all(input->parsev(arg).str(), "time", "(time - dt)"),
+  // src/fix_velocity_particles.cpp:84-88, src/fix_temperature_nodes.cpp:50-52
+  auto time_shifted = [&](const std::string &arg) {
+    std::string e = input.parsev(arg).str(); size_t pos = 0;
+    while ((pos = e.find("time", pos)) != std::string::npos) { e.replace(pos, 4, "(time - dt)"); pos += 11; }
+    return e;
+  };
   if (style == "initial_velocity_particles") {
     auto f = new FixInitialVelocityParticles(); fix.reset(f); group_of(*f);
     if (a.size() != 6) fatal("Error: fix initial_velocity_particles: wrong number of arguments.\n");
@@ -144,6 +313,42 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
       while ((pos = previous.find("time", pos)) != std::string::npos) { previous.replace(pos, 4, "time - dt"); pos += 9; }
       f->prev[d] = input.parsev(previous);
     }
+    f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
+  } else if (style == "velocity_particles") {
+    auto f = new FixVelocityParticles(); fix.reset(f); group_of(*f);
+    if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_velocity_nodes.\n");
+    if (gpon[f->igroup] != "particles") fatal("fix_velocity_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    for (int d = 0; d < dimension; d++) {
+      if (a[3 + d] == "NULL") continue;
+      f->val[d] = input.parsev(a[3 + d]); f->set[d] = true;
+      f->prev[d] = input.parsev(time_shifted(a[3 + d]));
+    }
+    f->mask = INITIAL_INTEGRATE | POST_ADVANCE_PARTICLES;
+  } else if (style == "temperature_particles" || style == "temperature_nodes") {
+    if (a.size() < 4) fatal("Error: not enough arguments.\nUsage: fix(fix-ID, temperature_nodes, group-ID, T)\n");
+    const bool nodes = style == "temperature_nodes";
+    Var val = input.parsev(a[3]), prev = input.parsev(time_shifted(a[3]));
+    if (nodes) {
+      auto f = new FixTemperatureNodes(); fix.reset(f); group_of(*f);
+      if (gpon[f->igroup] != "nodes") fatal("fix_temperature_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+      f->val = val; f->prev = prev; f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
+    } else {
+      auto f = new FixTemperatureParticles(); fix.reset(f); group_of(*f);
+      if (gpon[f->igroup] != "particles") fatal("fix_temperature_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+      f->val = val; f->prev = prev; f->mask = INITIAL_INTEGRATE | POST_ADVANCE_PARTICLES;
+    }
+  } else if (style == "initial_stress") {
+    auto f = new FixInitialStress(); fix.reset(f); group_of(*f);
+    if (a.size() < 9) fatal("Error: not enough arguments.\nUsage: fix(fix-ID, initial_stress, group-ID, sigma_xx, sigma_yy, sigma_zz, sigma_yz, sigma_xz, sigma_xy)\n");
+    if (a.size() > 9) fatal("Error: too many arguments.\nUsage: fix(fix-ID, initial_stress, group-ID, sigma_xx, sigma_yy, sigma_zz, sigma_yz, sigma_xz, sigma_xy)\n");
+    if (gpon[f->igroup] != "particles" && gpon[f->igroup] != "all") fatal("fix_initial_stress needs to be given a group of particles" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    for (int k = 0; k < 6; k++) if (a[3 + k] != "NULL") { f->val[k] = input.parsev(a[3 + k]); f->set[k] = true; }
+    f->mask = INITIAL_INTEGRATE;
+  } else if (style == "initial_velocity_nodes") {
+    auto f = new FixInitialVelocityNodes(); fix.reset(f); group_of(*f);
+    if (a.size() < 6) fatal("Error: too few arguments for fix_initial_velocity_nodes: requires at least 6 arguments. " + std::to_string(a.size()) + " received.\n");
+    if (gpon[f->igroup] != "nodes") fatal("fix_initial_velocity_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    for (int d = 0; d < 3; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
     f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
   } else if (style == "body_force") {
     auto f = new FixBodyForce(); fix.reset(f); group_of(*f);
@@ -201,6 +406,7 @@ void Sim::hooks(int which) {
     case INITIAL_INTEGRATE: f->initial_integrate(*this); break;
     case POST_PARTICLES_TO_GRID: f->post_particles_to_grid(*this); break;
     case POST_UPDATE_GRID_STATE: f->post_update_grid_state(*this); break;
+    case POST_ADVANCE_PARTICLES: f->post_advance_particles(*this); break;
     case POST_VELOCITIES_TO_GRID: f->post_velocities_to_grid(*this); break;
     case FINAL_INTEGRATE: f->final_integrate(*this); break;
     default: break;

@@ -70,6 +70,7 @@ struct Fix {
   virtual void initial_integrate(Sim &) {}
   virtual void post_particles_to_grid(Sim &) {}
   virtual void post_update_grid_state(Sim &) {}
+  virtual void post_advance_particles(Sim &) {}
   virtual void post_velocities_to_grid(Sim &) {}
   virtual void final_integrate(Sim &) {}
 };

@@ -326,6 +326,47 @@ dt_factor(0.5)
 """
 
 
+# Rigid bodies (material(..., rigid, rho), src/material.h:49): the second disk / ball is rigid; nodes inside its stencils carry
+# Grid::rigid, take mass and momentum from the rigid solid only and keep v_update = v, so the deformable disk sees the rigid
+# one as a moving velocity boundary condition (a6, a7, a11, a12).  No shipped example still parses its own
+# rigid material line (the usage gained a density argument), so these variants of C1 / C4 stand in.
+def rigid_disks(scheme="musl", method="method(ulmpm, FLIP, linear, 0.99)", tl=False):
+    base = bouncing_balls("minimize_penetration", method=method) if tl else two_disks(scheme, method=method)
+    marker, mat = "solid(sBall2, region, rBall2, ppc1d, mat1, cellsize,0)", "material(mat1, linear, rho, E, nu)\n"
+    assert marker in base and mat in base
+    # both materials are declared before the first solid: the reference keeps raw pointers into a growing vector<Mat>
+    # (src/material.cpp:293-298, src/solid.cpp:72), so a material added after a solid leaves that solid's pointer dangling
+    return base.replace(mat, mat + "material(matr, rigid, rho)\n").replace(marker, "solid(sBall2, region, rBall2, ppc1d, matr, cellsize,0)")
+
+
+# Fixes that sit between the stages beyond those of the BASELINE configs: velocity_particles (a rigid tool
+# driven at a prescribed, time-dependent velocity), initial_stress, initial_velocity_nodes, temperature_nodes / _particles.
+def driven_tool():
+    return rigid_disks("musl", method="method(ulmpm, FLIP, cubic-spline, 0.99)").replace(
+        "fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, NULL)",
+        "fix(vtool, velocity_particles, gBall2, -v*(0.5+time), -v)")
+
+
+def prestressed_disks():
+    return two_disks("musl", method="method(ulmpm, FLIP, linear, 0.99)") + """
+fix(s0, initial_stress, gBall1, 0.5, -0.25+x0, NULL, NULL, NULL, 0.125)
+region(rKick, block, -0.1, 0.1, -0.1, 0.1)
+group(gKick, nodes, region, rKick, solid, sBall1)
+fix(vn0, initial_velocity_nodes, gKick, 0.05*y0, -0.05, NULL)
+"""
+
+
+def heated_bar():
+    return tensile(True) + """
+region(rHot, block, INF, -hLx+cellsize, INF, INF, INF, INF)
+group(gHotN, nodes, region, rHot, solid, solid1)
+fix(fTn, temperature_nodes, gHotN, Tr+200*time/1e-4)
+region(rCold, block, hLx-cellsize, INF, INF, INF, INF, INF)
+group(gColdP, particles, region, rCold, solid, solid1)
+fix(fTp, temperature_particles, gColdP, Tr-10+x0)
+"""
+
+
 # name -> (script, is_TL, thermal, steps)
 CASES = {
     "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
@@ -358,4 +399,15 @@ CASES = {
     "x_cpdi_ul_q4": (cpdi_bar("ulcpdi", "Q4"), False, False, 100),
     "x_cpdi_tl_r4": (cpdi_bar("tlcpdi", "R4"), True, False, 100),
     "x_cpdi_tl_q4": (cpdi_bar("tlcpdi", "Q4"), True, False, 100),
+    # rigid bodies: ULMPM linear MUSL, ULMPM cubic USL, TLMPM with contact
+    "x_rigid_ul_linear_musl": (rigid_disks("musl"), False, False, 100),
+    "x_rigid_ul_cubic_usl": (rigid_disks("usl", method="method(ulmpm, FLIP, cubic-spline, 0.99)"), False, False, 100),
+    "x_rigid_tl_contact": (rigid_disks(tl=True, method="method(tlmpm, FLIP, linear, 0.99)"), True, False, 100),
+    # gradient-enhanced momentum projection (method(..., mechanical, gradient-enhanced), src/solid.cpp:369-371)
+    "x_ge_ul_cubic_musl": (two_disks("musl", method="method(ulmpm, FLIP, cubic-spline, 0.99, mechanical, gradient-enhanced)"), False, False, 100),
+    "x_ge_ul_linear_usl": (two_disks("usl", method="method(ulmpm, FLIP, linear, 0.99, mechanical, gradient-enhanced)"), False, False, 100),
+    # fixes between the stages beyond the BASELINE configs
+    "x_fix_velocity_particles": (driven_tool(), False, False, 100),
+    "x_fix_initial_stress_velocity_nodes": (prestressed_disks(), False, False, 100),
+    "x_fix_temperature": (heated_bar(), True, True, 100),
 }
