@@ -384,7 +384,8 @@ int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   Solid *S = c->solids[sid]; const long long np = S->s.np;
   if (field == KML_P_PTAG) { CU(cudaMemcpyAsync(S->s.ptag, src, sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_P_MASK) { CU(cudaMemcpyAsync(S->s.mask, src, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
-  if (field == KML_P_X && !c->c.is_TL) S->moved = false;
+  // KML_P_X between advance_particles and the next weight evaluation lands in the advanced positions (xn, see solid_field): the
+  // rest of the step keeps the step-start weights, like the reference's cached lists (fix velocity_particles, src/fix_velocity_particles.cpp:228-300)
   if (field == KML_P_MBP) S->mbp_nonzero = true;
   { RowMap rm;
     if (cpdi_rowmap(S, field, rm)) {

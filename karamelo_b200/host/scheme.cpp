@@ -7,6 +7,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <zlib.h>
 
 namespace kmlh {
 
@@ -275,6 +276,40 @@ struct ComputeEnergy : Compute {
     s.input.vars[id] = Var(id, e);
   }
 };
+// "if (update->ntimestep != output->next && update->ntimestep != update->nsteps) return;" at the top of every compute_value
+// (src/compute_max_plastic_strain.cpp:64-65): nothing is evaluated at step 0 of a run
+static bool output_due(const Sim &s) {
+  bool due = s.ntimestep == s.next_log || s.ntimestep == s.nsteps;
+  for (auto &d : s.dumps) due = due || d.next == s.ntimestep;
+  return due;
+}
+// ComputeMaxPlasticStrain, reference src/compute_max_plastic_strain.cpp:62-106: <id>_Epmax, <id>_Tmax over the group
+struct ComputeMaxPlasticStrain : Compute {
+  void compute_value(Sim &s) override {
+    if (!output_due(s)) return;
+    double epmax = 0, tmax = 0;
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      std::vector<double> ep(S.np), T(S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN, ep.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_T, T.data()));
+      for (int64_t ip = 0; ip < S.np; ip++) if (S.mask[ip] & groupbit) { epmax = std::max(epmax, ep[ip]); tmax = std::max(tmax, T[ip]); }
+    });
+    s.input.vars[id + "_Epmax"] = Var(id + "_Epmax", epmax); s.input.vars[id + "_Tmax"] = Var(id + "_Tmax", tmax);
+  }
+};
+// ComputeAverageVelocity, reference src/compute_average_velocity.cpp:60-117: <id>_x/_y/_z = sum(v) / n over the group
+struct ComputeAverageVelocity : Compute {
+  void compute_value(Sim &s) override {
+    if (!output_due(s)) return;
+    double sum[3] = {0, 0, 0}; int n = 0;
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      std::vector<double> v(3 * S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
+      for (int64_t ip = 0; ip < S.np; ip++) if (S.mask[ip] & groupbit) { for (int d = 0; d < 3; d++) sum[d] += v[3 * ip + d]; n++; }
+    });
+    const char *sfx[3] = {"_x", "_y", "_z"};
+    for (int d = 0; d < 3; d++) s.input.vars[id + sfx[d]] = Var(id + sfx[d], sum[d] / n);
+  }
+};
 } // namespace
 
 // Modify::add_fix, reference src/modify.cpp:95-140 (fix(ID, style, group-ID, args...))
@@ -390,12 +425,17 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
 
 Var Sim::cmd_compute(std::vector<std::string> &a) { // Modify::add_compute
   if (a.size() < 3) fatal("Error: too few arguments for the compute command.\n");
-  if (a[1] != "kinetic_energy" && a[1] != "strain_energy") fatal("compute style " + a[1] + " is outside the hot path covered by this build.\n");
-  auto c = new ComputeEnergy(); c->id = a[0]; c->style = a[1]; c->kinetic = a[1] == "kinetic_energy";
+  Compute *c = nullptr;
+  if (a[1] == "kinetic_energy" || a[1] == "strain_energy") { auto e = new ComputeEnergy(); e->kinetic = a[1] == "kinetic_energy"; c = e; input.vars[a[0]] = Var(a[0], 0); }
+  else if (a[1] == "max_plastic_strain") { c = new ComputeMaxPlasticStrain(); input.vars[a[0] + "_Epmax"] = Var(a[0] + "_Epmax", 0); input.vars[a[0] + "_Tmax"] = Var(a[0] + "_Tmax", 0); }
+  else if (a[1] == "average_velocity") { c = new ComputeAverageVelocity(); for (const char *sfx : {"_x", "_y", "_z"}) input.vars[a[0] + sfx] = Var(a[0] + sfx, 0); }
+  else fatal("compute style " + a[1] + " is outside the hot path covered by this build.\n");
+  c->id = a[0]; c->style = a[1];
   c->igroup = find_group(a[2]); if (c->igroup == -1) fatal("Error: could not find group ID " + a[2] + "\n");
   c->groupbit = gbitmask[c->igroup];
+  if (a[1] != "kinetic_energy" && a[1] != "strain_energy" && gpon[c->igroup] != "particles" && gpon[c->igroup] != "all")
+    fatal("compute_" + a[1] + " needs to be given a group of particles" + gpon[c->igroup] + ", " + a[2] + " is a group of " + gpon[c->igroup] + ".\n");
   computes.emplace_back(c);
-  input.vars[c->id] = Var(c->id, 0);
   return Var(0);
 }
 
@@ -423,11 +463,24 @@ Var Sim::cmd_dump(std::vector<std::string> &a) { // Output::add_dump: dump(ID, g
   dumps.push_back(d); return Var(0);
 }
 
+// DumpParticleGz / DumpGridGz (src/dump_particle_gz.cpp, src/dump_grid_gz.cpp) write the same text through gzstream
+static void emit_dump(const std::string &fn, const std::string &text, bool gz) {
+  if (!gz) {
+    std::ofstream f(fn, std::ios::out | std::ios::binary);
+    if (!f) fatal("Error: cannot write in file: " + fn + ".\n");
+    f << text; return;
+  }
+  gzFile f = gzopen(fn.c_str(), "wb");
+  if (!f) fatal("Error: cannot write in file: " + fn + ".\n");
+  size_t off = 0;
+  while (off < text.size()) { const unsigned n = (unsigned)std::min<size_t>(text.size() - off, 1u << 30); if (gzwrite(f, text.data() + off, n) <= 0) { gzclose(f); fatal("Error: cannot write in file: " + fn + ".\n"); } off += n; }
+  gzclose(f);
+}
+
 static void write_particle_dump(Sim &s, const Dump &d) { // DumpParticle::write, reference src/dump_particle.cpp:52-161
   std::string fn = d.filename; size_t star = fn.find('*');
   if (star != std::string::npos) fn = fn.substr(0, star) + std::to_string(s.ntimestep) + fn.substr(star + 1);
-  std::ofstream os(fn);
-  if (!os) fatal("Error: cannot write in file: " + fn + ".\n");
+  std::ostringstream os;
   int64_t total = 0; for (auto &S : s.solids) total += S->np;
   os << "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n" << total << "\nITEM: BOX BOUNDS sm sm sm\n";
   for (int k = 0; k < 3; k++) os << s.boxlo[k] << " " << s.boxhi[k] << "\n";
@@ -469,19 +522,20 @@ static void write_particle_dump(Sim &s, const Dump &d) { // DumpParticle::write,
       os << "\n";
     }
   }
+  emit_dump(fn, os.str(), d.style == "particle/gz");
 }
 
 static void write_grid_dump(Sim &s, const Dump &d) { // DumpGrid::write, reference src/dump_grid.cpp:50-150
   std::string fn = d.filename; size_t star = fn.find('*');
   if (star != std::string::npos) fn = fn.substr(0, star) + (s.nranks > 1 ? "proc-" + std::to_string(s.rank) + "." : "") + std::to_string(s.ntimestep) + fn.substr(star + 1);
-  std::ofstream os(fn);
-  if (!os) fatal("Error: cannot write in file: " + fn + ".\n");
+  std::ostringstream os;
   std::vector<GridH *> grids;
   for (auto &S : s.solids) if (std::find(grids.begin(), grids.end(), S->grid) == grids.end()) grids.push_back(S->grid);
   int64_t total = 0; for (auto g : grids) total += g->nnodes;
   os << "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n" << total << "\nITEM: BOX BOUNDS sm sm sm\n";
   for (int k = 0; k < 3; k++) os << s.boxlo[k] << " " << s.boxhi[k] << "\n";
-  os << "ITEM: ATOMS id type tag ";
+  const bool gz = d.style == "grid/gz"; // the gz variant has no tag column (src/dump_grid_gz.cpp:99,108)
+  os << (gz ? "ITEM: ATOMS id type " : "ITEM: ATOMS id type tag ");
   for (auto &f : d.fields) os << f << " ";
   os << "\n";
   int igrid = 0;
@@ -494,7 +548,8 @@ static void write_grid_dump(Sim &s, const Dump &d) { // DumpGrid::write, referen
     if (s.temp) s.check(kml_grid_download(s.ctx, g->id, KML_N_T, T.data()));
     for (int64_t i = 0; i < n; i++) {
       const int64_t tag = i + (int64_t)gd.goff * gd.n[1] * gd.n[2]; // ntag = nz ny i + nz j + k of the global grid, src/grid.cpp:251
-      os << tag << " " << igrid + 1 << " " << tag << " ";
+      os << tag << " " << igrid + 1 << " ";
+      if (!gz) os << tag << " ";
       for (auto &f : d.fields) {
         if (f == "x") os << x[3 * i]; else if (f == "y") os << x[3 * i + 1]; else if (f == "z") os << x[3 * i + 2];
         else if (f == "vx") os << v[3 * i]; else if (f == "vy") os << v[3 * i + 1]; else if (f == "vz") os << v[3 * i + 2];
@@ -508,6 +563,7 @@ static void write_grid_dump(Sim &s, const Dump &d) { // DumpGrid::write, referen
     }
     igrid++;
   }
+  emit_dump(fn, os.str(), d.style == "grid/gz");
 }
 
 void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
@@ -524,7 +580,7 @@ void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
 
 void Sim::output_write(int64_t step) { // Output::write, src/output.cpp:128-199
   for (auto &d : dumps)
-    if (d.next == step) { if (d.style == "particle") write_particle_dump(*this, d); else if (d.style == "grid") write_grid_dump(*this, d); d.next += d.every; }
+    if (d.next == step) { if (d.style == "particle" || d.style == "particle/gz") write_particle_dump(*this, d); else if (d.style == "grid" || d.style == "grid/gz") write_grid_dump(*this, d); d.next += d.every; }
   if (next_log == step || step == 0) {
     for (auto &c : computes) c->compute_value(*this); // Modify::run_computes
     if (!quiet) {

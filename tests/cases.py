@@ -360,7 +360,7 @@ def heated_bar():
     return tensile(True) + """
 region(rHot, block, INF, -hLx+cellsize, INF, INF, INF, INF)
 group(gHotN, nodes, region, rHot, solid, solid1)
-fix(fTn, temperature_nodes, gHotN, Tr+200*time/1e-4)
+fix(fTn, temperature_nodes, gHotN, Tr+100*time/0.01)
 region(rCold, block, hLx-cellsize, INF, INF, INF, INF, INF)
 group(gColdP, particles, region, rCold, solid, solid1)
 fix(fTp, temperature_particles, gColdP, Tr-10+x0)

@@ -1,0 +1,80 @@
+"""Script-surface features beyond the shipped examples, checked against the UNMODIFIED reference binary: the computes
+max_plastic_strain / average_velocity (src/compute_max_plastic_strain.cpp, src/compute_average_velocity.cpp), the gz dump
+styles (src/dump_particle_gz.cpp, src/dump_grid_gz.cpp), and the output variables of fix velocity_particles
+(src/fix_velocity_particles.cpp:228-300).  Build-container only (needs /root/reference and oracle/_ref); the back end is
+the CPU oracle, the CUDA back end shares the same host code and runs the same cases in tests/test_parity_gpu.py."""
+import glob
+import gzip
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+from cases import driven_tool, taylor_bar, tensile, two_disks
+from conftest import ROOT
+from test_shipped_examples import OUR_CLI, REF_BIN, log_rows
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.isdir("/root/reference")), reason="needs /root/reference and oracle/_ref (build container only)")
+
+
+def run_both(text):
+    out = {}
+    for name, exe in (("ref", REF_BIN), ("our", OUR_CLI)):
+        d = tempfile.mkdtemp(prefix="kmlextra_")
+        try:
+            open(os.path.join(d, "in.mpm"), "w").write(text)
+            p = subprocess.run([exe, "-i", "in.mpm"], cwd=d, capture_output=True, text=True, timeout=600)
+            files = {os.path.basename(f): open(f, "rb").read() for f in sorted(glob.glob(os.path.join(d, "dump*")))}
+            out[name] = (p.returncode, p.stdout + p.stderr, files)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return out["ref"], out["our"]
+
+
+def same_log(ref, our):
+    a, b = log_rows(ref), log_rows(our)
+    assert len(a) >= 2 and len(a) == len(b), (len(a), len(b))
+    for ra, rb in zip(a, b):
+        assert len(ra) == len(rb), (ra, rb)
+        for x, y in zip(ra, rb):
+            assert abs(x - y) <= 2e-5 * max(abs(x), abs(y)) + 1e-12, (ra, rb)  # 6 printed digits; sums of ~1e-16 noise stay below 1e-12
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cli(oracle_lib):
+    if not os.path.exists(OUR_CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+
+
+def test_compute_average_velocity():
+    text = taylor_bar("linear") + "compute(va, average_velocity, gBall1)\nlog_modify(custom, step, dt, time, va_x)\nlog(5)\nrun(20)\n"
+    (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+
+
+def test_compute_max_plastic_strain_thermal():
+    # the reference reads Solid::T unconditionally (src/compute_max_plastic_strain.cpp:79), so it only runs thermo-mechanical
+    text = tensile(True) + "compute(Ep, max_plastic_strain, all)\nlog_modify(custom, step, dt, time, Ep_Epmax, Ep_Tmax)\nlog(20)\nrun(100)\n"
+    (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+
+
+def test_gz_dumps_hold_the_reference_text():
+    text = two_disks("musl") + ("dump(d1, all, particle/gz, 5, dump_p.*.LAMMPS.gz, x, y, z, vx, s11, seq, mass)\n"
+                                "dump(d2, all, grid/gz, 5, dump_g.*.LAMMPS.gz, x, y, z, vx, vy, mass)\nrun(10)\n")
+    (rc_r, _, files_r), (rc_o, out_o, files_o) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    assert len(files_r) == 4 and set(files_r) == set(files_o)
+    for k, v in files_r.items():
+        assert gzip.decompress(files_o[k]) == gzip.decompress(v), "gz dump %s differs from the reference's" % k
+
+
+def test_fix_velocity_particles_publishes_the_reaction():
+    text = driven_tool() + "log_modify(custom, step, dt, time, vtool_x, vtool_y)\nlog(10)\nrun(60)\n"
+    (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
