@@ -103,6 +103,53 @@ void Sim::register_commands() {
   };
   c["xcm"] = [group_sum](std::vector<std::string> &a) { return group_sum(a, true); };
   c["internal_force"] = [group_sum](std::vector<std::string> &a) { return group_sum(a, false); };
+  // ExtForce command (src/external_force.cpp -> Group::external_force, src/group.cpp:410-462): the sum of the particle forces
+  // f_p = a_p m_p of a particle group restricted to one solid, as a lazy variable
+  c["external_force"] = [this](std::vector<std::string> &a) -> Var {
+    if (a.size() < 2) fatal("Illegal run command");
+    const int ig = find_group(a[0]);
+    if (ig == -1) fatal("Error: could not find group named: " + a[0] + "\n");
+    int dir; if (a[1] == "x") dir = 0; else if (a[1] == "y") dir = 1; else if (a[1] == "z") dir = 2;
+    else fatal("Error: directions should be either x,y or z: " + a[1] + " not understood.\n");
+    if (gpon[ig] == "nodes") fatal("Error: cannot calculate the external forces applied to the node group " + a[0] + ".\n");
+    if (gsolid[ig] == -1) fatal("Error: external_force needs a group restricted to one solid (the reference indexes solids[-1] for \"all\").\n");
+    SolidH &s = *solids[gsolid[ig]]; const int bit = gbitmask[ig];
+    int64_t np = 0; check(kml_solid_np(ctx, s.dev, &np));
+    std::vector<double> f(3 * np); std::vector<int> mask(np);
+    check(kml_solid_download(ctx, s.dev, KML_P_F, f.data())); check(kml_solid_download(ctx, s.dev, KML_P_MASK, mask.data()));
+    double sum = 0; for (int64_t i = 0; i < np; i++) if (mask[i] & bit) sum += f[3 * i + dir];
+    return Var("external_force(" + a[0] + "," + a[1] + ")", sum);
+  };
+  c["delete_compute"] = [this](std::vector<std::string> &a) { // Modify::delete_compute, src/modify.cpp:218-231
+    for (size_t i = 0; i < computes.size(); i++) if (computes[i]->id == a[0]) { computes.erase(computes.begin() + i); return Var(0); }
+    fatal("Could not find compute ID to delete.\n");
+  };
+  // TranslateParticles (src/translate_particles.cpp:28-120): translate_particles(solid | all, region, region-ID, dx, dy, dz) moves the
+  // particles currently inside the region, reference positions included
+  c["translate_particles"] = [this](std::vector<std::string> &a) -> Var {
+    if (a.size() < 6) fatal("Error: not enough arguments.\nUsage: translate_particles(solid-ID, region, region-ID, delx, dely, delz)\n");
+    const int isolid = find_solid(a[0]);
+    if (isolid < 0 && a[0] != "all") fatal("Error: solid " + a[0] + " unknown.\n");
+    if (a[1] != "region") fatal("Error: use of illegal keyword for translate_particles command: " + a[1] + "\n");
+    const int ir = find_region(a[2]);
+    if (ir < 0) fatal("Error: region " + a[2] + " unknown.\n");
+    Var del[3]; bool set[3];
+    for (int d = 0; d < 3; d++) { del[d] = input.parsev(a[3 + d]); set[d] = !(del[d].is_constant() && std::fabs(del[d].result()) <= 1.0e-12); }
+    for (size_t is = 0; is < solids.size(); is++) {
+      if (isolid >= 0 && (int)is != isolid) continue;
+      SolidH &S = *solids[is];
+      std::vector<double> x(3 * S.np), x0(3 * S.np);
+      check(kml_solid_download(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_download(ctx, S.dev, KML_P_X0, x0.data()));
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (regions[ir]->inside(x[3 * ip], x[3 * ip + 1], x[3 * ip + 2]) != 1) continue;
+        input.vars["x0"] = Var("x0", x0[3 * ip]); input.vars["y0"] = Var("y0", x0[3 * ip + 1]); input.vars["z0"] = Var("z0", x0[3 * ip + 2]);
+        input.vars["x"] = Var("x", x[3 * ip]); input.vars["y"] = Var("y", x[3 * ip + 1]); input.vars["z"] = Var("z", x[3 * ip + 2]);
+        for (int d = 0; d < 3; d++) if (set[d]) { const double v = del[d].result(&input); x0[3 * ip + d] += v; x[3 * ip + d] += v; S.x0[ip][d] = x0[3 * ip + d]; }
+      }
+      check(kml_solid_upload(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_upload(ctx, S.dev, KML_P_X0, x0.data()));
+    }
+    return Var(0);
+  };
   c["plot"] = [](std::vector<std::string> &) { return Var(0); };
   c["save_plot"] = [](std::vector<std::string> &) { return Var(0); };
 }

@@ -78,3 +78,14 @@ def test_fix_velocity_particles_publishes_the_reaction():
     (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
     assert rc_r == 0 and rc_o == 0, out_o[-400:]
     same_log(out_r, out_o)
+
+
+def test_translate_particles_external_force_delete_compute():
+    # src/translate_particles.cpp, Group::external_force (src/group.cpp:410-462), Modify::delete_compute (src/modify.cpp:218-231)
+    text = two_disks("musl") + ("region(rMove, block, 0, INF, 0, INF)\ntranslate_particles(sBall2, region, rMove, -0.05, 0.025*x0, 0)\n"
+                                "compute(Ek, kinetic_energy, all)\nfe = external_force(gBall1, x)\nlog_modify(custom, step, dt, time, Ek, fe)\nlog(10)\n"
+                                "dump(d1, all, particle, 20, dump_p.*.LAMMPS, x, y, z, x0, y0, vx)\nrun(40)\ndelete_compute(Ek)\n")
+    (rc_r, out_r, files_r), (rc_o, out_o, files_o) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+    assert len(files_r) == 2 and files_r == files_o
