@@ -231,6 +231,18 @@ int kml_fix_body_force(kml_ctx *ctx, int solid, int groupbit, int set_mask, cons
 /* FixForceNodes::post_particles_to_grid, src/fix_force_nodes.cpp:96-193: the force f is shared equally by the n nodes of the
  * group that carry mass (mb_I += f / n). solid = -1: every solid's grid, n counted per grid. */
 int kml_fix_force_nodes(kml_ctx *ctx, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]);
+/* FixVelocityParticles::initial_integrate / post_advance_particles, src/fix_velocity_particles.cpp:131-300, for values that do not
+ * depend on the particle (x, y, z, x0, y0, z0 absent from the expressions; the host evaluates v(t) and v(t - dt)).
+ * which = 0 (before the step): v = vprev on the group's particles, their positions are remembered;
+ * which = 1 (after advance_particles): ftot += m (v - v_p) / dt, v_p = v, x_p = x_remembered + dt v.  solid = -1: every solid. */
+int kml_fix_velocity_particles(kml_ctx *ctx, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which,
+                               double ftot[3]);
+/* FixTemperatureNodes::post_update_grid_state / post_velocities_to_grid, src/fix_temperature_nodes.cpp:74-146.
+ * which = 0: T_update = T, T = Tprev on masked nodes; which = 1: T = T.  solid = -1: all grids. */
+int kml_fix_temperature_nodes(kml_ctx *ctx, int solid, int groupbit, double T, double Tprev, int which);
+/* FixTemperatureParticles::initial_integrate / post_advance_particles with a particle-independent value,
+ * src/fix_temperature_particles.cpp:92-181: T_p = T on the group's particles.  solid = -1: every solid. */
+int kml_fix_temperature_particles(kml_ctx *ctx, int solid, int groupbit, double T);
 /* FixContactHertz::initial_integrate, src/fix_contact_hertz.cpp:84-201 */
 int kml_fix_contact_hertz(kml_ctx *ctx, int solid1, int solid2, double ftot[3]);
 /* FixContactMinPenetration::initial_integrate, src/fix_contact_min_penetration.cpp:88-258 */

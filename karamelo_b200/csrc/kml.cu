@@ -66,7 +66,7 @@ StepParams step_params(kml_ctx *c) {
   for (int d = 0; d < 3; d++) { sp.boxlo[d] = c->c.boxlo[d]; sp.boxhi[d] = c->c.boxhi[d]; }
   sp.axisymmetric = c->c.axisymmetric; sp.temp = c->c.temp; sp.inv_tav = 0.0; sp.flags = c->d_flags;
   sp.apic = c->apic; sp.mls = !c->c.is_TL && c->c.sub_method == KML_SUB_MLS; sp.asflip = !c->c.is_TL && c->c.sub_method == KML_SUB_ASFLIP;
-  sp.Di[0] = sp.Di[1] = sp.Di[2] = 1.0; sp.rigid_mode = 0; sp.ge = c->c.ge;
+  sp.Di[0] = sp.Di[1] = sp.Di[2] = 1.0; sp.ext = c->c.ge ? 1 : 0;
   return sp;
 }
 
@@ -588,7 +588,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (what == 0) continue;
     bool done = false;
     fill_inertia(c, G, sp);
-    sp.rigid_mode = c->has_rigid ? (S->rigid ? 2 : 1) : 0;
+    sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
     if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
@@ -652,7 +652,7 @@ int kml_advance_particles(kml_ctx *c) {
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
     fill_inertia(c, G, sp);
-    sp.rigid_mode = c->has_rigid ? (S->rigid ? 2 : 1) : 0;
+    sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
     if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
@@ -846,6 +846,52 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
   if (check_launch("k_fix_velocity_nodes")) return 1;
   if (which == 0 && ftot) return read_scratch3(c, ftot);
   return 0;
+}
+
+int kml_fix_velocity_particles(kml_ctx *c, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which, double ftot[3]) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_OTHER);
+  if (c->c.is_CPDI) return fail("kml: fix velocity_particles on the device is not implemented for CPDI (particle domains are not moved)");
+  if (which == 1) CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
+  const double *val = which == 0 ? vprev : v;
+  for (size_t is = 0; is < c->solids.size(); is++) {
+    if (solid != -1 && (int)is != solid) continue;
+    Solid *S = c->solids[is];
+    if (S->s.np == 0) continue;
+    if (which == 1 && !c->c.is_TL && !S->moved) return fail("fix velocity_particles (after the step) called before advance_particles");
+    if (which == 0 && !c->c.is_TL && S->moved) return fail("fix velocity_particles (before the step) called after advance_particles");
+    k_fix_velocity_particles<<<nblocks(S->s.np, 256), 256, 0, c->stream>>>(S->s, groupbit, set_mask, val[0], val[1], val[2], which, c->c.is_TL, c->dt, c->d_scratch);
+    c->launches[KML_STAGE_OTHER]++;
+  }
+  if (check_launch("k_fix_velocity_particles")) return 1;
+  if (which == 1 && ftot) return read_scratch3(c, ftot);
+  return 0;
+}
+
+int kml_fix_temperature_nodes(kml_ctx *c, int solid, int groupbit, double T, double Tprev, int which) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_GRID);
+  std::vector<Grid *> gs;
+  if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
+  for (Grid *G : gs) {
+    if (grid_normalize_if_needed(c, G)) return 1;
+    k_fix_temperature_nodes<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, T, Tprev, which);
+    c->launches[KML_STAGE_GRID]++;
+  }
+  return check_launch("k_fix_temperature_nodes");
+}
+
+int kml_fix_temperature_particles(kml_ctx *c, int solid, int groupbit, double T) {
+  CU(cudaSetDevice(c->dev));
+  StageTimer t(c, KML_STAGE_OTHER);
+  for (size_t is = 0; is < c->solids.size(); is++) {
+    if (solid != -1 && (int)is != solid) continue;
+    Solid *S = c->solids[is];
+    if (S->s.np == 0) continue;
+    k_fix_temperature_particles<<<nblocks(S->s.np, 256), 256, 0, c->stream>>>(S->s, groupbit, T);
+    c->launches[KML_STAGE_OTHER]++;
+  }
+  return check_launch("k_fix_temperature_particles");
 }
 
 int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]) {

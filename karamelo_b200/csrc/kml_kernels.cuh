@@ -26,12 +26,15 @@ struct StepParams {
   // APIC family (Update::SubMethodType APIC / MLS / AFLIP / ASFLIP): affine momentum transfer with the diagonal inertia
   // tensor Di of Solid::compute_inertia_tensor (src/solid.cpp:1440-1478)
   int apic, mls, asflip;
-  int ge;                  // gradient-enhanced momentum projection v_p + L_p (x_I - x_p) (Method::ge, src/solid.cpp:369-371)
+  // ext fills the padding after asflip: growing this struct by even 8 bytes makes ptxas spill in k_g2p_cell (128 registers), +7 % on that stage.
+  // bit 0: gradient-enhanced momentum projection v_p + L_p (x_I - x_p) (Method::ge, src/solid.cpp:369-371).
+  // bits 1-2: rigid bodies (material(..., rigid), src/material.h:49): 0 = no rigid solid in this run, 1 = there are rigid solids and the
+  // solid being processed is deformable, 2 = the solid being processed is rigid.  Nodes inside the stencil of a rigid particle carry
+  // Grid::rigid (src/ulmpm.cpp:267-268, src/tlmpm.cpp:283); the flag is never cleared (src/grid.cpp:248).
+  int ext;
+  __host__ __device__ bool ge() const { return (ext & 1) != 0; }
+  __host__ __device__ int rigid_mode() const { return ext >> 1; }
   double Di[3];
-  // rigid bodies (material(..., rigid), src/material.h:49): 0 = no rigid solid in this run, 1 = there are rigid solids and
-  // the solid being processed is deformable, 2 = the solid being processed is rigid.  Nodes inside the stencil of a rigid
-  // particle carry Grid::rigid (src/ulmpm.cpp:267-268, src/tlmpm.cpp:283); the flag is never cleared (src/grid.cpp:248).
-  int rigid_mode;
   unsigned *flags;         // device error word
 };
 
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   }
   if (what & P2G_MB) { mbp[0] = s.mbp[0][ip]; mbp[1] = s.mbp[1][ip]; mbp[2] = s.mbp[2][ip]; }
   double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, pp[3] = {px, py, pz};
-  const bool affine = sp.apic || sp.ge;
+  const bool affine = sp.apic || sp.ge();
   if (affine) { // compute_velocity_nodes_APIC / compute_external_and_internal_forces_nodes_UL_MLS use the particle position explicitly
     if ((what & P2G_MOM) && s.Lst[0]) {
 #pragma unroll
@@ -131,8 +134,8 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   KML_FOR_STENCIL(st, g, {
     // rigid nodes take mass and momentum from rigid solids only (src/solid.cpp:326,355,412), no body force (:438,:493-:512)
     // and, TL, no internal force (:460)
-    const bool nrigid = sp.rigid_mode != 0 && g.rigid[node] != 0;
-    const bool take_mv = !(nrigid && sp.rigid_mode != 2);
+    const bool nrigid = sp.rigid_mode() != 0 && g.rigid[node] != 0;
+    const bool take_mv = !(nrigid && sp.rigid_mode() != 2);
     if ((what & P2G_MASS) && take_mv) atomicAdd(&g.nv[node].w, wf * m);
     double dxn[3] = {0, 0, 0}; // x_I - x_p (APIC family)
     if (affine) {
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(128) k_g2p(SolidDev s, GridDev g, StepParams s
     if (sp.temp) Tp += wf * ru.w;
     (void)wfd0; (void)wfd1; (void)wfd2;
   })
-  if (sp.rigid_mode == 2) a[0] = a[1] = a[2] = 0.0; // rigid particles: Solid::compute_particle_acceleration leaves a = 0 (src/solid.cpp:767-784)
+  if (sp.rigid_mode() == 2) a[0] = a[1] = a[2] = 0.0; // rigid particles: Solid::compute_particle_acceleration leaves a = 0 (src/solid.cpp:767-784)
   particle_advance<TL>(s, sp, ip, vu, a, Tp);
 }
 
@@ -582,6 +585,46 @@ __global__ void k_fix_velocity_nodes(GridDev g, int groupbit, int set_mask, doub
       if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
     }
   }
+}
+// FixVelocityParticles, src/fix_velocity_particles.cpp:131-300 (particle-independent values).  xold: the positions at the start of the
+// step - UL keeps them in x until the next weight evaluation (G2P writes xn), TL remembers them in the otherwise unused xn.
+__global__ void k_fix_velocity_particles(SolidDev s, int groupbit, int set_mask, double v0, double v1, double v2, int which, int is_TL, double dt, double *ftot) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double f[3] = {0, 0, 0};
+  if (ip < s.np && (s.mask[ip] & groupbit)) {
+    const double v[3] = {v0, v1, v2};
+    if (which == 0) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) { if (is_TL) s.xn[d][ip] = s.x[d][ip]; if (set_mask & (1 << d)) s.v[d][ip] = v[d]; }
+    } else {
+      const double c = (1.0 / dt) * s.mass[ip];
+#pragma unroll
+      for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) {
+        f[d] = c * (v[d] - s.v[d][ip]); s.v[d][ip] = v[d];
+        if (is_TL) s.x[d][ip] = s.xn[d][ip] + dt * v[d]; else s.xn[d][ip] = s.x[d][ip] + dt * v[d];
+      }
+    }
+  }
+  if (which == 1) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double x = f[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
+    }
+  }
+}
+// FixTemperatureNodes, src/fix_temperature_nodes.cpp:74-146
+__global__ void k_fix_temperature_nodes(GridDev g, int groupbit, double T, double Tprev, int which) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nn || !(g.mask[i] & groupbit)) return;
+  if (which == 0) { g.nvu[i].w = T; g.T[i] = Tprev; } else g.T[i] = T;
+}
+// FixTemperatureParticles, src/fix_temperature_particles.cpp:92-181 (particle-independent value)
+__global__ void k_fix_temperature_particles(SolidDev s, int groupbit, double T) {
+  long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip < s.np && (s.mask[ip] & groupbit)) s.T[ip] = T;
 }
 // FixBodyforce, src/fix_body_force.cpp:106-180
 __global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f0, double f1, double f2, double *ftot) {

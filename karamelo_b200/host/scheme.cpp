@@ -2,6 +2,7 @@
 // the fix / compute commands that sit between stages, run commands and log/dump output.
 #include <algorithm>
 #include "sim.h"
+#include <cctype>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -49,6 +50,21 @@ static inline void publish_particle(Sim &s, const double *x, const std::array<do
   s.input.vars["x"] = Var("x", x[0]); s.input.vars["y"] = Var("y", x[1]); s.input.vars["z"] = Var("z", x[2]);
   s.input.vars["x0"] = Var("x0", x0[0]); s.input.vars["y0"] = Var("y0", x0[1]); s.input.vars["z0"] = Var("z0", x0[2]);
 }
+// does the expression mention x, y, z, x0, y0 or z0 as a whole word?  (Expressions that do not can be evaluated once per step and
+// applied by a device kernel; the others are evaluated per particle on the host, like the reference does for every particle.)
+static bool particle_dependent(const Var &v) {
+  if (v.is_constant()) return false;
+  const std::string &e = v.eq();
+  for (size_t i = 0; i < e.size();) {
+    if (std::isalpha((unsigned char)e[i]) || e[i] == '_') {
+      size_t j = i; while (j < e.size() && (std::isalnum((unsigned char)e[j]) || e[j] == '_')) j++;
+      const std::string w = e.substr(i, j - i);
+      if (w == "x" || w == "y" || w == "z" || w == "x0" || w == "y0" || w == "z0") return true;
+      i = j;
+    } else i++;
+  }
+  return false;
+}
 template <class F> static void for_group_solids(Sim &s, int igroup, F f) { // "solid == -1: every solid" loops of the reference's fixes
   const int solid = s.gsolid[igroup];
   for (size_t is = 0; is < s.solids.size(); is++) if (solid == -1 || (int)is == solid) f(*s.solids[is]);
@@ -61,7 +77,15 @@ template <class F> static void for_group_solids(Sim &s, int igroup, F f) { // "s
 struct FixVelocityParticles : Fix {
   bool set[3] = {false, false, false}; Var val[3], prev[3];
   std::vector<std::vector<double>> xold; // per solid, rows [np][3]
+  bool on_device() const { for (int d = 0; d < 3; d++) if (set[d] && (particle_dependent(val[d]) || particle_dependent(prev[d]))) return false; return true; }
+  int dev_solid(Sim &s) const { return s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev; }
   void initial_integrate(Sim &s) override {
+    if (on_device()) { // kernel path: the values are the same for every particle of the group
+      double v[3] = {0, 0, 0}, vp[3] = {0, 0, 0}; int m = 0;
+      for (int d = 0; d < 3; d++) if (set[d]) { m |= 1 << d; v[d] = val[d].result(&s.input); vp[d] = prev[d].result(&s.input); }
+      s.check(kml_fix_velocity_particles(s.ctx, dev_solid(s), groupbit, m, v, vp, 0, nullptr));
+      return;
+    }
     xold.assign(s.solids.size(), {});
     const int solid = s.gsolid[igroup];
     for (size_t is = 0; is < s.solids.size(); is++) {
@@ -81,6 +105,13 @@ struct FixVelocityParticles : Fix {
   }
   void post_advance_particles(Sim &s) override {
     double ftot[3] = {0, 0, 0}; const double inv_dt = 1.0 / s.dt;
+    if (on_device()) {
+      double v[3] = {0, 0, 0}; int m = 0;
+      for (int d = 0; d < 3; d++) if (set[d]) { m |= 1 << d; v[d] = val[d].result(&s.input); }
+      s.check(kml_fix_velocity_particles(s.ctx, dev_solid(s), groupbit, m, v, v, 1, ftot));
+      s.input.vars[id + "_x"] = Var(id + "_x", ftot[0]); s.input.vars[id + "_y"] = Var(id + "_y", ftot[1]); s.input.vars[id + "_z"] = Var(id + "_z", ftot[2]);
+      return;
+    }
     const int solid = s.gsolid[igroup];
     for (size_t is = 0; is < s.solids.size(); is++) {
       if (solid != -1 && (int)is != solid) continue;
@@ -112,6 +143,10 @@ struct FixVelocityParticles : Fix {
 struct FixTemperatureParticles : Fix {
   Var val, prev;
   void apply(Sim &s, Var &e) {
+    if (!particle_dependent(e)) { // kernel path
+      s.check(kml_fix_temperature_particles(s.ctx, s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev, groupbit, e.result(&s.input)));
+      return;
+    }
     for_group_solids(s, igroup, [&](SolidH &S) {
       std::vector<double> x(3 * S.np), T(S.np);
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_T, T.data()));
@@ -164,23 +199,12 @@ template <class F> static void for_group_grids(Sim &s, int igroup, F f) {
 // T = T(t) after the MUSL re-projection
 struct FixTemperatureNodes : Fix {
   Var val, prev;
+  int dev_solid(Sim &s) const { return s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev; }
   void post_update_grid_state(Sim &s) override {
-    const double T = val.result(&s.input), Told = prev.result(&s.input);
-    for_group_grids(s, igroup, [&](GridH &g) {
-      std::vector<double> Tn(g.nnodes), Tu(g.nnodes);
-      s.check(kml_grid_download(s.ctx, g.id, KML_N_T, Tn.data())); s.check(kml_grid_download(s.ctx, g.id, KML_N_T_UPDATE, Tu.data()));
-      for (int64_t i = 0; i < g.nnodes; i++) if (g.mask[i] & groupbit) { Tu[i] = T; Tn[i] = Told; }
-      s.check(kml_grid_upload(s.ctx, g.id, KML_N_T, Tn.data())); s.check(kml_grid_upload(s.ctx, g.id, KML_N_T_UPDATE, Tu.data()));
-    });
+    s.check(kml_fix_temperature_nodes(s.ctx, dev_solid(s), groupbit, val.result(&s.input), prev.result(&s.input), 0));
   }
   void post_velocities_to_grid(Sim &s) override {
-    const double T = val.result(&s.input);
-    for_group_grids(s, igroup, [&](GridH &g) {
-      std::vector<double> Tn(g.nnodes);
-      s.check(kml_grid_download(s.ctx, g.id, KML_N_T, Tn.data()));
-      for (int64_t i = 0; i < g.nnodes; i++) if (g.mask[i] & groupbit) Tn[i] = T;
-      s.check(kml_grid_upload(s.ctx, g.id, KML_N_T, Tn.data()));
-    });
+    s.check(kml_fix_temperature_nodes(s.ctx, dev_solid(s), groupbit, val.result(&s.input), 0.0, 1));
   }
 };
 

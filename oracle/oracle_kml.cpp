@@ -147,7 +147,7 @@ struct OGrid {
 struct OSolid {
   int64_t np; int grid; kml_material mat;
   std::vector<int64_t> ptag;
-  std::vector<Vec3> x, x0, v, v_update, a, mbp, f, q;
+  std::vector<Vec3> x, x0, v, v_update, a, mbp, f, q, xold;
   std::vector<Mat3> sigma, strain_el, vol0PK1, L, F, R, D, Finv, Fdot;
   std::vector<double> J, vol0, vol, rho0, rho, mass, eps, epsdot, damage, damage_init, ienergy, T, gamma;
   std::vector<int> mask;
@@ -1147,6 +1147,43 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
   return 0;
 }
 // FixBodyforce::post_particles_to_grid with constant components, reference src/fix_body_force.cpp:106-180
+// FixVelocityParticles::initial_integrate / post_advance_particles, reference src/fix_velocity_particles.cpp:131-300 (particle-independent values)
+int kml_fix_velocity_particles(kml_ctx *c, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which, double ftot[3]) {
+  const double inv_dt = 1.0 / c->dt;
+  if (which == 1 && ftot) ftot[0] = ftot[1] = ftot[2] = 0;
+  for (size_t is = 0; is < c->solids.size(); is++) {
+    if (solid != -1 && (int)is != solid) continue;
+    OSolid *s = c->solids[is];
+    if (which == 0) s->xold = s->x;
+    for (int64_t ip = 0; ip < s->np; ip++) {
+      if (!(s->mask[ip] & groupbit)) continue;
+      if (which == 0) { for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { s->v_update[ip][d] = v[d]; s->v[ip][d] = vprev[d]; } }
+      else {
+        Vec3 Dv; Dv.setZero();
+        for (int d = 0; d < 3; d++) if (set_mask & (1 << d)) { Dv[d] = v[d] - s->v[ip][d]; s->v[ip][d] = v[d]; s->x[ip][d] = s->xold[ip][d] + c->dt * v[d]; }
+        if (ftot) for (int d = 0; d < 3; d++) ftot[d] += (inv_dt * s->mass[ip]) * Dv[d];
+      }
+    }
+  }
+  return 0;
+}
+// FixTemperatureNodes, reference src/fix_temperature_nodes.cpp:74-146
+int kml_fix_temperature_nodes(kml_ctx *c, int solid, int groupbit, double T, double Tprev, int which) {
+  auto apply = [&](OGrid *g) {
+    for (int64_t i = 0; i < g->nn; i++) if (g->mask[i] & groupbit) { if (which == 0) { g->T_update[i] = T; g->T[i] = Tprev; } else g->T[i] = T; }
+  };
+  if (solid == -1) { for (OSolid *s : c->solids) apply(c->grids[s->grid]); } else apply(c->grids[c->solids[solid]->grid]);
+  return 0;
+}
+// FixTemperatureParticles, reference src/fix_temperature_particles.cpp:92-181 (particle-independent value)
+int kml_fix_temperature_particles(kml_ctx *c, int solid, int groupbit, double T) {
+  for (size_t is = 0; is < c->solids.size(); is++) {
+    if (solid != -1 && (int)is != solid) continue;
+    OSolid *s = c->solids[is];
+    for (int64_t ip = 0; ip < s->np; ip++) if (s->mask[ip] & groupbit) s->T[ip] = T;
+  }
+  return 0;
+}
 int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const double fv[3], double ftot[3]) {
   Vec3 ft; ft.setZero();
   auto apply = [&](OGrid *g) {

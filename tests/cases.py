@@ -347,6 +347,10 @@ def driven_tool():
         "fix(vtool, velocity_particles, gBall2, -v*(0.5+time), -v)")
 
 
+def driven_tool_nonuniform():  # the same fix with a particle-dependent value: evaluated per particle on the host, not by the kernel
+    return driven_tool().replace("-v*(0.5+time), -v)", "-v*(0.5+time), -v*(1+0.5*x0))")
+
+
 def prestressed_disks():
     return two_disks("musl", method="method(ulmpm, FLIP, linear, 0.99)") + """
 fix(s0, initial_stress, gBall1, 0.5, -0.25+x0, NULL, NULL, NULL, 0.125)
@@ -410,4 +414,5 @@ CASES = {
     "x_fix_velocity_particles": (driven_tool(), False, False, 100),
     "x_fix_initial_stress_velocity_nodes": (prestressed_disks(), False, False, 100),
     "x_fix_temperature": (heated_bar(), True, True, 100),
+    "x_fix_velocity_particles_x0": (driven_tool_nonuniform(), False, False, 100),
 }
