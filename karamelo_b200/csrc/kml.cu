@@ -130,7 +130,6 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (cfg->is_CPDI && cfg->dimension != 2) return fail("Error: ULCPDI is only 2D....\n"); // src/ulcpdi.cpp:115-118, src/tlcpdi.cpp:102-104
   if (cfg->is_CPDI && (cfg->axisymmetric || cfg->temp)) return fail("kml: CPDI with axisymmetry / thermo-mechanical coupling is not implemented in the CUDA engine");
   if (cfg->ge && (cfg->is_TL || cfg->is_CPDI)) return fail("kml: gradient-enhanced projection is implemented for ulmpm only in the CUDA engine");
-  if (cfg->ge && cfg->nranks > 1) return fail("kml: gradient-enhanced projection is single-GPU in the CUDA engine (the stored velocity gradient is not migrated)");
   const bool apic_ = cfg->is_TL ? cfg->sub_method == KML_SUB_APIC
                                 : (cfg->sub_method == KML_SUB_APIC || cfg->sub_method == KML_SUB_MLS || cfg->sub_method == KML_SUB_AFLIP || cfg->sub_method == KML_SUB_ASFLIP);
   if (cfg->is_TL && cfg->sub_method != KML_SUB_PIC && cfg->sub_method != KML_SUB_FLIP && cfg->sub_method != KML_SUB_APIC)
@@ -139,7 +138,6 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
     if (cfg->is_CPDI) return fail("kml: APIC with CPDI is not implemented in the CUDA engine");
     if (cfg->shape_function == KML_SHAPE_BERNSTEIN) return fail("Shape function not supported for APIC.");
     if (cfg->shape_function == KML_SHAPE_LINEAR && !cfg->is_TL) return fail("Shape function not supported for APIC and ULMPM.");
-    if (cfg->nranks > 1) return fail("kml: the APIC family is single-GPU in the CUDA engine (the stored velocity gradient is not migrated)");
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("kml: no CUDA device available - the engine has no CPU fallback");
@@ -767,7 +765,7 @@ int kml_exchange_particles(kml_ctx *c) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid]; SolidDev &s = S->s;
     if (S->moved) { for (int k = 0; k < 3; k++) std::swap(s.x[k], s.xn[k]); S->moved = false; }
-    const int narr = SOLID_NDBL_UL;
+    const int narr = SOLID_NDBL_UL + (s.Lst[0] ? 9 : 0); // the stored velocity gradient of the APIC family / gradient-enhanced projection follows the UL block
     const int cap_mig = (int)std::min<long long>(std::max<long long>(s.np / 8, 1024), 1 << 24);
     if (cap_mig > cm.mig_cap) {
       cudaFree(cm.mig_list); cudaFree(cm.mig_send); cudaFree(cm.mig_recv); cudaFree(cm.mig_flag);

@@ -54,6 +54,8 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
 
   const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
   const double h = g.h, ih = g.inv_cellsize;
+  unsigned tile_s = smem_addr(tile2);
+  asm volatile("" : "+r"(tile_s)); // opaque: otherwise the window base is rematerialised (S2R + LEA) at the top of every particle
   while (ip >= 0) {
     // next particle of this thread
     const int pn = p + THREADS;
@@ -75,10 +77,10 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const double gxy = wx[a] * wy[b];
-        const double *row = tile2 + ((size_t)(a * 4 + b) * TLEN + koff) * 6;
+        const unsigned row = tile_s + (unsigned)(((a * 4 + b) * TLEN + koff) * 48); // explicit shared-space address (see smem_addr)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          const double2 r01 = *(const double2 *)(row + 6 * c), r23 = *(const double2 *)(row + 6 * c + 2), r45 = *(const double2 *)(row + 6 * c + 4);
+          const double2 r01 = lds_d2(row + 48 * c), r23 = lds_d2(row + 48 * c + 16), r45 = lds_d2(row + 48 * c + 32);
           const double wf = gxy * wz[c];
           vu[0] = fma(wf, r01.x, vu[0]); vu[1] = fma(wf, r01.y, vu[1]); vu[2] = fma(wf, r23.x, vu[2]);
           acc[0] = fma(wf, r23.y, acc[0]); acc[1] = fma(wf, r45.x, acc[1]); acc[2] = fma(wf, r45.y, acc[2]);

@@ -17,6 +17,17 @@
 
 namespace kml {
 
+// Shared-memory loads through an explicit 32-bit shared-space address.  A generic pointer into __shared__ makes the compiler rebuild the
+// shared window base (S2R SR_CgaCtaId + LEA) in front of the loads - inside the particle loop when registers are tight, where that S2R
+// sits on the critical path of every iteration.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds_d2(unsigned addr) {
+  double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ double lds_d1(unsigned addr) {
+  double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
+}
+
 // the four cubic B-spline pieces of an interior stencil (ntype 0 everywhere): node a sees r in [1-a, 2-a)
 __device__ __forceinline__ void cubic_piece(int a, double r, double ih, double &w, double &dw) {
   if (a == 0) { w = ((-1.0 / 6.0 * r + 1) * r - 2) * r + 4.0 / 3.0; dw = ih * ((-0.5 * r + 2) * r - 2); }
@@ -162,20 +173,23 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
 
   // register copy of one staged record, as this lane needs it
   struct RecR { double2 X, Y[NB], Z01, Z23, D01, D23, MM, MV, A01, A23, A45; };
-  auto rec_load = [&](RecR &R, const double *r) {
+  const unsigned rec0s = smem_addr(rec0);              // the group's records as a shared-space address
+  const unsigned offx = FULL ? 16u * a : 8u * a;       // byte offsets of this lane's x / y weights inside a record
+  const unsigned offy = FULL ? 64u + 16u * b0 : 32u + 8u * b0;
+  auto rec_load = [&](RecR &R, unsigned r) { // r: shared-space byte address of the record
     if (FULL) {
-      R.X = *(const double2 *)(r + 2 * a);
+      R.X = lds_d2(r + offx);
 #pragma unroll
-      for (int e = 0; e < NB; e++) R.Y[e] = *(const double2 *)(r + 8 + 2 * (b0 + e));
-      R.Z01 = *(const double2 *)(r + 16); R.Z23 = *(const double2 *)(r + 18); R.D01 = *(const double2 *)(r + 20); R.D23 = *(const double2 *)(r + 22);
-      R.MM = *(const double2 *)(r + 24); R.MV = *(const double2 *)(r + 26);
-      R.A01 = *(const double2 *)(r + 28); R.A23 = *(const double2 *)(r + 30); R.A45 = *(const double2 *)(r + 32);
+      for (int e = 0; e < NB; e++) R.Y[e] = lds_d2(r + offy + 16u * e);
+      R.Z01 = lds_d2(r + 128); R.Z23 = lds_d2(r + 144); R.D01 = lds_d2(r + 160); R.D23 = lds_d2(r + 176);
+      R.MM = lds_d2(r + 192); R.MV = lds_d2(r + 208);
+      R.A01 = lds_d2(r + 224); R.A23 = lds_d2(r + 240); R.A45 = lds_d2(r + 256);
     } else {
-      R.X.x = r[a];
+      R.X.x = lds_d1(r + offx);
 #pragma unroll
-      for (int e = 0; e < NB; e++) R.Y[e].x = r[4 + b0 + e];
-      R.Z01 = *(const double2 *)(r + 8); R.Z23 = *(const double2 *)(r + 10);
-      R.MM = *(const double2 *)(r + 12); R.MV.x = r[14];
+      for (int e = 0; e < NB; e++) R.Y[e].x = lds_d1(r + offy + 8u * e);
+      R.Z01 = lds_d2(r + 64); R.Z23 = lds_d2(r + 80);
+      R.MM = lds_d2(r + 96); R.MV.x = lds_d1(r + 112);
     }
   };
   auto rec_accumulate = [&](const RecR &R) {
@@ -232,7 +246,7 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
       dirty = 0xF;
     };
     for (int q = 0; q < n; q++) {
-      RecR cur; rec_load(cur, rec0 + q * REC);
+      RecR cur; rec_load(cur, rec0s + (unsigned)(q * REC * 8));
       boundary(q); rec_accumulate(cur);
     }
     __syncwarp(gmask);

@@ -77,6 +77,10 @@ def step(args):
     assert torch.cuda.is_available()
     cells = tuple(args.cells)
     script = block(cells, args.scheme, args.shape, a=args.a, drift=args.drift)
+    if args.method:  # e.g. "APIC, cubic-spline" or "FLIP, cubic-spline, 0.99, mechanical, gradient-enhanced"
+        line = [ln for ln in script.splitlines() if ln.startswith("method(ulmpm")]
+        assert len(line) == 1, line
+        script = script.replace(line[0], "method(ulmpm, %s)" % args.method)
     fields = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "VOL")
     eng = slab.make_engine(None)
     eng.script(script)
@@ -115,6 +119,7 @@ if __name__ == "__main__":
     ap.add_argument("--scheme", default="musl")
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--drift", type=float, default=0.0)
+    ap.add_argument("--method", default="", help="arguments of method(ulmpm, ...) replacing the block's FLIP cubic-spline default")
     ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
     a = ap.parse_args()
     try:

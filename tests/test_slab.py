@@ -62,6 +62,15 @@ def test_two_slabs_match_single_rank_oracle(oracle_lib, scheme, drift):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", ["APIC, cubic-spline", "MLS, quadratic-spline", "FLIP, cubic-spline, 0.99, mechanical, gradient-enhanced"])
+def test_two_slabs_affine_transfer(oracle_lib, method):
+    """APIC family / gradient-enhanced projection over two slabs: the stored velocity gradient migrates with the particle."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    print(launch(2, ["step", "--cells", "12", "6", "6", "--scheme", "musl", "--drift", "0.03", "--steps", "100", "--a", "2.5e-3", "--method", method]))
+
+
+@pytest.mark.gpu
 def test_four_slabs_match_single_rank_oracle(oracle_lib):
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
