@@ -1,0 +1,51 @@
+// fp64_peak.cu - measured DFMA issue rate of one B200 (the FP64 roof of DESIGN.md section 3).
+// Every thread runs ILP independent DFMA chains; blocks fill every SM with WARPS warps per sub-partition.
+// Prints DFMA per clock per SM (from the SM clock the kernel itself reads) and T DFMA/s.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o karamelo_b200/lib/fp64_peak tools/fp64_peak.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int ILP>
+__global__ void k_dfma(double *out, int iters, long long *clocks) {
+  double a[ILP], x = 1.0000001 + threadIdx.x * 1e-9, y = 0.9999999;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) a[i] = i + threadIdx.x;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) a[i] = fma(a[i], x, y);
+  }
+  long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += a[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+}
+
+template <int ILP> void run(int nsm, int threads, int blocks_per_sm, int iters) {
+  const int nb = nsm * blocks_per_sm;
+  double *out; long long *clk; cudaMalloc(&out, sizeof(double) * nb * threads); cudaMalloc(&clk, sizeof(long long) * nb);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma<ILP><<<nb, threads>>>(out, iters / 8, clk); cudaDeviceSynchronize();
+  cudaEventRecord(e0); k_dfma<ILP><<<nb, threads>>>(out, iters, clk); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  long long *h = new long long[nb]; cudaMemcpy(h, clk, sizeof(long long) * nb, cudaMemcpyDeviceToHost);
+  double cavg = 0; for (int i = 0; i < nb; i++) cavg += h[i]; cavg /= nb;
+  const double dfma = (double)nb * threads * ILP * iters;
+  printf("ILP %2d threads/block %4d blocks/SM %d: %.2f DFMA/clk/SM (block clocks), %.2f T DFMA/s (events, %.3f ms)\n", ILP, threads, blocks_per_sm,
+         (double)threads * blocks_per_sm * ILP * iters / cavg, dfma / (ms * 1e-3) * 1e-12, ms);
+  delete[] h; cudaFree(out); cudaFree(clk);
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  printf("%s: %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+  const int nsm = p.multiProcessorCount, iters = 1 << 15;
+  run<8>(nsm, 128, 1, iters);   // 1 warp per sub-partition
+  run<8>(nsm, 128, 3, iters);   // 3 warps per sub-partition (the occupancy of k_p2g_cell3)
+  run<8>(nsm, 256, 4, iters);   // 8 warps per sub-partition
+  run<16>(nsm, 128, 3, iters);
+  run<2>(nsm, 1024, 2, iters);  // 16 warps per sub-partition, little ILP
+  return 0;
+}
