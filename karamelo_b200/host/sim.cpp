@@ -296,6 +296,8 @@ Var Sim::cmd_dimension(std::vector<std::string> &a) {
   if (dim == 3) { boxlo[2] = input.parsev(a[++m]); boxhi[2] = input.parsev(a[++m]); }
   double cs = 0;
   if (!is_TL) { cs = input.parsev(a[++m]); if (cs < 0) fatal("Error: cellsize negative!\n"); }
+  // Universe::set_proc_grid stops every 1-D run (src/universe.cpp:645-647); the engine's 1-D kernels stay reachable through the C ABI
+  if (dim == 1) fatal("New partitioning not supported for dimensions 1 yet!\n");
   for (int d = 0; d < 3; d++) {
     if (d < dim) { double h = (boxhi[d] - boxlo[d]) / 1; sublo[d] = 0 * h + boxlo[d]; subhi[d] = sublo[d] + h; }
     else sublo[d] = subhi[d] = 0;
