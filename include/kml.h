@@ -256,7 +256,7 @@ int kml_compute_strain_energy(kml_ctx *ctx, int solid, int groupbit, double *es)
 /* Device error word, the invariants of SURVEY section 4: bit0 particle left the domain
  * (src/solid.cpp:617-627), bit1 J <= 0 (src/solid.cpp:1208-1215), bit2 dtCFL NaN/0
  * (src/ulmpm.cpp:535-544), bit3 polar decomposition failed (src/solid.cpp:1229-1236). */
-int kml_error_flags(kml_ctx *ctx, unsigned *flags);
+int kml_error_flags(kml_ctx *ctx, unsigned *flags); /* on a decomposed run: collective (call on every rank), returns the union */
 
 /* ---- slab decomposition over several GPUs (replaces Grid::reduce_ghost_nodes
  *      src/grid.cpp:477-621,881-1132 and ULMPM::exchange_particles) ------------------------ */

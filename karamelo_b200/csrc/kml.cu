@@ -964,8 +964,9 @@ static int energy(kml_ctx *c, int solid, int groupbit, int kinetic, double *out)
 int kml_compute_kinetic_energy(kml_ctx *c, int solid, int groupbit, double *ek) { return energy(c, solid, groupbit, 1, ek); }
 int kml_compute_strain_energy(kml_ctx *c, int solid, int groupbit, double *es) { return energy(c, solid, groupbit, 0, es); }
 
-int kml_error_flags(kml_ctx *c, unsigned *flags) {
+int kml_error_flags(kml_ctx *c, unsigned *flags) { // collective on a decomposed run: every rank sees every rank's bits
   CU(cudaSetDevice(c->dev));
+  if (c->comm.nranks > 1) NC(nccl().AllReduce(c->d_flags, c->d_flags, 1, ncclUint32, ncclMax, c->comm.comm, c->stream));
   CU(cudaMemcpyAsync(c->h_pinned + 48, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   memcpy(flags, c->h_pinned + 48, sizeof(unsigned)); return 0;

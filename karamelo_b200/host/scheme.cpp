@@ -664,6 +664,10 @@ void Sim::run(Var condition) {
     check(kml_exchange_particles(ctx));
     atime += (ntimestep - atimestep) * dt; atimestep = ntimestep; input.vars["time"] = Var("time", atime); // Update::update_time
     if (!dt_constant) { check(kml_adjust_dt(ctx, dt_factor, &dt)); input.vars["dt"] = Var("dt", dt); }       // Method::adjust_dt
+    else { // set_dt: adjust_dt (which returns the device error word) is skipped, so ask for it - the reference stops inside the failing step
+      unsigned fl = 0; check(kml_error_flags(ctx, &fl));
+      if (fl) fatal("device error flags set: " + std::to_string(fl) + " (bit0 particle left the domain, bit1 J<=0, bit2 dtCFL invalid, bit3 polar decomposition failed)\n");
+    }
     hooks(FINAL_INTEGRATE);
     if (maxtime != -1 && atime > maxtime) { nsteps = ntimestep; output_write(ntimestep); break; }
     bool due = ntimestep == next_log || ntimestep == nsteps;
