@@ -181,6 +181,10 @@ int kml_solid_create(kml_ctx *ctx, const kml_solid_desc *desc, int *solid_id);
 int kml_solid_np(kml_ctx *ctx, int solid_id, int64_t *np);
 int kml_solid_upload(kml_ctx *ctx, int solid_id, int field, const void *src);
 int kml_solid_download(kml_ctx *ctx, int solid_id, int field, void *dst);
+/* DeleteParticles::command, src/delete_particles.cpp:51-80: dlist[np] flags the particles to remove.  For k ascending a flagged particle
+ * is overwritten by the solid's last particle (Solid::copy_particle(np - 1, k), src/solid.cpp:1555-1589) and np shrinks by one; the
+ * particle moved in is examined next - the surviving particles end up in exactly the reference's order. */
+int kml_solid_delete_particles(kml_ctx *ctx, int solid_id, const int *dlist);
 /* Device-resident state for callers that generate particles on the GPU
  * (synthetic blocks): device pointer of the SoA component `comp` of `field`. */
 int kml_solid_device_ptr(kml_ctx *ctx, int solid_id, int field, int comp, void **dptr);

@@ -121,6 +121,21 @@ int stage_reserve(kml_ctx *c, size_t bytes) {
 }
 } // namespace
 
+namespace {
+// the source index of every surviving slot after the reference's swap-with-last compaction (src/delete_particles.cpp:56-66)
+std::vector<int> delete_order(const int *dlist, long long np) {
+  std::vector<int> src(np), dl(dlist, dlist + np);
+  for (long long i = 0; i < np; i++) src[i] = (int)i;
+  long long n = np, k = 0;
+  while (k < n) { if (dl[k]) { src[k] = src[n - 1]; dl[k] = dl[n - 1]; n--; } else k++; }
+  src.resize(n); return src;
+}
+template <class T> __global__ void k_gather_rows(T *dst, const T *src, const int *idx, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+} // namespace
+
 extern "C" {
 
 const char *kml_last_error(void) { return g_err.c_str(); }
@@ -443,6 +458,38 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
   CU(cudaMemcpyAsync(dst, c->d_stage, sizeof(double) * np * ncols, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid]; const long long np = S->s.np;
+  if (c->c.is_CPDI) return fail("kml: delete_particles with CPDI is not supported (the reference does not move the particle domains either, src/solid.cpp:1590-1610)");
+  if (c->c.nranks > 1) return fail("kml: delete_particles is a single-GPU set-up command in the CUDA engine");
+  if (!c->c.is_TL && S->moved) { for (int k = 0; k < 3; k++) std::swap(S->s.x[k], S->s.xn[k]); S->moved = false; }
+  const std::vector<int> src = delete_order(dlist, np); const long long n = (long long)src.size();
+  if (n == np) return 0;
+  int *d_idx = nullptr;
+  CU(cudaMalloc(&d_idx, sizeof(int) * std::max<long long>(n, 1)));
+  CU(cudaMemcpyAsync(d_idx, src.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  if (stage_reserve(c, sizeof(double) * std::max<long long>(n, 1))) { cudaFree(d_idx); return 1; }
+  const int nd = (c->c.is_TL ? SOLID_NDBL_TL : SOLID_NDBL_UL) + ((c->apic || c->c.ge) ? 9 : 0);
+  if (n > 0) {
+    for (int a = 0; a < nd; a++) { // every double array of the solid, then tag and mask
+      double *arr = S->buf + (size_t)a * S->cap;
+      k_gather_rows<double><<<nblocks(n, 256), 256, 0, c->stream>>>((double *)c->d_stage, arr, d_idx, n);
+      CU(cudaMemcpyAsync(arr, c->d_stage, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    k_gather_rows<long long><<<nblocks(n, 256), 256, 0, c->stream>>>((long long *)c->d_stage, S->s.ptag, d_idx, n);
+    CU(cudaMemcpyAsync(S->s.ptag, c->d_stage, sizeof(long long) * n, cudaMemcpyDeviceToDevice, c->stream));
+    k_gather_rows<int><<<nblocks(n, 256), 256, 0, c->stream>>>((int *)c->d_stage, S->s.mask, d_idx, n);
+    CU(cudaMemcpyAsync(S->s.mask, c->d_stage, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const int rc = check_launch("k_gather_rows");
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_idx);
+  S->s.np = n; S->d.np = n;
+  c->tl_mass_done = false; // TL: node masses are computed once from the particle set (update_mass_nodes, src/tlmpm.cpp:345-351)
+  return rc;
 }
 
 int kml_solid_device_ptr(kml_ctx *c, int sid, int field, int comp_idx, void **dptr) {

@@ -150,6 +150,34 @@ void Sim::register_commands() {
     }
     return Var(0);
   };
+  // DeleteParticles (src/delete_particles.cpp:30-113): delete_particles(solid | all, region, region-ID) removes the particles whose
+  // REFERENCE position lies in the region; survivors keep the reference's swap-with-last order (kml_solid_delete_particles)
+  c["delete_particles"] = [this](std::vector<std::string> &a) -> Var {
+    if (a.size() < 3) fatal("Error: not enough arguments.\nUsage: delete_particles(solid-ID, region, region-ID)\n");
+    const int isolid = find_solid(a[0]);
+    if (isolid < 0 && a[0] != "all") fatal("Error: solid " + a[0] + " unknown.\n");
+    if (a[1] != "region") fatal("Error: use of illegal keyword for delete_particles command: " + a[1] + "\n");
+    const int ir = find_region(a[2]);
+    if (ir < 0) fatal("Error: region " + a[2] + " unknown.\n");
+    for (size_t is = 0; is < solids.size(); is++) {
+      if (isolid >= 0 && (int)is != isolid) continue;
+      SolidH &S = *solids[is];
+      std::vector<int> dl(S.np);
+      for (int64_t ip = 0; ip < S.np; ip++) dl[ip] = regions[ir]->inside(S.x0[ip][0], S.x0[ip][1], S.x0[ip][2]) == 1;
+      check(kml_solid_delete_particles(ctx, S.dev, dl.data()));
+      int64_t n = S.np, k = 0; // the same compaction on the host copies
+      while (k < n) {
+        if (dl[k]) { S.x0[k] = S.x0[n - 1]; S.mask[k] = S.mask[n - 1]; S.ptag[k] = S.ptag[n - 1]; dl[k] = dl[n - 1]; n--; } else k++;
+      }
+      np_total -= S.np - n;
+      S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n);
+      std::vector<double> vol(n), mass(n);
+      check(kml_solid_download(ctx, S.dev, KML_P_VOL, vol.data())); check(kml_solid_download(ctx, S.dev, KML_P_MASS, mass.data()));
+      S.vtot = S.mtot = 0; for (int64_t i = 0; i < n; i++) { S.vtot += vol[i]; S.mtot += mass[i]; }
+      if (!quiet) std::cout << "Solid " << S.id << " new total volume = " << S.vtot << std::endl;
+    }
+    return Var(0);
+  };
   c["plot"] = [](std::vector<std::string> &) { return Var(0); };
   c["save_plot"] = [](std::vector<std::string> &) { return Var(0); };
 }

@@ -339,6 +339,30 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
   }
   return 0;
 }
+// DeleteParticles::command, reference src/delete_particles.cpp:51-80 with Solid::copy_particle (src/solid.cpp:1555-1589)
+int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
+  OSolid *s = c->solids[sid];
+  if (c->c.is_CPDI) return fail("kml: delete_particles with CPDI is not supported (the reference does not move the particle domains either, src/solid.cpp:1590-1610)");
+  std::vector<int> dl(dlist, dlist + s->np);
+  auto copy_particle = [&](int64_t i, int64_t j) {
+    s->ptag[j] = s->ptag[i]; s->x0[j] = s->x0[i]; s->x[j] = s->x[i]; s->v[j] = s->v[i]; s->v_update[j] = s->v_update[i]; s->a[j] = s->a[i];
+    s->mbp[j] = s->mbp[i]; s->f[j] = s->f[i]; s->vol0[j] = s->vol0[i]; s->vol[j] = s->vol[i]; s->rho0[j] = s->rho0[i]; s->rho[j] = s->rho[i];
+    s->mass[j] = s->mass[i]; s->eps[j] = s->eps[i]; s->epsdot[j] = s->epsdot[i]; s->damage[j] = s->damage[i]; s->damage_init[j] = s->damage_init[i];
+    s->T[j] = s->T[i]; s->gamma[j] = s->gamma[i]; s->q[j] = s->q[i];
+    s->ienergy[j] = s->ienergy[i]; s->mask[j] = s->mask[i]; s->sigma[j] = s->sigma[i]; s->strain_el[j] = s->strain_el[i]; s->vol0PK1[j] = s->vol0PK1[i];
+    s->L[j] = s->L[i]; s->F[j] = s->F[i]; s->R[j] = s->R[i]; s->D[j] = s->D[i]; s->Finv[j] = s->Finv[i]; s->Fdot[j] = s->Fdot[i]; s->J[j] = s->J[i];
+  };
+  int64_t n = s->np, k = 0;
+  while (k < n) { if (dl[k]) { copy_particle(n - 1, k); dl[k] = dl[n - 1]; n--; } else k++; }
+  s->np = n; // the reference keeps its vectors at the old length and only lowers np_local; downloads here copy whole vectors, so shrink them
+  s->ptag.resize(n); s->mask.resize(n);
+  for (auto *v : {&s->x, &s->x0, &s->v, &s->v_update, &s->a, &s->mbp, &s->f, &s->q, &s->xold}) if (v->size() > (size_t)n) v->resize(n);
+  for (auto *v : {&s->sigma, &s->strain_el, &s->vol0PK1, &s->L, &s->F, &s->R, &s->D, &s->Finv, &s->Fdot}) v->resize(n);
+  for (auto *v : {&s->J, &s->vol0, &s->vol, &s->rho0, &s->rho, &s->mass, &s->eps, &s->epsdot, &s->damage, &s->damage_init, &s->ienergy, &s->T, &s->gamma}) v->resize(n);
+  s->neigh_pn.resize(n); s->wf_pn.resize(n); s->wfd_pn.resize(n);
+  c->update_mass_nodes = true; c->update_wf = true;
+  return 0;
+}
 int kml_solid_device_ptr(kml_ctx *, int, int, int, void **) { return fail("oracle: no device pointers"); }
 
 int kml_set_dt(kml_ctx *c, double dt) { c->dt = dt; return 0; }

@@ -371,6 +371,14 @@ fix(fTp, temperature_particles, gColdP, Tr-10+x0)
 """
 
 
+# delete_particles (src/delete_particles.cpp): particles removed before the run; the survivors keep the reference's swap-with-last order
+def carved_disks(tl=False):
+    if tl:
+        return bouncing_balls("minimize_penetration") + "region(rCut2, cylinder, -0.16, -0.16, 0.08)\ndelete_particles(sBall1, region, rCut2)\n"
+    return two_disks("musl") + ("region(rCut, block, 0.15, 0.3, INF, 0.25)\ndelete_particles(sBall2, region, rCut)\n"
+                                "region(rCut2, cylinder, -0.2, -0.2, 0.08)\ndelete_particles(all, region, rCut2)\n")
+
+
 # name -> (script, is_TL, thermal, steps)
 CASES = {
     "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
@@ -415,4 +423,6 @@ CASES = {
     "x_fix_initial_stress_velocity_nodes": (prestressed_disks(), False, False, 100),
     "x_fix_temperature": (heated_bar(), True, True, 100),
     "x_fix_velocity_particles_x0": (driven_tool_nonuniform(), False, False, 100),
+    "x_delete_particles_ul": (carved_disks(False), False, False, 100),
+    "x_delete_particles_tl": (carved_disks(True), True, False, 100),
 }

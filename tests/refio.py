@@ -38,25 +38,28 @@ def read_restart_solids(path, nps, is_tl, temp):
     dt = _record_dtype(is_tl, temp)
     out, pos, first_tag = [], 0, 1
     for npart in nps:
-        sig = struct.pack("<qi", npart, npart)
+        # np (bigint) is the solid's size at creation; np_local (int) follows and is smaller after delete_particles, whose swap-with-last
+        # compaction also leaves the tags unordered (src/delete_particles.cpp:56-80) - so: every tag inside the solid's range, none twice
+        sig = struct.pack("<q", npart)
         found = None
         o = buf.find(sig, pos)
         while o != -1:
             hdr = o - 96
             rec0 = hdr + 124
-            end = rec0 + npart * dt.itemsize
-            if hdr >= 0 and end <= len(buf):
+            nloc = struct.unpack_from("<i", buf, o + 8)[0] if o + 12 <= len(buf) else -1
+            end = rec0 + nloc * dt.itemsize
+            if hdr >= 0 and 0 < nloc <= npart and end <= len(buf):
                 nc = struct.unpack_from("<i", buf, o + 12)[0]
-                t0 = struct.unpack_from("<q", buf, rec0)[0]
-                t1 = struct.unpack_from("<q", buf, end - dt.itemsize)[0]
-                if nc in (0, 2, 4, 8) and t0 == first_tag and t1 == first_tag + npart - 1:
-                    found = (hdr, rec0, end)
-                    break
+                if nc in (0, 2, 4, 8):
+                    tags = np.frombuffer(buf, dtype=dt, count=nloc, offset=rec0)["ptag"]
+                    if tags.min() >= first_tag and tags.max() <= first_tag + npart - 1 and len(np.unique(tags)) == nloc and (nloc < npart or (tags[0] == first_tag and tags[-1] == first_tag + npart - 1)):
+                        found = (hdr, rec0, end, nloc)
+                        break
             o = buf.find(sig, o + 1)
         if found is None:
             raise RuntimeError("solid with np=%d (first tag %d) not found in %s" % (npart, first_tag, path))
-        hdr, rec0, end = found
-        rec = np.frombuffer(buf, dtype=dt, count=npart, offset=rec0)
+        hdr, rec0, end, nloc = found
+        rec = np.frombuffer(buf, dtype=dt, count=nloc, offset=rec0)
         d = {k: np.array(rec[k]) for k in dt.names}
         for k in ("sigma", "strain_el", "F", "vol0PK1"):
             if k in d:

@@ -89,3 +89,15 @@ def test_translate_particles_external_force_delete_compute():
     assert rc_r == 0 and rc_o == 0, out_o[-400:]
     same_log(out_r, out_o)
     assert len(files_r) == 2 and files_r == files_o
+
+
+@pytest.mark.parametrize("tl", [False, True])
+def test_delete_particles_keeps_the_reference_order(tl):
+    # src/delete_particles.cpp:51-80: the dump lists the survivors in storage order, so byte-identical dumps pin the compaction order
+    from cases import carved_disks
+    text = carved_disks(tl) + ("compute(Ek, kinetic_energy, all)\nlog_modify(custom, step, dt, time, Ek)\nlog(10)\n"
+                               "dump(d1, all, particle, 25, dump_p.*.LAMMPS, x, y, z, vx, vy, s11, mass)\nrun(50)\n")
+    (rc_r, out_r, files_r), (rc_o, out_o, files_o) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+    assert len(files_r) == 2 and files_r == files_o
