@@ -221,10 +221,10 @@ __global__ void k_grid_positions(GridDev g, double dt) {
 __global__ void k_grid_zero_v(GridDev g, int zero_mass) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
-  double4 rec = g.nv[i];
-  rec.x = rec.y = rec.z = 0.0;
-  if (zero_mass) rec.w = 0.0;
-  g.nv[i] = rec;
+  // write-only: the mass (component w) is left alone instead of being read and written back
+  double *r = (double *)&g.nv[i];
+  *(double2 *)r = make_double2(0.0, 0.0);
+  if (zero_mass) *(double2 *)(r + 2) = make_double2(0.0, 0.0); else r[2] = 0.0;
 }
 
 #endif // KML_MISC_KERNELS
