@@ -170,7 +170,11 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
-  c->gtune.seg_target = std::min(std::max(env_int("KML_SEGLEN", 32), 8), 96);
+  // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
+  auto seg_env = [&](const char *name, int dflt) { return std::min(std::max(env_int(name, env_int("KML_SEGLEN", dflt)), 8), 96); };
+  c->gtune.seg_target = seg_env("KML_SEGLEN_P2G", 32);
+  c->gtune.seg_g2p = seg_env("KML_SEGLEN_G2P", 32);
+  c->gtune.seg_stress = seg_env("KML_SEGLEN_STRESS", 24);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;
   *out = c; return 0;
 }

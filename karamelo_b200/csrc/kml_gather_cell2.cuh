@@ -191,13 +191,18 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
 }
 
 // measurement knobs (environment, see kml.cu): cells per segment and threads per block
-struct GatherTune { int seg_target = 32, threads = 64; };
+struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads = 64; }; // seg_target: P2G / re-projection
 
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
 inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
                               const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
   if (sp.axisymmetric || sp.temp || !cl.valid) return -1;
-  int seglen, nseg; cell_segments(g.n[2], tune.seg_target, &seglen, &nseg);
+  // G2P: segments of (almost) equal length.  Stress: segments of EXACTLY seg_stress cells (the last one shorter) - measured at 100 M
+  // particles: 24 cells 10.6 ms, 15 cells 11.0, 20 cells 12.0, 30 cells (the equalised split of 210 planes) 12.4, 12 cells 13.4; a short
+  // tile leaves more of the SM's 256 KB to L1 for the 55 streamed state arrays, and 24 x 8 particles are 3 per thread on the usual lattice.
+  int seglen, nseg;
+  if (stress) { seglen = tune.seg_stress; nseg = (g.n[2] + seglen - 1) / seglen; }
+  else cell_segments(g.n[2], tune.seg_g2p, &seglen, &nseg);
   const long long nblocks = (long long)g.n[0] * g.n[1] * nseg;
   if (nblocks >= (1ll << 31)) return -1;
   const size_t tile = sizeof(double) * 16 * (size_t)(seglen + 3) * (stress ? 4 : 6);
