@@ -379,6 +379,37 @@ def carved_disks(tl=False):
                                 "region(rCut2, cylinder, -0.2, -0.2, 0.08)\ndelete_particles(all, region, rCut2)\n")
 
 
+# Two elastic spheres colliding in 3-D on one background grid: several solids through the generic 3-D scatter / gather kernels
+# (the cell kernels serve one solid per grid), sphere regions, cubic B-splines
+def two_spheres(scheme="musl", shape="cubic-spline"):
+    return f"""
+E   = 1e+3
+nu  = 0.3
+rho = 1000
+L   = 1
+hL  = 0.5*L
+method(ulmpm, FLIP, {shape}, 0.99)
+scheme({scheme})
+N        = 12
+cellsize = L/N
+dimension(3,-hL, hL, -hL, hL, -hL, hL, cellsize)
+R = 0.17
+c = 0.14
+region(rBall1, sphere, -c, -c, -c, R)
+region(rBall2, sphere,  c,  c,  c, R)
+material(mat1, linear, rho, E, nu)
+ppc1d = 2
+solid(sBall1, region, rBall1, ppc1d, mat1, cellsize,0)
+solid(sBall2, region, rBall2, ppc1d, mat1, cellsize,0)
+group(gBall1, particles, region, rBall1, solid, sBall1)
+group(gBall2, particles, region, rBall2, solid, sBall2)
+v = 0.2
+fix(v0Ball1, initial_velocity_particles, gBall1,  v,  v, 0.8*v)
+fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, -0.8*v)
+dt_factor(0.1)
+"""
+
+
 # name -> (script, is_TL, thermal, steps)
 CASES = {
     "c1_two_disks_usl": (two_disks("usl"), False, False, 100),
@@ -425,4 +456,6 @@ CASES = {
     "x_fix_velocity_particles_x0": (driven_tool_nonuniform(), False, False, 100),
     "x_delete_particles_ul": (carved_disks(False), False, False, 100),
     "x_delete_particles_tl": (carved_disks(True), True, False, 100),
+    "x_two_spheres_3d": (two_spheres(), False, False, 100),
+    "x_tensile_tl_cubic": (tensile(False, shape="cubic-spline"), True, False, 100),
 }
