@@ -457,5 +457,5 @@ CASES = {
     "x_delete_particles_ul": (carved_disks(False), False, False, 100),
     "x_delete_particles_tl": (carved_disks(True), True, False, 100),
     "x_two_spheres_3d": (two_spheres(), False, False, 100),
-    "x_tensile_tl_cubic": (tensile(False, shape="cubic-spline"), True, False, 100),
+    "x_tensile_tl_cubic": (tensile(False, shape="cubic-spline", vgrip=20), True, False, 100),
 }
