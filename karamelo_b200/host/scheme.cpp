@@ -14,6 +14,17 @@ namespace kmlh {
 
 // ------------------------------------------------------------------ fixes -------------------
 namespace {
+// ---- restart files in the reference's binary layout (src/write_restart.cpp and the write_restart members it calls) ----
+template <class T> void rput(std::ostream &os, const T &v) { os.write(reinterpret_cast<const char *>(&v), sizeof(T)); }
+void rput_str(std::ostream &os, const std::string &t) { const size_t n = t.size(); rput(os, n); os.write(t.data(), (std::streamsize)n); }
+void rput_var(std::ostream &os, const Var &v) { // Var::write_to_restart, src/var.cpp:312-319
+  rput_str(os, v.eq()); const double val = v.result(); rput(os, val); const bool c = v.is_constant(); rput(os, c);
+}
+void rput_sets(std::ostream &os, const bool *set, const Var *val, const Var *prev) { // the xset/yset/zset + Var blocks of the node / particle fixes
+  for (int d = 0; d < 3; d++) rput(os, set[d]);
+  for (int d = 0; d < 3; d++) if (set[d]) { rput_var(os, val[d]); if (prev) rput_var(os, prev[d]); }
+}
+
 
 // FixInitialVelocityParticles, reference src/fix_initial_velocity_particles.cpp:36-161.
 // Per-particle expressions are evaluated by the script interpreter exactly as the reference
@@ -75,6 +86,7 @@ template <class F> static void for_group_solids(Sim &s, int igroup, F f) { // "s
 // (The reference also writes v_update at initial_integrate; only Solid::compute_velocity_nodes of a rigid solid reads it,
 // into the scratch copy it keeps in grid->mb, which nothing consumes - src/solid.cpp:366-381, src/grid.cpp:455-461.)
 struct FixVelocityParticles : Fix {
+  void write_restart(std::ostream &os) const override { rput_sets(os, set, val, prev); } // src/fix_velocity_particles.cpp:303-320
   bool set[3] = {false, false, false}; Var val[3], prev[3];
   std::vector<std::vector<double>> xold; // per solid, rows [np][3]
   bool on_device() const { for (int d = 0; d < 3; d++) if (set[d] && (particle_dependent(val[d]) || particle_dependent(prev[d]))) return false; return true; }
@@ -141,6 +153,7 @@ struct FixVelocityParticles : Fix {
 // FixTemperatureParticles, reference src/fix_temperature_particles.cpp:92-181: T = T(t - dt) before the step, T = T(t) after
 // advance_particles
 struct FixTemperatureParticles : Fix {
+  void write_restart(std::ostream &os) const override { rput_var(os, val); rput_var(os, prev); } // src/fix_temperature_particles.cpp:184-187
   Var val, prev;
   void apply(Sim &s, Var &e) {
     if (!particle_dependent(e)) { // kernel path
@@ -198,6 +211,7 @@ template <class F> static void for_group_grids(Sim &s, int igroup, F f) {
 // FixTemperatureNodes, reference src/fix_temperature_nodes.cpp:74-146: T_update = T(t), T = T(t - dt) after the grid update;
 // T = T(t) after the MUSL re-projection
 struct FixTemperatureNodes : Fix {
+  void write_restart(std::ostream &os) const override { rput_var(os, val); rput_var(os, prev); } // src/fix_temperature_nodes.cpp:149-152
   Var val, prev;
   int dev_solid(Sim &s) const { return s.gsolid[igroup] == -1 ? -1 : s.solids[s.gsolid[igroup]]->dev; }
   void post_update_grid_state(Sim &s) override {
@@ -231,6 +245,7 @@ struct FixInitialVelocityNodes : Fix {
 
 // FixVelocityNodes, reference src/fix_velocity_nodes.cpp:36-268
 struct FixVelocityNodes : Fix {
+  void write_restart(std::ostream &os) const override { rput_sets(os, set, val, prev); } // src/fix_velocity_nodes.cpp:270-292
   bool set[3] = {false, false, false}; Var val[3], prev[3];
   void apply(Sim &s, int which) {
     double v[3] = {0, 0, 0}, vp[3] = {0, 0, 0}, ftot[3]; int m = 0;
@@ -244,6 +259,7 @@ struct FixVelocityNodes : Fix {
 
 // FixBodyforce, reference src/fix_body_force.cpp:36-180 (components that do not depend on x0,y0,z0)
 struct FixBodyForce : Fix {
+  void write_restart(std::ostream &os) const override { rput_sets(os, set, val, nullptr); } // src/fix_body_force.cpp:183-195
   bool set[3] = {false, false, false}; Var val[3];
   void post_particles_to_grid(Sim &s) override {
     double f[3] = {0, 0, 0}, ftot[3]; int m = 0;
@@ -256,6 +272,7 @@ struct FixBodyForce : Fix {
 
 // FixForceNodes, reference src/fix_force_nodes.cpp:32-193
 struct FixForceNodes : Fix {
+  void write_restart(std::ostream &os) const override { rput_sets(os, set, val, nullptr); } // src/fix_force_nodes.cpp:196-230
   bool set[3] = {false, false, false}; Var val[3];
   void post_particles_to_grid(Sim &s) override {
     double f[3] = {0, 0, 0}, ftot[3]; int m = 0;
@@ -282,6 +299,7 @@ struct FixEnergy : Fix {
 
 // FixContactHertz / FixContactMinPenetration, reference src/fix_contact_hertz.cpp, src/fix_contact_min_penetration.cpp
 struct FixContact : Fix {
+  void write_restart(std::ostream &os) const override { rput(os, solid1); rput(os, solid2); if (!hertz) rput(os, mu); } // src/fix_contact_hertz.cpp:204-207, src/fix_contact_min_penetration.cpp:261-265
   int solid1 = -1, solid2 = -1; double mu = 0; bool hertz = true;
   void initial_integrate(Sim &s) override {
     double ftot[3];
@@ -438,6 +456,7 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
     f->solid1 = find_solid(a[2]); if (f->solid1 < 0) fatal("Error: solid " + a[2] + " unknown.\n");
     f->solid2 = find_solid(a[3]); if (f->solid2 < 0) fatal("Error: solid " + a[3] + " unknown.\n");
     if (!f->hertz) f->mu = input.parsev(a[4]);
+    f->igroup = find_group(a[2]); // Fix::Fix looks the third argument up as a group (src/fix.cpp:36): a solid name gives -1, and that is what restart files hold
     f->mask = INITIAL_INTEGRATE;
   } else fatal("fix style " + style + " is outside the hot path covered by this build (see DESIGN.md).\n");
   fix->id = a[0]; fix->style = style;
@@ -602,9 +621,112 @@ void Sim::output_setup() { // Output::setup, src/output.cpp:64-126
   else next_log = laststep;
 }
 
+// WriteRestart::write, src/write_restart.cpp:51-88: header, Update, Domain (box, regions, materials, solids), Group, Modify - every block in
+// the byte layout of the reference's own write_restart members, so that read_restart(file) of the reference accepts the file.  The
+// version string is ours unless KML_RESTART_VERSION names another one (the byte-for-byte test compares with the reference build's).
+void Sim::write_restart(const std::string &pattern) {
+  std::string fn = pattern; const size_t star = fn.find('*');
+  if (star != std::string::npos) fn = fn.substr(0, star) + (nranks > 1 ? "proc-" + std::to_string(rank) + "." : "") + std::to_string(ntimestep) + fn.substr(star + 1);
+  else fn = pattern + "proc-" + std::to_string(rank) + "."; // src/write_restart.cpp:64-65
+  if (!quiet && rank == 0) std::cout << "write " << fn << std::endl;
+  std::ofstream os(fn, std::ios::out | std::ios::binary);
+  if (!os) fatal("Error: cannot write in file: " + fn + ".\n");
+  // header (rank 0), src/write_restart.cpp:92-101
+  if (rank == 0) {
+    const char *ver = getenv("KML_RESTART_VERSION");
+    int flag = 0; rput(os, flag); rput_str(os, ver && *ver ? ver : "karamelo-b200");
+    flag = 1; rput(os, flag); rput(os, dimension);
+    flag = 2; rput(os, flag); rput(os, nranks);
+    flag = -1; rput(os, flag);
+  }
+  // Update::write_restart, src/update.cpp:220-275
+  rput_str(os, method_type); { const bool t = temp; rput(os, t); }
+  rput_str(os, scheme_style); rput(os, sub_method); rput(os, PIC_FLIP_script); rput(os, shape_function);
+  { const size_t n = additional_args.size(); rput(os, n); for (auto &a : additional_args) rput_str(os, a); }
+  rput(os, atime); rput(os, ntimestep); rput(os, dt); rput(os, dt_factor); { const bool c = dt_constant; rput(os, c); }
+  // Domain::write_restart, src/domain.cpp:574-631
+  for (int d = 0; d < 3; d++) rput(os, boxlo[d]);
+  for (int d = 0; d < 3; d++) rput(os, boxhi[d]);
+  for (int d = 0; d < 3; d++) rput(os, sublo[d]);
+  for (int d = 0; d < 3; d++) rput(os, subhi[d]);
+  { const bool ax = axisymmetric; rput(os, ax); } rput(os, np_total);
+  if (!is_TL) rput(os, grid->cellsize);
+  { const int n = (int)regions.size(); rput(os, n); }
+  for (auto &r : regions) { rput_str(os, r->id); rput_str(os, r->style); r->write_restart(os); }
+  // Material::write_restart, src/material.cpp:384-497
+  static const char *eos_style[] = {"", "linear", "shock", "fluid"}, *str_style[] = {"", "linear", "plastic", "johnson_cook", "swift", "fluid"};
+  { const int n = (int)eoss.size(); rput(os, n); }
+  for (auto &e : eoss) {
+    rput_str(os, e.id); rput_str(os, eos_style[e.type]); rput(os, e.rho0); rput(os, e.K);
+    if (e.type == KML_EOS_SHOCK) { rput(os, e.c0); rput(os, e.S); rput(os, e.Gamma); rput(os, e.Tr); rput(os, e.cv); rput(os, e.Q1); rput(os, e.Q2); }
+    else if (e.type == KML_EOS_FLUID) rput(os, e.Gamma);
+  }
+  { const int n = (int)strengths.size(); rput(os, n); }
+  for (auto &t : strengths) {
+    rput_str(os, t.id); rput_str(os, str_style[t.type]); rput(os, t.G);
+    if (t.type == KML_STRENGTH_PLASTIC) rput(os, t.A);
+    else if (t.type == KML_STRENGTH_JOHNSON_COOK) { rput(os, t.A); rput(os, t.B); rput(os, t.n); rput(os, t.m); rput(os, t.epsdot0); rput(os, t.C); rput(os, t.Tr); rput(os, t.Tm); }
+    else if (t.type == KML_STRENGTH_SWIFT) { rput(os, t.A); rput(os, t.B); rput(os, t.C); rput(os, t.n); }
+  }
+  { const int n = (int)damages.size(); rput(os, n); }
+  for (auto &d : damages) { rput_str(os, d.id); rput_str(os, "damage_johnson_cook"); rput(os, d.d1); rput(os, d.d2); rput(os, d.d3); rput(os, d.d4); rput(os, d.d5); rput(os, d.epsdot0); rput(os, d.Tr); rput(os, d.Tm); }
+  { const int n = (int)temperatures.size(); rput(os, n); }
+  for (auto &t : temperatures) { rput_str(os, t.id); rput_str(os, "plastic_work"); rput(os, t.chi); rput(os, t.kappa); rput(os, t.cp); rput(os, t.alpha); rput(os, t.T0); rput(os, t.Tm); }
+  { const int n = (int)materials.size(); rput(os, n); }
+  for (auto &m : materials) {
+    rput_str(os, m.id);
+    static const int ref_type[] = {1, 2, 3, 0}; // Material::constitutive_model: RIGID 0, LINEAR 1, NEO_HOOKEAN 2, SHOCK 3 (src/material.h:114-119)
+    const int type = ref_type[m.km.type]; rput(os, type);
+    if (type == 3) { rput(os, m.ieos); rput(os, m.istrength); rput(os, m.idamage); rput(os, m.itemperature); }
+    else if (type == 1 || type == 2) { rput(os, m.km.rho0); rput(os, m.km.E); rput(os, m.km.nu); rput(os, m.km.cp); rput(os, m.km.kappa); }
+  }
+  { const int flag = -2; rput(os, flag); }
+  // solids: Domain::write_restart + Solid::write_restart, src/solid.cpp:2841-2887 (matrices in Eigen's column-major order)
+  { const int n = (int)solids.size(); rput(os, n); }
+  for (auto &Sp : solids) {
+    SolidH &S = *Sp; const int64_t n = S.np;
+    rput_str(os, S.id);
+    for (int d = 0; d < 3; d++) rput(os, S.solidlo[d]);
+    for (int d = 0; d < 3; d++) rput(os, S.solidhi[d]);
+    for (int d = 0; d < 3; d++) { const double v = std::max(S.solidlo[d], sublo[d]); rput(os, v); } // solidsublo / solidsubhi, src/solid.cpp:1840-1846
+    for (int d = 0; d < 3; d++) { const double v = std::min(S.solidhi[d], subhi[d]); rput(os, v); }
+    rput(os, S.np_created); { const int nl = (int)n; rput(os, nl); } { const int nc = is_CPDI ? 1 << dimension : 0; rput(os, nc); } // Solid::nc (src/solid.cpp:83-88); the particle domains themselves are not in the layout
+    rput(os, S.mat); rput(os, S.grid->cellsize);
+    std::vector<int64_t> tag(n); std::vector<int> mask(n);
+    std::vector<double> x0(3 * n), x(3 * n), v(3 * n), sig(9 * n), eel(9 * n), pk1, F(9 * n), J(n), vol0(n), rho0(n), ep(n), epdot(n), dmg(n), dmgi(n), T, ie(n);
+    check(kml_solid_download(ctx, S.dev, KML_P_PTAG, tag.data())); check(kml_solid_download(ctx, S.dev, KML_P_MASK, mask.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_X0, x0.data())); check(kml_solid_download(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_download(ctx, S.dev, KML_P_V, v.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_SIGMA, sig.data())); check(kml_solid_download(ctx, S.dev, KML_P_STRAIN_EL, eel.data()));
+    if (is_TL) { pk1.resize(9 * n); check(kml_solid_download(ctx, S.dev, KML_P_VOL0PK1, pk1.data())); }
+    check(kml_solid_download(ctx, S.dev, KML_P_FDEF, F.data())); check(kml_solid_download(ctx, S.dev, KML_P_J, J.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_VOL0, vol0.data())); check(kml_solid_download(ctx, S.dev, KML_P_RHO0, rho0.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN, ep.data())); check(kml_solid_download(ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN_RATE, epdot.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_DAMAGE, dmg.data())); check(kml_solid_download(ctx, S.dev, KML_P_DAMAGE_INIT, dmgi.data()));
+    if (temp) { T.resize(n); check(kml_solid_download(ctx, S.dev, KML_P_T, T.data())); }
+    check(kml_solid_download(ctx, S.dev, KML_P_IENERGY, ie.data()));
+    auto put_mat = [&](const double *m) { for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) rput(os, m[3 * r + c]); };
+    for (int64_t i = 0; i < n; i++) {
+      rput(os, tag[i]); os.write((const char *)&x0[3 * i], 24); os.write((const char *)&x[3 * i], 24); os.write((const char *)&v[3 * i], 24);
+      put_mat(&sig[9 * i]); put_mat(&eel[9 * i]); if (is_TL) put_mat(&pk1[9 * i]); put_mat(&F[9 * i]);
+      rput(os, J[i]); rput(os, vol0[i]); rput(os, rho0[i]); rput(os, ep[i]); rput(os, epdot[i]); rput(os, dmg[i]); rput(os, dmgi[i]);
+      if (temp) rput(os, T[i]);
+      rput(os, ie[i]); rput(os, mask[i]);
+    }
+  }
+  // Group::write_restart, src/group.cpp:470-504
+  rput(os, ngroup);
+  for (int ig = 1; ig < ngroup; ig++) {
+    rput_str(os, gnames[ig]); rput(os, gbitmask[ig]); const bool p_or_n = gpon[ig] != "particles"; rput(os, p_or_n); rput(os, gsolid[ig]); rput(os, gregion[ig]);
+  }
+  // Modify::write_restart, src/modify.cpp:312-331
+  { const size_t n = fixes.size(); rput(os, n); }
+  for (auto &f : fixes) { rput_str(os, f->id); rput_str(os, f->style); rput(os, f->igroup); f->write_restart(os); }
+}
+
 void Sim::output_write(int64_t step) { // Output::write, src/output.cpp:128-199
   for (auto &d : dumps)
     if (d.next == step) { if (d.style == "particle" || d.style == "particle/gz") write_particle_dump(*this, d); else if (d.style == "grid" || d.style == "grid/gz") write_grid_dump(*this, d); d.next += d.every; }
+  if (restart_every && next_restart == step) { write_restart(restart_name); next_restart += restart_every; } // src/output.cpp:152-155
   if (next_log == step || step == 0) {
     for (auto &c : computes) c->compute_value(*this); // Modify::run_computes
     if (!quiet) {
@@ -670,7 +792,7 @@ void Sim::run(Var condition) {
     }
     hooks(FINAL_INTEGRATE);
     if (maxtime != -1 && atime > maxtime) { nsteps = ntimestep; output_write(ntimestep); break; }
-    bool due = ntimestep == next_log || ntimestep == nsteps;
+    bool due = ntimestep == next_log || ntimestep == nsteps || (restart_every && next_restart == ntimestep);
     for (auto &d : dumps) due = due || d.next == ntimestep;
     if (due) output_write(ntimestep);
   }

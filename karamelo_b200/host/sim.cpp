@@ -68,7 +68,20 @@ void Sim::register_commands() {
     if (a.empty() || a[0] != "custom") fatal("Unknown log style.\n");
     log_fields.assign(a.begin() + 1, a.end()); return Var(0);
   };
-  c["restart"] = [this](std::vector<std::string> &a) { restart_every = (int)(double)input.parsev(a[0]); if (a.size() > 1) restart_name = a[1]; return Var(0); };
+  c["restart"] = [this](std::vector<std::string> &a) { // Output::create_restart, src/output.cpp:323-350
+    if (a.size() < 1) fatal("Illegal restart command: too few arguments.\n");
+    if (a.size() > 2) fatal("Illegal restart command: too many arguments.\n");
+    restart_every = (int)(double)input.parsev(a[0]);
+    if (restart_every == 0) { next_restart = 0; return Var(0); }
+    if (a.size() < 2) fatal("Illegal restart command: too few arguments.\n");
+    restart_name = a[1];
+    next_restart = (ntimestep / restart_every) * restart_every + restart_every;
+    return Var(0);
+  };
+  c["write_restart"] = [](std::vector<std::string> &a) { // WriteRestart::command only records the file name (src/write_restart.cpp:36-48);
+    if (a.size() < 1) fatal("Illegal write command.\n");  // files are written by restart(N, file), through Output::write
+    return Var(0);
+  };
   c["run"] = [this](std::vector<std::string> &a) { return cmd_run(a, 0); };
   c["run_time"] = [this](std::vector<std::string> &a) { return cmd_run(a, 1); };
   c["run_until"] = [this](std::vector<std::string> &a) { return cmd_run(a, 2); };
@@ -169,7 +182,7 @@ void Sim::register_commands() {
       while (k < n) {
         if (dl[k]) { S.x0[k] = S.x0[n - 1]; S.mask[k] = S.mask[n - 1]; S.ptag[k] = S.ptag[n - 1]; dl[k] = dl[n - 1]; n--; } else k++;
       }
-      np_total -= S.np - n;
+      np_total = n; // sic: the reference stores this solid's remaining count (domain->np_total = np_local_reduced, src/delete_particles.cpp:78)
       S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n);
       std::vector<double> vol(n), mass(n);
       check(kml_solid_download(ctx, S.dev, KML_P_VOL, vol.data())); check(kml_solid_download(ctx, S.dev, KML_P_MASS, mass.data()));
@@ -220,6 +233,7 @@ Var Sim::cmd_method(std::vector<std::string> &a) {
   n++;
   if (a.size() >= n + 1 && a[n] == "gradient-enhanced") { ge = true; n++; }
   std::vector<std::string> extra; if (n < a.size()) extra.assign(a.begin() + n, a.end());
+  additional_args = extra;
   if (is_CPDI) { // TLCPDI/ULCPDI::setup: style R4 / Q4
     if (!extra.empty()) { if (extra[0] == "R4") cpdi_style = 0; else if (extra[0] == "Q4") cpdi_style = 1; else fatal("Unknown CPDI style " + extra[0]); }
   } else if (!extra.empty()) fatal("Illegal modify_method command: too many arguments.\n");
@@ -229,6 +243,7 @@ Var Sim::cmd_method(std::vector<std::string> &a) {
   // ULCPDI::advance_particles blends with its OWN member `FLIP` (src/ulcpdi.cpp:468, declared src/ulcpdi.h:31), which no code
   // ever assigns: the ratio given in the script is ignored and the freshly allocated Method object holds 0.0, i.e. the
   // reference's ULCPDI is pure PIC whatever the script says (verified against the reference build: bit-identical with 0).
+  PIC_FLIP_script = PIC_FLIP; // Update::PIC_FLIP as the reference keeps (and writes to restart files) it
   if (method_type == "ulcpdi") PIC_FLIP = 0;
   method_set = true;
   return Var(0);
@@ -336,8 +351,10 @@ Var Sim::cmd_dimension(std::vector<std::string> &a) {
 }
 
 namespace {
+template <class T> void put(std::ostream &os, const T &v) { os.write(reinterpret_cast<const char *>(&v), sizeof(T)); }
 struct Block : Region {
   int inside(double x, double y, double z) const override { return x >= lim[0] && x <= lim[1] && y >= lim[2] && y <= lim[3] && z >= lim[4] && z <= lim[5]; }
+  void write_restart(std::ostream &os) const override { for (int k = 0; k < 6; k++) put(os, lim[k]); } // src/region_block.cpp:170-177
 };
 struct Cylinder : Region {
   char axis = 'z'; double c1 = 0, c2 = 0, R = 0, RSq = 0, lo = 0, hi = 0;
@@ -347,10 +364,14 @@ struct Cylinder : Region {
     if (axis == 'y') { dSq = (x - c1) * (x - c1) + (z - c2) * (z - c2); return y >= lo && y <= hi && dSq <= RSq; }
     dSq = (x - c1) * (x - c1) + (y - c2) * (y - c2); return z >= lo && z <= hi && dSq <= RSq;
   }
+  void write_restart(std::ostream &os) const override { // src/region_cylinder.cpp:184-197
+    put(os, c1); put(os, c2); put(os, R); put(os, lo); put(os, hi); put(os, axis); for (int k = 0; k < 6; k++) put(os, lim[k]);
+  }
 };
 struct Sphere : Region {
-  double c1 = 0, c2 = 0, c3 = 0, RSq = 0;
+  double c1 = 0, c2 = 0, c3 = 0, R = 0, RSq = 0;
   int inside(double x, double y, double z) const override { return (x - c1) * (x - c1) + (y - c2) * (y - c2) + (z - c3) * (z - c3) <= RSq; }
+  void write_restart(std::ostream &os) const override { put(os, c1); put(os, c2); put(os, c3); put(os, R); for (int k = 0; k < 6; k++) put(os, lim[k]); } // src/region_sphere.cpp:145-156
 };
 } // namespace
 
@@ -402,7 +423,7 @@ Var Sim::cmd_region(std::vector<std::string> &a) {
     s->c1 = input.parsev(a[i++]); if (dim >= 2) s->c2 = input.parsev(a[i++]); if (dim == 3) s->c3 = input.parsev(a[i++]);
     double R = input.parsev(a[i++]);
     if (R < 0) fatal("Error: R cannot be negative.\n");
-    s->RSq = R * R;
+    s->R = R; s->RSq = R * R;
     double *l = s->lim; l[0] = s->c1 - R; l[1] = s->c1 + R; l[2] = s->c2 - R; l[3] = s->c2 + R; l[4] = s->c3 - R; l[5] = s->c3 + R;
     if (method_type == "tlmpm") {
       for (int d = 0; d < (dim == 3 ? 3 : 2); d++) { if (boxlo[d] > l[2 * d]) boxlo[d] = l[2 * d]; if (boxhi[d] < l[2 * d + 1]) boxhi[d] = l[2 * d + 1]; }
@@ -504,6 +525,8 @@ Var Sim::cmd_material(std::vector<std::string> &a) {
       }
     }
     m.type = KML_MAT_EOS_STRENGTH;
+    M.ieos = (int)(e - eoss.data()); M.istrength = (int)(s - strengths.data()); M.idamage = d ? (int)(d - damages.data()) : -1;
+    M.itemperature = t ? (int)(t - temperatures.data()) : -1;
     m.eos_type = e->type; m.eos_K = e->K; m.eos_c0 = e->c0; m.eos_S = e->S; m.eos_Gamma = e->Gamma; m.eos_cv = e->cv; m.eos_Tr = e->Tr; m.eos_Q1 = e->Q1; m.eos_Q2 = e->Q2;
     m.strength_type = s->type; m.str_G = s->G; m.str_A = s->A; m.str_B = s->B; m.str_n = s->n; m.str_epsdot0 = s->epsdot0; m.str_C = s->C; m.str_m = s->m; m.str_Tr = s->Tr; m.str_Tm = s->Tm;
     if (d) { m.damage_type = d->type; m.dmg_d1 = d->d1; m.dmg_d2 = d->d2; m.dmg_d3 = d->d3; m.dmg_d4 = d->d4; m.dmg_d5 = d->d5; m.dmg_epsdot0 = d->epsdot0; m.dmg_Tr = d->Tr; m.dmg_Tm = d->Tm; }
@@ -627,7 +650,7 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
     lattice([&](const std::array<double, 3> &x) { s.x0.push_back(x); });
     np_global = (int64_t)s.x0.size();
   }
-  s.np = (int64_t)s.x0.size();
+  s.np = (int64_t)s.x0.size(); s.np_created = np_global;
   if (s.np == 0) fatal("Error: solid does not have any particles.\n");
   s.mask.assign(s.np, 1);
   s.ptag.resize(s.np);

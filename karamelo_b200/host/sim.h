@@ -4,6 +4,7 @@
 // (node counts, particle lattice, group masks) is restated from the reference with
 // file:line citations; the per-step work is delegated to the C ABI in include/kml.h.
 #pragma once
+#include <ostream>
 #include "../../include/kml.h"
 #include "input.h"
 #include <array>
@@ -23,11 +24,13 @@ struct Region {
   virtual ~Region() {}
   virtual int inside(double x, double y, double z) const = 0;
   int match(double x, double y, double z) const { return interior ? inside(x, y, z) : !inside(x, y, z); } // src/region.cpp:64-72
+  virtual void write_restart(std::ostream &) const {} // Region::write_restart of the style (src/region_block.cpp:170-177, ...)
 };
 
 struct MaterialH {
   std::string id;
   kml_material km;
+  int ieos = -1, istrength = -1, idamage = -1, itemperature = -1; // indices into the EOS / strength / ... lists (restart files)
 };
 struct EOSH { std::string id; int type; double rho0, K, c0, S, Gamma, cv, Tr, Q1, Q2; };
 struct StrengthH { std::string id; int type; double G, A, B, n, epsdot0, C, m, Tr, Tm; };
@@ -50,6 +53,7 @@ struct SolidH {
   GridH *grid = nullptr;       // UL: the domain grid; TL: own grid
   std::unique_ptr<GridH> own_grid;
   int64_t np = 0;
+  int64_t np_created = 0;      // Solid::np: set by populate, unchanged by delete_particles (written to restart files)
   int np_per_cell = 0;
   double solidlo[3], solidhi[3];
   double T0 = 0;
@@ -73,6 +77,7 @@ struct Fix {
   virtual void post_advance_particles(Sim &) {}
   virtual void post_velocities_to_grid(Sim &) {}
   virtual void final_integrate(Sim &) {}
+  virtual void write_restart(std::ostream &) const {} // Fix::write_restart of the style (src/fix_velocity_nodes.cpp:270-292, ...)
 };
 struct Compute {
   std::string id, style;
@@ -94,7 +99,7 @@ public:
   int64_t ntimestep = 0, atimestep = 0, firststep = 0, laststep = 0; double atime = 0, maxtime = -1; int64_t nsteps = 0;
   std::string method_type, scheme_style = "musl";                    // default scheme MUSL, src/update.cpp:42-45
   bool method_set = false, is_TL = false, is_CPDI = false, temp = false, ge = false; int cpdi_style = 0;
-  int shape_function = KML_SHAPE_LINEAR, sub_method = KML_SUB_FLIP; double PIC_FLIP = 0.99;
+  int shape_function = KML_SHAPE_LINEAR, sub_method = KML_SUB_FLIP; double PIC_FLIP = 0.99, PIC_FLIP_script = 0.99;
 
   // ---- Domain ----
   int dimension = 0; double boxlo[3] = {0, 0, 0}, boxhi[3] = {0, 0, 0}, sublo[3] = {0, 0, 0}, subhi[3] = {0, 0, 0};
@@ -117,7 +122,9 @@ public:
   // ---- Output ----
   int every_log = 1 /* src/output.cpp:48 */; std::vector<std::string> log_fields{"step", "dt", "time"}; int64_t next_log = 0;
   std::vector<Dump> dumps; std::ofstream logfile; bool quiet = false;
-  int restart_every = 0; std::string restart_name; // accepted and ignored
+  int restart_every = 0; int64_t next_restart = 0; std::string restart_name; // Output::create_restart, src/output.cpp:323-350
+  std::vector<std::string> additional_args;                                  // Update::additional_args (CPDI style), src/update.cpp:189-194
+  void write_restart(const std::string &pattern);                            // WriteRestart::write, src/write_restart.cpp:51-88
 
   // ---- device ----
   kml_ctx *ctx = nullptr; int device = 0;

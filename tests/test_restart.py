@@ -1,0 +1,51 @@
+"""Restart files: `restart(N, file-*.restart)` / `write_restart(file)` of our host write the reference's binary layout
+(src/write_restart.cpp:51-88 and the write_restart member of every class it calls: Update, Domain, regions, Material with its EOS /
+strength / damage / temperature lists, Solid, Group, Modify and the fixes).  With the CPU oracle behind the host the state is
+bit-identical to the reference's, so the whole FILE must be: every parity case is run for 20 steps through the unmodified reference
+binary and through our CLI and the two restart files are compared byte for byte (the version string of the header is set to the
+reference build's).  Build-container only (needs /root/reference and oracle/_ref)."""
+import os
+import subprocess
+
+import pytest
+
+from cases import CASES
+from conftest import ROOT
+from test_shipped_examples import OUR_CLI, REF_BIN
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.isdir("/root/reference")), reason="needs /root/reference and oracle/_ref (build container only)")
+ENV = dict(os.environ, KML_RESTART_VERSION="oracle-ref-build")  # Version::GIT_SHA1 of oracle/ref_version.cpp
+
+
+def run(exe, d, text):
+    os.makedirs(d)
+    with open(os.path.join(d, "in.mpm"), "w") as f:
+        f.write(text)
+    p = subprocess.run([exe, "-i", "in.mpm"], cwd=d, capture_output=True, text=True, timeout=600, env=ENV)
+    assert p.returncode == 0, (exe, p.stdout[-300:], p.stderr[-300:])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cli(oracle_lib):
+    if not os.path.exists(OUR_CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_restart_file_is_the_reference_file(name, tmp_path):
+    text = CASES[name][0] + "\nrestart(10, rst-*.restart)\nrun(20)\n"
+    run(REF_BIN, str(tmp_path / "ref"), text)
+    run(OUR_CLI, str(tmp_path / "our"), text)
+    for step in (10, 20):
+        a = open(tmp_path / "ref" / ("rst-%d.restart" % step), "rb").read()
+        b = open(tmp_path / "our" / ("rst-%d.restart" % step), "rb").read()
+        assert len(a) == len(b) and a == b, "restart file of step %d differs from the reference's (first difference at byte %d of %d)" % (
+            step, next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b))), len(a))
+
+
+def test_write_restart_command_only_records_the_name(tmp_path):
+    # WriteRestart::command stores the file name and returns (src/write_restart.cpp:36-48): neither program writes a file
+    text = CASES["c1_two_disks_musl"][0] + "\nrun(5)\nwrite_restart(snap-*.restart)\n"
+    run(REF_BIN, str(tmp_path / "ref"), text)
+    run(OUR_CLI, str(tmp_path / "our"), text)
+    assert not [f for d in ("ref", "our") for f in os.listdir(tmp_path / d) if f.endswith(".restart")]
