@@ -354,6 +354,32 @@ struct ComputeAverageVelocity : Compute {
 };
 } // namespace
 
+// Modify::read_restart, src/modify.cpp:335-366: the fix is created through its "restart" constructor (group from the stored index) and
+// then reads what its write_restart wrote - flags and Vars as (equation, value, constant), src/var.cpp:322-331
+std::unique_ptr<Fix> Sim::fix_from_restart(const std::string &id, const std::string &style, int ig, std::istream &is) {
+  auto get = [&](auto &v) { is.read(reinterpret_cast<char *>(&v), sizeof v); };
+  auto get_var = [&]() { size_t n = 0; get(n); if (n > (1u << 20)) fatal("read_restart: corrupt Var\n"); std::string eq(n, '\0'); is.read(&eq[0], (std::streamsize)n); double v = 0; bool c = false; get(v); get(c); return Var(eq, v, c); };
+  auto get_sets = [&](bool *set, Var *val, Var *prev) { for (int d = 0; d < 3; d++) get(set[d]); for (int d = 0; d < 3; d++) if (set[d]) { val[d] = get_var(); if (prev) prev[d] = get_var(); } };
+  std::unique_ptr<Fix> fix;
+  if (style == "velocity_nodes") { auto f = new FixVelocityNodes(); fix.reset(f); get_sets(f->set, f->val, f->prev); f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID; }
+  else if (style == "velocity_particles") { auto f = new FixVelocityParticles(); fix.reset(f); get_sets(f->set, f->val, f->prev); f->mask = INITIAL_INTEGRATE | POST_ADVANCE_PARTICLES; }
+  else if (style == "body_force") { auto f = new FixBodyForce(); fix.reset(f); get_sets(f->set, f->val, nullptr); f->mask = POST_PARTICLES_TO_GRID; }
+  else if (style == "force_nodes") { auto f = new FixForceNodes(); fix.reset(f); get_sets(f->set, f->val, nullptr); f->mask = POST_PARTICLES_TO_GRID; }
+  else if (style == "temperature_nodes") { auto f = new FixTemperatureNodes(); fix.reset(f); f->val = get_var(); f->prev = get_var(); f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID; }
+  else if (style == "temperature_particles") { auto f = new FixTemperatureParticles(); fix.reset(f); f->val = get_var(); f->prev = get_var(); f->mask = INITIAL_INTEGRATE | POST_ADVANCE_PARTICLES; }
+  else if (style == "kinetic_energy" || style == "strain_energy") { auto f = new FixEnergy(); fix.reset(f); f->kinetic = style == "kinetic_energy"; f->mask = FINAL_INTEGRATE; }
+  else if (style == "contact/hertz" || style == "contact/minimize_penetration") {
+    auto f = new FixContact(); fix.reset(f); f->hertz = style == "contact/hertz"; get(f->solid1); get(f->solid2); if (!f->hertz) get(f->mu); f->mask = INITIAL_INTEGRATE;
+  }
+  else if (style == "initial_velocity_particles") { fix.reset(new FixInitialVelocityParticles()); fix->mask = INITIAL_INTEGRATE; }   // nothing stored: these act at step 1 only
+  else if (style == "initial_stress") { fix.reset(new FixInitialStress()); fix->mask = INITIAL_INTEGRATE; }
+  else if (style == "initial_velocity_nodes") { fix.reset(new FixInitialVelocityNodes()); fix->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID; }
+  else fatal("read_restart: fix style " + style + " is not supported\n");
+  fix->id = id; fix->style = style; fix->igroup = ig; fix->groupbit = ig >= 0 ? gbitmask[ig] : 0;
+  for (const char *sfx : {"_x", "_y", "_z", "_s"}) if (!input.vars.count(id + sfx)) input.vars[id + sfx] = Var(id + sfx, 0.0);
+  return fix;
+}
+
 // Modify::add_fix, reference src/modify.cpp:95-140 (fix(ID, style, group-ID, args...))
 Var Sim::cmd_fix(std::vector<std::string> &a) {
   if (a.size() < 3) fatal("Error: too few arguments for the fix command.\n");
@@ -804,6 +830,7 @@ void Sim::run(Var condition) {
 Var Sim::cmd_run(std::vector<std::string> &a, int kind) {
   if (a.size() < 1) fatal("Illegal run command.\n");
   if (!method_set || !ctx) fatal("Error: no method was defined!\n");
+  if (restarted_TL) fatal("Bad domain decomposition, some CPUs (at least CPU #0) do not have any particles attached to.\nTry to increase or decrease the number of CPUs (using prime numbers might help).\n");
   check(kml_set_dt(ctx, dt));
   // Run::command calls scheme->setup() (-> Output::setup) BEFORE it updates laststep (src/run.cpp:41-53): the log interval of a
   // second run is therefore clipped by the PREVIOUS run's last step, which is why the reference repeats that step's row

@@ -78,6 +78,10 @@ void Sim::register_commands() {
     next_restart = (ntimestep / restart_every) * restart_every + restart_every;
     return Var(0);
   };
+  c["read_restart"] = [this](std::vector<std::string> &a) { // ReadRestart::command, src/read_restart.cpp:36-83
+    if (a.size() < 1) fatal("Illegal read command.\n");
+    read_restart(a[0]); return Var(0);
+  };
   c["write_restart"] = [](std::vector<std::string> &a) { // WriteRestart::command only records the file name (src/write_restart.cpp:36-48);
     if (a.size() < 1) fatal("Illegal write command.\n");  // files are written by restart(N, file), through Output::write
     return Var(0);
@@ -435,6 +439,184 @@ Var Sim::cmd_region(std::vector<std::string> &a) {
   regions.push_back(std::move(reg));
   if (ctx) check(kml_set_domain_box(ctx, boxlo, boxhi));
   return Var(0);
+}
+
+// ReadRestart::command (src/read_restart.cpp:36-83) and the read_restart members it calls: Update (src/update.cpp:279-349), Domain
+// (src/domain.cpp:635-721), regions, Material (src/material.cpp:499-612), Solid (src/solid.cpp:2889-2957), Group (src/group.cpp:508-600),
+// Modify (src/modify.cpp:335-366).  Objects whose constructors derive values (materials, the domain, groups) are rebuilt through the same
+// command code as a script would use, with every number handed over as a constant variable so that no digit passes through the parser.
+namespace {
+template <class T> T rget(std::istream &is) { T v{}; is.read(reinterpret_cast<char *>(&v), sizeof(T)); return v; }
+std::string rget_str(std::istream &is) { const size_t n = rget<size_t>(is); if (n > (1u << 20)) fatal("read_restart: corrupt string length\n"); std::string t(n, '\0'); is.read(&t[0], (std::streamsize)n); return t; }
+} // namespace
+
+void Sim::read_restart(const std::string &pattern) {
+  std::string fn = pattern; const size_t star = fn.find('*');
+  if (star != std::string::npos) fn = fn.substr(0, star) + (nranks > 1 ? "proc-" + std::to_string(rank) + "." : "") + fn.substr(star + 1);
+  if (!quiet && rank == 0) std::cout << "read " << fn << std::endl;
+  std::ifstream is(fn, std::ios::in | std::ios::binary);
+  if (!is) fatal("Error: cannot read in file: " + fn + ".\n");
+  if (nranks > 1) fatal("read_restart on a decomposed run is not supported\n");
+  int nvar = 0;
+  auto num = [&](double v) { const std::string name = "__rst" + std::to_string(nvar++); input.vars[name] = Var(v); return name; }; // exact constant
+  auto call = [&](const char *cmd, std::vector<std::string> a) { input.commands.at(cmd)(a); };
+  // header
+  for (int flag = rget<int>(is); flag >= 0 && is; flag = rget<int>(is)) {
+    if (flag == 0) { const std::string v = rget_str(is); if (!quiet) std::cout << "version = " << v << std::endl; }
+    else if (flag == 1) dimension = rget<int>(is);
+    else if (flag == 2) { const int np = rget<int>(is); if (np != nranks) fatal("Restart file written for " + std::to_string(np) + " CPUs.\n"); }
+  }
+  // Update
+  const std::string mtype = rget_str(is); const bool temp_ = rget<bool>(is); const std::string scheme = rget_str(is);
+  const int sub = rget<int>(is); const double pf = rget<double>(is); const int shape = rget<int>(is);
+  std::vector<std::string> extra(rget<size_t>(is)); for (auto &e : extra) e = rget_str(is);
+  const double atime_ = rget<double>(is); const int64_t nt = rget<int64_t>(is); const double dt_ = rget<double>(is), dtf = rget<double>(is);
+  const bool dtc = rget<bool>(is);
+  static const char *subn[] = {"PIC", "FLIP", "APIC", "AFLIP", "ASFLIP", "MLS"}, *shn[] = {"linear", "cubic-spline", "quadratic-spline", "Bernstein-quadratic"};
+  if (sub < 0 || sub > 5 || shape < 0 || shape > 3) fatal("read_restart: unknown method enumerators\n");
+  { std::vector<std::string> a{mtype, subn[sub], shn[shape]};
+    if (sub == KML_SUB_FLIP || sub == KML_SUB_AFLIP || sub == KML_SUB_ASFLIP) a.push_back(num(pf));
+    a.push_back(temp_ ? "thermo-mechanical" : "mechanical");
+    a.insert(a.end(), extra.begin(), extra.end());
+    call("method", a); }
+  call("scheme", {scheme});
+  // Domain
+  double lo[3], hi[3];
+  for (double &v : lo) v = rget<double>(is);
+  for (double &v : hi) v = rget<double>(is);
+  for (int k = 0; k < 6; k++) rget<double>(is); // sublo / subhi: one rank, recomputed
+  const bool axi = rget<bool>(is); const int64_t np_total_ = rget<int64_t>(is);
+  if (axi) call("axisymmetric", {"true"});
+  { std::vector<std::string> a{std::to_string(dimension)};
+    for (int d = 0; d < dimension; d++) { a.push_back(num(lo[d])); a.push_back(num(hi[d])); }
+    a.push_back(is_TL ? num(0.0) : num(rget<double>(is))); // TL: dimension() takes and ignores a cell size
+    call("dimension", a); }
+  for (int n = rget<int>(is), i = 0; i < n; i++) { // regions: restart constructors do not touch the box (src/region_block.cpp:35-42)
+    const std::string id = rget_str(is), style = rget_str(is);
+    std::unique_ptr<Region> reg;
+    if (style == "block") { auto b = new Block(); reg.reset(b); for (double &v : b->lim) v = rget<double>(is); }
+    else if (style == "cylinder") {
+      auto c = new Cylinder(); reg.reset(c);
+      c->c1 = rget<double>(is); c->c2 = rget<double>(is); c->R = rget<double>(is); c->lo = rget<double>(is); c->hi = rget<double>(is); c->axis = rget<char>(is);
+      for (double &v : c->lim) v = rget<double>(is);
+      c->RSq = c->R * c->R;
+    } else if (style == "sphere") {
+      auto sp = new Sphere(); reg.reset(sp);
+      sp->c1 = rget<double>(is); sp->c2 = rget<double>(is); sp->c3 = rget<double>(is); sp->R = rget<double>(is); for (double &v : sp->lim) v = rget<double>(is);
+      sp->RSq = sp->R * sp->R;
+    } else fatal("read_restart: region style " + style + " is not supported\n");
+    reg->id = id; reg->style = style; regions.push_back(std::move(reg));
+  }
+  // Material
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is), style = rget_str(is);
+    const double rho0 = rget<double>(is), K = rget<double>(is);
+    if (style == "linear") call("eos", {id, style, num(rho0), num(K)});
+    else if (style == "shock") { const double c0 = rget<double>(is), S = rget<double>(is), G = rget<double>(is), Tr = rget<double>(is), cv = rget<double>(is), Q1 = rget<double>(is), Q2 = rget<double>(is);
+      call("eos", {id, style, num(rho0), num(K), num(c0), num(S), num(G), num(cv), num(Tr), num(Q1), num(Q2)}); }
+    else if (style == "fluid") call("eos", {id, style, num(rho0), num(K), num(rget<double>(is))});
+    else fatal("read_restart: EOS style " + style + " unknown\n");
+  }
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is), style = rget_str(is); const double G = rget<double>(is);
+    if (style == "linear" || style == "fluid") call("strength", {id, style, num(G)});
+    else if (style == "plastic") call("strength", {id, style, num(G), num(rget<double>(is))});
+    else if (style == "johnson_cook") { const double A = rget<double>(is), B = rget<double>(is), n_ = rget<double>(is), m = rget<double>(is), e0 = rget<double>(is), C = rget<double>(is), Tr = rget<double>(is), Tm = rget<double>(is);
+      call("strength", {id, style, num(G), num(A), num(B), num(n_), num(e0), num(C), num(m), num(Tr), num(Tm)}); }
+    else if (style == "swift") { const double A = rget<double>(is), B = rget<double>(is), C = rget<double>(is), n_ = rget<double>(is); call("strength", {id, style, num(G), num(A), num(B), num(C), num(n_)}); }
+    else fatal("read_restart: strength style " + style + " unknown\n");
+  }
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is), style = rget_str(is); std::vector<std::string> a{id, style};
+    for (int k = 0; k < 8; k++) a.push_back(num(rget<double>(is))); // d1..d5, epsdot0, Tr, Tm
+    call("damage", a);
+  }
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is), style = rget_str(is);
+    const double chi = rget<double>(is), kappa = rget<double>(is), cp = rget<double>(is), alpha = rget<double>(is), T0 = rget<double>(is), Tm = rget<double>(is);
+    call("temperature", {id, style, num(chi), num(cp), num(kappa), num(alpha), num(T0), num(Tm)});
+  }
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is); const int type = rget<int>(is);
+    if (type == 3) {
+      const int ie = rget<int>(is), ist = rget<int>(is), id_ = rget<int>(is), it = rget<int>(is);
+      std::vector<std::string> a{id, "eos-strength", eoss.at(ie).id, strengths.at(ist).id};
+      if (id_ >= 0) a.push_back(damages.at(id_).id);
+      if (it >= 0) a.push_back(temperatures.at(it).id);
+      call("material", a);
+    } else if (type == 1 || type == 2) {
+      const double rho0 = rget<double>(is), E = rget<double>(is), nu = rget<double>(is), cp = rget<double>(is), kappa = rget<double>(is);
+      std::vector<std::string> a{id, type == 1 ? "linear" : "neo-hookean", num(rho0), num(E), num(nu)};
+      if (cp != 0 || kappa != 0) { a.push_back(num(cp)); a.push_back(num(kappa)); }
+      call("material", a);
+    } else fatal("read_restart: the reference's writer stores nothing for a rigid material, its reader expects a density (src/material.cpp:478-484, :598-601): such files cannot be read\n");
+  }
+  if (rget<int>(is) != -2) fatal("Error: unexpected end to Material::read_restart(). Number of read entities unexpected.\n");
+  // solids
+  for (int n = rget<int>(is), i = 0; i < n; i++) {
+    std::unique_ptr<SolidH> sp(new SolidH()); SolidH &S = *sp; S.id = rget_str(is);
+    if (is_TL) { S.own_grid.reset(new GridH()); S.grid = S.own_grid.get(); } else S.grid = grid.get();
+    for (double &v : S.solidlo) v = rget<double>(is);
+    for (double &v : S.solidhi) v = rget<double>(is);
+    for (int k = 0; k < 6; k++) rget<double>(is); // solidsublo / solidsubhi
+    S.np_created = rget<int64_t>(is); S.np = rget<int>(is); const int nc = rget<int>(is); (void)nc;
+    S.mat = rget<int>(is); const double cs = rget<double>(is);
+    if (is_CPDI) fatal("read_restart: the layout holds no CPDI particle domains (src/solid.cpp:2889-2957)\n");
+    if (S.mat < 0 || S.mat >= (int)materials.size()) fatal("read_restart: bad material index\n");
+    if (is_TL) { S.grid->cellsize = cs; init_grid(*S.grid, S.solidlo, S.solidhi); }
+    const int64_t np = S.np;
+    std::vector<double> x(3 * np), v(3 * np), sig(9 * np), eel(9 * np), pk1(is_TL ? 9 * np : 0), F(9 * np), vol0(np), vol(np), rho0(np), mass(np), ep(np), epd(np), dmg(np), dmgi(np), T(temp ? np : 0), ie(np);
+    S.x0.resize(np); S.mask.resize(np); S.ptag.resize(np);
+    auto get_mat = [&](double *m) { for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) m[3 * r + c] = rget<double>(is); }; // Eigen column-major -> rows
+    for (int64_t ip = 0; ip < np; ip++) {
+      S.ptag[ip] = rget<int64_t>(is);
+      for (int d = 0; d < 3; d++) S.x0[ip][d] = rget<double>(is);
+      for (int d = 0; d < 3; d++) x[3 * ip + d] = rget<double>(is);
+      for (int d = 0; d < 3; d++) v[3 * ip + d] = rget<double>(is);
+      get_mat(&sig[9 * ip]); get_mat(&eel[9 * ip]); if (is_TL) get_mat(&pk1[9 * ip]); get_mat(&F[9 * ip]);
+      const double J = rget<double>(is); vol0[ip] = rget<double>(is); vol[ip] = J * vol0[ip]; rho0[ip] = rget<double>(is); mass[ip] = rho0[ip] * vol0[ip];
+      ep[ip] = rget<double>(is); epd[ip] = rget<double>(is); dmg[ip] = rget<double>(is); dmgi[ip] = rget<double>(is);
+      if (temp) T[ip] = rget<double>(is);
+      ie[ip] = rget<double>(is); S.mask[ip] = rget<int>(is);
+    }
+    if (!is) fatal("read_restart: unexpected end of file in solid " + S.id + "\n");
+    kml_solid_desc d; memset(&d, 0, sizeof d); d.np = np; d.capacity = np; d.grid = S.grid->id; d.mat = materials[S.mat].km;
+    check(kml_solid_create(ctx, &d, &S.dev));
+    check(kml_solid_upload(ctx, S.dev, KML_P_PTAG, S.ptag.data())); check(kml_solid_upload(ctx, S.dev, KML_P_MASK, S.mask.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_upload(ctx, S.dev, KML_P_X0, S.x0.data())); check(kml_solid_upload(ctx, S.dev, KML_P_V, v.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_SIGMA, sig.data())); check(kml_solid_upload(ctx, S.dev, KML_P_STRAIN_EL, eel.data()));
+    if (is_TL) check(kml_solid_upload(ctx, S.dev, KML_P_VOL0PK1, pk1.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_FDEF, F.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_VOL0, vol0.data())); check(kml_solid_upload(ctx, S.dev, KML_P_VOL, vol.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_RHO0, rho0.data())); check(kml_solid_upload(ctx, S.dev, KML_P_MASS, mass.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN, ep.data())); check(kml_solid_upload(ctx, S.dev, KML_P_EFF_PLASTIC_STRAIN_RATE, epd.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_DAMAGE, dmg.data())); check(kml_solid_upload(ctx, S.dev, KML_P_DAMAGE_INIT, dmgi.data()));
+    if (temp) check(kml_solid_upload(ctx, S.dev, KML_P_T, T.data()));
+    check(kml_solid_upload(ctx, S.dev, KML_P_IENERGY, ie.data()));
+    S.vtot = S.mtot = 0; for (int64_t ip = 0; ip < np; ip++) { S.vtot += vol[ip]; S.mtot += mass[ip]; }
+    solids.push_back(std::move(sp));
+  }
+  np_total = np_total_;
+  // groups: re-assigned from region and reference position like Group::read_restart does
+  const int ng = rget<int>(is);
+  for (int ig = 1; ig < ng; ig++) {
+    const std::string name = rget_str(is); const int bit = rget<int>(is); const bool nodes = rget<bool>(is); const int isolid = rget<int>(is), ireg = rget<int>(is); (void)bit;
+    if (ireg < 0 || ireg >= (int)regions.size()) fatal("Error: could not find region with ID " + std::to_string(ireg) + ".\n");
+    std::vector<std::string> a{name, nodes ? "nodes" : "particles", "region", regions[ireg]->id};
+    if (isolid == -1) a.push_back("all"); else { a.push_back("solid"); a.push_back(solids.at(isolid)->id); }
+    call("group", a);
+  }
+  // fixes
+  for (size_t n = rget<size_t>(is), i = 0; i < n; i++) {
+    const std::string id = rget_str(is), style = rget_str(is); const int ig = rget<int>(is);
+    fixes.push_back(fix_from_restart(id, style, ig, is));
+  }
+  if (!is) fatal("read_restart: unexpected end of file\n");
+  // Update::read_restart: time, step, dt
+  restarted_TL = is_TL; // Domain::np_local is not restored (src/domain.cpp:635-721): TLMPM refuses the next run (src/tlmpm.cpp:91-99)
+  atime = atime_; ntimestep = nt; atimestep = nt; dt = dt_; dt_factor = dtf; dt_constant = dtc;
+  input.vars["time"] = Var("time", atime); input.vars["timestep"] = Var("timestep", (double)ntimestep); input.vars["dt"] = Var("dt", dt);
+  check(kml_set_dt(ctx, dt));
 }
 
 // Material::add_EOS + EOS ctors (src/material.cpp:94-123, src/eos_linear.cpp, src/eos_shock.cpp:30-82, src/eos_fluid.cpp)

@@ -4,6 +4,7 @@
 // (node counts, particle lattice, group masks) is restated from the reference with
 // file:line citations; the per-step work is delegated to the C ABI in include/kml.h.
 #pragma once
+#include <istream>
 #include <ostream>
 #include "../../include/kml.h"
 #include "input.h"
@@ -123,8 +124,11 @@ public:
   int every_log = 1 /* src/output.cpp:48 */; std::vector<std::string> log_fields{"step", "dt", "time"}; int64_t next_log = 0;
   std::vector<Dump> dumps; std::ofstream logfile; bool quiet = false;
   int restart_every = 0; int64_t next_restart = 0; std::string restart_name; // Output::create_restart, src/output.cpp:323-350
+  bool restarted_TL = false;                                                 // read_restart of a total-Lagrangian run (see Sim::read_restart)
   std::vector<std::string> additional_args;                                  // Update::additional_args (CPDI style), src/update.cpp:189-194
   void write_restart(const std::string &pattern);                            // WriteRestart::write, src/write_restart.cpp:51-88
+  void read_restart(const std::string &pattern);                             // ReadRestart::command, src/read_restart.cpp:36-83
+  std::unique_ptr<Fix> fix_from_restart(const std::string &id, const std::string &style, int igroup, std::istream &is); // Modify::read_restart
 
   // ---- device ----
   kml_ctx *ctx = nullptr; int device = 0;
