@@ -61,3 +61,23 @@ def test_cell_kernels_agree_with_atomic_scatter(cuda_lib):
         assert err <= 1e-11, (f[0], err)
     assert abs(a.state()["dt"] - b.state()["dt"]) <= 1e-12 * b.state()["dt"]
     a.close(); b.close()
+
+
+def test_restart_files_through_the_cuda_engine(cuda_lib, oracle_lib, tmp_path):
+    """restart(N, file) with the CUDA engine behind the host, then read_restart of that file by the CUDA engine and by the oracle:
+    both continue to the same state (1e-10), and the continued CUDA run agrees with the uninterrupted one."""
+    from common import compare_snaps, FIELDS
+    script = block((6, 6, 6), "musl")
+    e = Engine(cuda_lib)
+    e.script(script + "\nrestart(10, %s/rst-*.restart)\nrun(20)\n" % tmp_path)
+    straight = e.snapshot(FIELDS)
+    e.close()
+    snaps = {}
+    for label, lib in (("cuda", cuda_lib), ("oracle", oracle_lib)):
+        c = Engine(lib)
+        c.script("read_restart(%s/rst-10.restart)\nrun(10)\n" % tmp_path)
+        assert c.state()["ntimestep"] == 20
+        snaps[label] = c.snapshot(FIELDS)
+        c.close()
+    compare_snaps(snaps["cuda"], snaps["oracle"], 1e-10)
+    compare_snaps(snaps["cuda"], straight, 1e-9)
