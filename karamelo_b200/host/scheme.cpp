@@ -297,6 +297,38 @@ struct FixEnergy : Fix {
   }
 };
 
+// FixChecksolution, reference src/fix_check_solution.cpp:104-200: on output steps, the volume-weighted L2 distance between the particle
+// displacements x - x0 and the given u(x0, y0, z0, time): <id>_s = sqrt(sum / vtot) now, <id>_x and <id>_y the time integrals of the error
+// and of |u|^2, <id>_z = sqrt(<id>_x / <id>_y)
+struct FixCheckSolution : Fix {
+  bool set[3] = {false, false, false}; Var val[3];
+  void write_restart(std::ostream &os) const override { rput_sets(os, set, val, nullptr); } // src/fix_check_solution.cpp:202-240
+  void final_integrate(Sim &s) override {
+    bool due = s.ntimestep == s.next_log || s.ntimestep == s.nsteps;
+    for (auto &d : s.dumps) due = due || d.next == s.ntimestep;
+    if (!due) return;
+    double err[3] = {0, 0, 0}, uth[3] = {0, 0, 0}, vtot = 0; // (the reference leaves vtot uninitialised when the group names one solid)
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      vtot += S.vtot;
+      std::vector<double> x(3 * S.np), vol0(S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_VOL0, vol0.data()));
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(S.mask[ip] & groupbit)) continue;
+        s.input.vars["x0"] = Var("x0", S.x0[ip][0]); s.input.vars["y0"] = Var("y0", S.x0[ip][1]); s.input.vars["z0"] = Var("z0", S.x0[ip][2]);
+        for (int d = 0; d < 3; d++) if (set[d]) {
+          const double u = val[d].result(&s.input), e = u - (x[3 * ip + d] - S.x0[ip][d]);
+          err[d] += vol0[ip] * (e * e); uth[d] += vol0[ip] * u * u;
+        }
+      }
+    });
+    const double e = err[0] + err[1] + err[2], u = uth[0] + uth[1] + uth[2];
+    s.input.vars[id + "_s"] = Var(id + "_s", sqrt(e / vtot));
+    s.input.vars[id + "_x"] = Var(id + "_x", s.input.vars[id + "_x"].result() + s.dt * e);
+    s.input.vars[id + "_y"] = Var(id + "_y", s.input.vars[id + "_y"].result() + s.dt * u);
+    s.input.vars[id + "_z"] = Var(id + "_z", sqrt(s.input.vars[id + "_x"].result() / s.input.vars[id + "_y"].result()));
+  }
+};
+
 // FixContactHertz / FixContactMinPenetration, reference src/fix_contact_hertz.cpp, src/fix_contact_min_penetration.cpp
 struct FixContact : Fix {
   void write_restart(std::ostream &os) const override { rput(os, solid1); rput(os, solid2); if (!hertz) rput(os, mu); } // src/fix_contact_hertz.cpp:204-207, src/fix_contact_min_penetration.cpp:261-265
@@ -371,6 +403,7 @@ std::unique_ptr<Fix> Sim::fix_from_restart(const std::string &id, const std::str
   else if (style == "contact/hertz" || style == "contact/minimize_penetration") {
     auto f = new FixContact(); fix.reset(f); f->hertz = style == "contact/hertz"; get(f->solid1); get(f->solid2); if (!f->hertz) get(f->mu); f->mask = INITIAL_INTEGRATE;
   }
+  else if (style == "check_solution") { auto f = new FixCheckSolution(); fix.reset(f); get_sets(f->set, f->val, nullptr); f->mask = FINAL_INTEGRATE; }
   else if (style == "initial_velocity_particles") { fix.reset(new FixInitialVelocityParticles()); fix->mask = INITIAL_INTEGRATE; }   // nothing stored: these act at step 1 only
   else if (style == "initial_stress") { fix.reset(new FixInitialStress()); fix->mask = INITIAL_INTEGRATE; }
   else if (style == "initial_velocity_nodes") { fix.reset(new FixInitialVelocityNodes()); fix->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID; }
@@ -453,6 +486,12 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
     if (gpon[f->igroup] != "nodes") fatal("fix_initial_velocity_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
     for (int d = 0; d < 3; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
     f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
+  } else if (style == "check_solution") {
+    auto f = new FixCheckSolution(); fix.reset(f); group_of(*f);
+    if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_check_solution: requires at least " + std::to_string(3 + dimension) + " arguments. " + std::to_string(a.size()) + " received.\n");
+    if (gpon[f->igroup] != "nodes" && gpon[f->igroup] != "all") fatal("_check_solution needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    for (int d = 0; d < dimension; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
+    f->mask = FINAL_INTEGRATE;
   } else if (style == "body_force") {
     auto f = new FixBodyForce(); fix.reset(f); group_of(*f);
     if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_body_force.\n");

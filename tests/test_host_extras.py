@@ -101,3 +101,12 @@ def test_delete_particles_keeps_the_reference_order(tl):
     assert rc_r == 0 and rc_o == 0, out_o[-400:]
     same_log(out_r, out_o)
     assert len(files_r) == 2 and files_r == files_o
+
+
+def test_fix_check_solution():
+    # src/fix_check_solution.cpp:104-200; the "all" group, where the reference initialises its total volume
+    text = two_disks("musl") + ("fix(chk, check_solution, all, 0.1*time*(1+x0), 0.08*time)\n"
+                                "log_modify(custom, step, dt, time, chk_s, chk_x, chk_y, chk_z)\nlog(5)\nrun(20)\n")
+    (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
