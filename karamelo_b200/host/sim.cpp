@@ -379,6 +379,22 @@ struct Sphere : Region {
 };
 } // namespace
 
+namespace {
+// Union / Intersection / Difference of earlier regions (src/region_union.cpp, src/region_intersection.cpp, src/region_difference.cpp)
+struct Composite : Region {
+  int kind = 0; // 0 union, 1 intersection, 2 difference
+  std::vector<int> ir; const std::vector<std::unique_ptr<Region>> *all = nullptr;
+  int inside(double x, double y, double z) const override {
+    if (kind == 0) { for (int i : ir) if ((*all)[i]->inside(x, y, z) == 1) return 1; return 0; }
+    if (kind == 1) { for (int i : ir) if ((*all)[i]->inside(x, y, z) == 0) return 0; return 1; }
+    return (*all)[ir[0]]->inside(x, y, z) == 1 && (*all)[ir[1]]->inside(x, y, z) == 0;
+  }
+  void write_restart(std::ostream &os) const override { // src/region_union.cpp:98-110 (the three styles share the layout)
+    const size_t n = ir.size(); put(os, n); for (int i : ir) put(os, i); for (int k = 0; k < 6; k++) put(os, lim[k]);
+  }
+};
+} // namespace
+
 // Domain::add_region + Block_/Cylinder/Sphere constructors (src/domain.cpp:76-98, src/region_block.cpp:28-139,
 // src/region_cylinder.cpp:30-134, src/region_sphere.cpp:30-118)
 Var Sim::cmd_region(std::vector<std::string> &a) {
@@ -433,6 +449,20 @@ Var Sim::cmd_region(std::vector<std::string> &a) {
       for (int d = 0; d < (dim == 3 ? 3 : 2); d++) { if (boxlo[d] > l[2 * d]) boxlo[d] = l[2 * d]; if (boxhi[d] < l[2 * d + 1]) boxhi[d] = l[2 * d + 1]; }
     } else {
       for (int d = 0; d < (dim == 3 ? 3 : 2); d++) if (boxlo[d] > l[2 * d]) l[2 * d] = boxlo[d];
+    }
+  } else if (a[1] == "union" || a[1] == "intersection" || a[1] == "difference") {
+    auto c = new Composite(); reg.reset(c); c->all = &regions; c->kind = a[1] == "union" ? 0 : (a[1] == "intersection" ? 1 : 2);
+    if (a.size() < 4) fatal("Error: region_" + a[1] + " command not enough arguments\n");
+    if (c->kind == 2 && a.size() > 4) fatal("Error: region_difference command too many arguments\n");
+    double *l = c->lim;
+    for (int k = 0; k < 6; k++) l[k] = (c->kind == 0) == (k % 2 == 0) ? BIG : -BIG; // union starts from an empty box, intersection from everything
+    for (size_t i = 2; i < a.size(); i++) {
+      const int r = find_region(a[i]);
+      if (r == -1) fatal("Error: region " + a[i] + " does not exist.\n");
+      c->ir.push_back(r);
+      const double *m = regions[r]->lim;
+      if (c->kind == 2) { if (i == 2) for (int k = 0; k < 6; k++) l[k] = m[k]; continue; } // the box of the first region
+      for (int k = 0; k < 6; k++) { const bool lo = k % 2 == 0; if (c->kind == 0 ? (lo ? l[k] > m[k] : l[k] < m[k]) : (lo ? l[k] < m[k] : l[k] > m[k])) l[k] = m[k]; }
     }
   } else fatal("Unknown region style " + a[1] + "\n");
   reg->id = a[0]; reg->style = a[1];
@@ -504,6 +534,10 @@ void Sim::read_restart(const std::string &pattern) {
       auto sp = new Sphere(); reg.reset(sp);
       sp->c1 = rget<double>(is); sp->c2 = rget<double>(is); sp->c3 = rget<double>(is); sp->R = rget<double>(is); for (double &v : sp->lim) v = rget<double>(is);
       sp->RSq = sp->R * sp->R;
+    } else if (style == "union" || style == "intersection" || style == "difference") {
+      auto c = new Composite(); reg.reset(c); c->all = &regions; c->kind = style == "union" ? 0 : (style == "intersection" ? 1 : 2);
+      c->ir.resize(rget<size_t>(is)); for (int &r : c->ir) r = rget<int>(is);
+      for (double &v : c->lim) v = rget<double>(is);
     } else fatal("read_restart: region style " + style + " is not supported\n");
     reg->id = id; reg->style = style; regions.push_back(std::move(reg));
   }

@@ -110,3 +110,39 @@ def test_fix_check_solution():
     (rc_r, out_r, _), (rc_o, out_o, _) = run_both(text)
     assert rc_r == 0 and rc_o == 0, out_o[-400:]
     same_log(out_r, out_o)
+
+
+def test_composite_regions():
+    # src/region_union.cpp, src/region_intersection.cpp, src/region_difference.cpp: a solid cut out of nested set operations
+    text = """
+E   = 1e+3
+nu  = 0.3
+rho = 1000
+L   = 1
+hL  = 0.5*L
+method(ulmpm, FLIP, cubic-spline, 0.99)
+N        = 20
+cellsize = L/N
+dimension(2,-hL, hL, -hL, hL, cellsize)
+region(rA, cylinder, -0.15, -0.1, 0.2)
+region(rB, block, -0.3, 0.1, -0.1, 0.2)
+region(rC, cylinder, 0.2, 0.15, 0.15)
+region(rHole, cylinder, -0.1, 0.0, 0.07)
+region(rI, intersection, rA, rB)
+region(rD, difference, rI, rHole)
+region(rU, union, rD, rC)
+material(mat1, linear, rho, E, nu)
+solid(s1, region, rU, 2, mat1, cellsize, 0)
+group(g1, particles, region, rU, solid, s1)
+fix(v0, initial_velocity_particles, g1, 0.05, -0.1, NULL)
+dt_factor(0.3)
+compute(Ek, kinetic_energy, all)
+log_modify(custom, step, dt, time, Ek)
+log(10)
+dump(d1, all, particle, 20, dump_p.*.LAMMPS, x, y, vx, s11)
+run(20)
+"""
+    (rc_r, out_r, files_r), (rc_o, out_o, files_o) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+    assert len(files_r) == 1 and files_r == files_o
