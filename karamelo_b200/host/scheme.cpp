@@ -329,6 +329,43 @@ struct FixCheckSolution : Fix {
   }
 };
 
+// FixCuttingTool, reference src/fix_cutting_tool.cpp:118-285 (2-D): a wedge with its tip at (x_t, y_t) and edges through A and B pushes
+// the particles inside it out through the nearer edge with the penalty force K G p (1 - damage) n, added to the particle body force
+struct FixCuttingTool : Fix {
+  double K = 0; Var v[10]; // x_t, y_t, z_t, vt_x, vt_y, vt_z, x_A, y_A, x_B, y_B
+  void write_restart(std::ostream &os) const override { rput(os, K); for (const Var &x : v) rput_var(os, x); } // src/fix_cutting_tool.cpp:287-300
+  void initial_integrate(Sim &s) override {
+    if (s.dimension == 3) fatal("fix_cuttingtool not supported in 3D\n");
+    double q[10]; for (int i = 0; i < 10; i++) q[i] = v[i].result(&s.input);
+    const double xt[2] = {q[0], q[1]}, xA[2] = {q[6], q[7]}, xB[2] = {q[8], q[9]};
+    double l1[4] = {xA[1] - xt[1], -xA[0] + xt[0], xt[1] * xA[0] - xt[0] * xA[1], 0}, l2[4] = {xB[1] - xt[1], -xB[0] + xt[0], xt[1] * xB[0] - xt[0] * xB[1], 0};
+    l1[3] = 1.0 / sqrt(l1[0] * l1[0] + l1[1] * l1[1]); l2[3] = 1.0 / sqrt(l2[0] * l2[0] + l2[1] * l2[1]);
+    if (l1[0] * xB[0] + l1[1] * xB[1] + l1[2] < 0) for (int k = 0; k < 3; k++) l1[k] *= -1;
+    if (l2[0] * xA[0] + l2[1] * xA[1] + l2[2] < 0) for (int k = 0; k < 3; k++) l2[k] *= -1;
+    const double n1[2] = {l1[0] * -l1[3], l1[1] * -l1[3]}, n2[2] = {l2[0] * -l2[3], l2[1] * -l2[3]};
+    double ftot[3] = {0, 0, 0};
+    // with a group restricted to one solid the reference adds the line's y coefficient where the constant belongs (:222-223); kept
+    const bool one = s.gsolid[igroup] != -1; const double k1 = one ? l1[1] : l1[2], k2 = one ? l2[1] : l2[2];
+    for_group_solids(s, igroup, [&](SolidH &S) {
+      std::vector<double> x(3 * S.np), mass(S.np), dmg(S.np), mbp(3 * S.np);
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_MASS, mass.data()));
+      s.check(kml_solid_download(s.ctx, S.dev, KML_P_DAMAGE, dmg.data())); s.check(kml_solid_download(s.ctx, S.dev, KML_P_MBP, mbp.data()));
+      const double G = s.materials[S.mat].km.G;
+      for (int64_t ip = 0; ip < S.np; ip++) {
+        if (!(mass[ip] > 0) || !(S.mask[ip] & groupbit)) continue;
+        const double c1 = l1[0] * x[3 * ip] + l1[1] * x[3 * ip + 1] + k1, c2 = l2[0] * x[3 * ip] + l2[1] * x[3 * ip + 1] + k2;
+        if (!(c1 >= 0 && c2 >= 0)) continue;
+        const double p1 = fabs(c1 * l1[3]), p2 = fabs(c2 * l2[3]);
+        const double p = p1 < p2 ? p1 : p2; const double *n = p1 < p2 ? n1 : n2;
+        const double fmag = K * G * p * (1.0 - dmg[ip]);
+        for (int d = 0; d < 2; d++) { const double f = fmag * n[d]; mbp[3 * ip + d] += f; ftot[d] += f; }
+      }
+      s.check(kml_solid_upload(s.ctx, S.dev, KML_P_MBP, mbp.data()));
+    });
+    s.input.vars[id + "_x"] = Var(id + "_x", ftot[0]); s.input.vars[id + "_y"] = Var(id + "_y", ftot[1]); s.input.vars[id + "_z"] = Var(id + "_z", ftot[2]);
+  }
+};
+
 // FixContactHertz / FixContactMinPenetration, reference src/fix_contact_hertz.cpp, src/fix_contact_min_penetration.cpp
 struct FixContact : Fix {
   void write_restart(std::ostream &os) const override { rput(os, solid1); rput(os, solid2); if (!hertz) rput(os, mu); } // src/fix_contact_hertz.cpp:204-207, src/fix_contact_min_penetration.cpp:261-265
@@ -404,6 +441,7 @@ std::unique_ptr<Fix> Sim::fix_from_restart(const std::string &id, const std::str
     auto f = new FixContact(); fix.reset(f); f->hertz = style == "contact/hertz"; get(f->solid1); get(f->solid2); if (!f->hertz) get(f->mu); f->mask = INITIAL_INTEGRATE;
   }
   else if (style == "check_solution") { auto f = new FixCheckSolution(); fix.reset(f); get_sets(f->set, f->val, nullptr); f->mask = FINAL_INTEGRATE; }
+  else if (style == "cuttingtool") { auto f = new FixCuttingTool(); fix.reset(f); get(f->K); for (Var &x : f->v) x = get_var(); f->mask = INITIAL_INTEGRATE; }
   else if (style == "initial_velocity_particles") { fix.reset(new FixInitialVelocityParticles()); fix->mask = INITIAL_INTEGRATE; }   // nothing stored: these act at step 1 only
   else if (style == "initial_stress") { fix.reset(new FixInitialStress()); fix->mask = INITIAL_INTEGRATE; }
   else if (style == "initial_velocity_nodes") { fix.reset(new FixInitialVelocityNodes()); fix->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID; }
@@ -486,6 +524,13 @@ Var Sim::cmd_fix(std::vector<std::string> &a) {
     if (gpon[f->igroup] != "nodes") fatal("fix_initial_velocity_nodes needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
     for (int d = 0; d < 3; d++) if (a[3 + d] != "NULL") { f->val[d] = input.parsev(a[3 + d]); f->set[d] = true; }
     f->mask = POST_UPDATE_GRID_STATE | POST_VELOCITIES_TO_GRID;
+  } else if (style == "cuttingtool") {
+    auto f = new FixCuttingTool(); fix.reset(f); group_of(*f);
+    if (a.size() < 14) fatal("Error: not enough arguments.\nUsage: fix(fix-ID, cuttingtool, group, K, x_tip, y_tip, z_tip, vx_tip, vy_tip, vz_tip, xA, yA, xB, yB)\n");
+    if (gpon[f->igroup] != "particles" && gpon[f->igroup] != "all") fatal("fix_cuttingtool needs to be given a group of nodes" + gpon[f->igroup] + ", " + a[2] + " is a group of " + gpon[f->igroup] + ".\n");
+    f->K = input.parsev(a[3]).result(&input);
+    for (int i = 0; i < 10; i++) f->v[i] = input.parsev(a[4 + i]);
+    f->mask = INITIAL_INTEGRATE;
   } else if (style == "check_solution") {
     auto f = new FixCheckSolution(); fix.reset(f); group_of(*f);
     if (a.size() < (size_t)(3 + dimension)) fatal("Error: too few arguments for fix_check_solution: requires at least " + std::to_string(3 + dimension) + " arguments. " + std::to_string(a.size()) + " received.\n");

@@ -146,3 +146,20 @@ run(20)
     assert rc_r == 0 and rc_o == 0, out_o[-400:]
     same_log(out_r, out_o)
     assert len(files_r) == 1 and files_r == files_o
+
+
+@pytest.mark.parametrize("group,x0", [("all", 0.31), ("gBall2", 0.36)])
+def test_fix_cuttingtool(group, x0):
+    # src/fix_cutting_tool.cpp:118-285, both branches: "all" and a group restricted to one solid (where the reference adds the line's y
+    # coefficient in place of its constant, :222-223 - mirrored)
+    text = two_disks("musl", method="method(ulmpm, FLIP, cubic-spline, 0.99)") + (
+        "xt = %g-0.1*time\nyt = %g-0.1*time\n"
+        "fix(ftool, cuttingtool, %s, 0.05, xt, yt, 0, -0.1, -0.1, 0, xt+0.3, yt+0.05, xt+0.05, yt+0.3)\n"
+        "log_modify(custom, step, dt, time, ftool_x, ftool_y)\nlog(10)\n"
+        "dump(d1, all, particle, 30, dump_p.*.LAMMPS, x, y, vx, vy, s11)\nrun(30)\n" % (x0, x0, group))
+    (rc_r, out_r, files_r), (rc_o, out_o, files_o) = run_both(text)
+    assert rc_r == 0 and rc_o == 0, out_o[-400:]
+    same_log(out_r, out_o)
+    rows = log_rows(out_o)
+    assert abs(rows[-1][3]) > 0.1, "the tool never touched the disk"
+    assert len(files_r) == 1 and files_r == files_o
