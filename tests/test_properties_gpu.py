@@ -81,3 +81,24 @@ def test_restart_files_through_the_cuda_engine(cuda_lib, oracle_lib, tmp_path):
         c.close()
     compare_snaps(snaps["cuda"], snaps["oracle"], 1e-10)
     compare_snaps(snaps["cuda"], straight, 1e-9)
+
+
+def test_download_upload_fixes_through_the_cuda_engine(cuda_lib, oracle_lib):
+    """fix cuttingtool (particle body force through download / upload every step) and fix check_solution (reads positions on output steps)
+    drive the CUDA engine exactly like the oracle: same state after 30 steps (1e-10), same published totals."""
+    from cases import two_disks
+    from common import compare_snaps, FIELDS
+    script = two_disks("musl", method="method(ulmpm, FLIP, cubic-spline, 0.99)") + (
+        "xt = 0.31-0.1*time\nyt = 0.31-0.1*time\n"
+        "fix(ftool, cuttingtool, all, 0.05, xt, yt, 0, -0.1, -0.1, 0, xt+0.3, yt+0.05, xt+0.05, yt+0.3)\n"
+        "fix(chk, check_solution, all, 0.1*time*(1+x0), 0.08*time)\nlog(10)\nrun(30)\n")
+    out = {}
+    for label, lib in (("cuda", cuda_lib), ("oracle", oracle_lib)):
+        e = Engine(lib)
+        e.script(script)
+        out[label] = (e.snapshot(FIELDS), [e.var(v) for v in ("ftool_x", "ftool_y", "chk_s", "chk_z")])
+        e.close()
+    compare_snaps(out["cuda"][0], out["oracle"][0], 1e-10)
+    for a, b in zip(out["cuda"][1], out["oracle"][1]):
+        assert abs(a - b) <= 1e-9 * max(abs(b), 1e-30), (out["cuda"][1], out["oracle"][1])
+    assert abs(out["oracle"][1][0]) > 0.1
