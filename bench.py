@@ -28,7 +28,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FULL_CELLS = (248, 250, 202)  # 100 192 000 particles in a 256 x 258 x 210 box
 # algorithmic bytes per particle-step (fp64 SoA, every array once per kernel)
-ALGO_BYTES = {"rebin": 80, "p2g": 158, "grid": 18, "g2p": 103, "v2g": 64, "stress": 436}
+# rebin: SURVEY budgets 80 B for a radix sort of (key, index) pairs; the counting sort that is actually run moves x (24 B read), the cell key and
+# the rank inside the cell (4 + 4 B written, then read back) and the order entry (4 B written) + the cell offset it gathers (~4 B) = 48 B
+ALGO_BYTES = {"rebin": 48, "p2g": 158, "grid": 18, "g2p": 103, "v2g": 64, "stress": 436}
 # minimal FP64 instructions per particle and stage: the second roof of the fp64 stencil kernels
 FP64_INSTR = {"p2g": 1000, "g2p": 580, "v2g": 340, "stress": 960}
 FP64_LANES_PER_SM_CLK = 64   # B200: 64 DFMA / clk / SM (ncu sm__inst_executed_pipe_fp64 peak = 0.5 warp-inst / clk / sub-partition)
@@ -189,6 +191,59 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+CHECK_FIELDS = ("PTAG", "X", "V", "SIGMA", "EFF_PLASTIC_STRAIN")
+CHECK_STRIDE = 1000
+
+
+def _sample(eng):
+    """particles whose tag is 1 mod CHECK_STRIDE: {field: rows}"""
+    from karamelo_b200.api import P
+    tag = eng.download(0, P.PTAG)
+    keep = np.nonzero((tag - 1) % CHECK_STRIDE == 0)[0]
+    out = {"PTAG": tag[keep]}
+    for f in CHECK_FIELDS[1:]:
+        out[f] = eng.download(0, getattr(P, f))[keep]
+    return out
+
+
+def check_against_single_gpu(eng, cells, steps_done, rank, world, local, dist):
+    """SCALE carries correctness: after the timed steps every rank contributes its particles with tag = 1 mod 1000; rank 0 then runs the
+    SAME block undecomposed on its own GPU for the same number of steps and compares (tags exact, fields within 1e-10 of the field
+    magnitude - the north_star's tolerance).  The other ranks wait at a barrier."""
+    from karamelo_b200.api import Engine, P
+    mine = _sample(eng)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    res = None
+    if rank == 0:
+        got = {f: np.concatenate([p[f] for p in parts]) for f in CHECK_FIELDS}
+        order = np.argsort(got["PTAG"], kind="stable")
+        got = {f: v[order] for f, v in got.items()}
+        t0 = time.perf_counter()
+        ref_eng = Engine(None, device=local)
+        ref_eng.script(block_script(cells, velocity_fix=False))
+        x = ref_eng.download(0, P.X)
+        ref_eng.upload(0, P.V, squeeze_velocity(x, cells))
+        del x
+        ref_eng.line("run(%d)" % steps_done)
+        ref = _sample(ref_eng)
+        ref_flags = ref_eng.error_flags()
+        ref_eng.close()
+        order = np.argsort(ref["PTAG"], kind="stable")
+        ref = {f: v[order] for f, v in ref.items()}
+        tags_ok = bool(got["PTAG"].shape == ref["PTAG"].shape and (got["PTAG"] == ref["PTAG"]).all())
+        worst = {}
+        if tags_ok:
+            for f in CHECK_FIELDS[1:]:
+                scale = max(float(np.abs(ref[f]).max()), 1e-300)
+                worst[f] = float(np.abs(got[f] - ref[f]).max()) / scale
+        res = {"ok": bool(tags_ok and ref_flags == 0 and all(v <= 1e-10 for v in worst.values())), "tags_exact": tags_ok, "worst_rel": worst,
+               "tolerance": 1e-10, "sample": "%d particles (tag = 1 mod %d)" % (len(ref["PTAG"]), CHECK_STRIDE), "steps": steps_done,
+               "against": "the same block, undecomposed, on rank 0's GPU", "seconds": round(time.perf_counter() - t0, 1)}
+    dist.barrier()
+    return res
+
+
 def run_ours(args):
     import torch
     from karamelo_b200 import slab
@@ -220,9 +275,14 @@ def run_ours(args):
     setup_s = time.perf_counter() - t0
     npart = eng.slab_info(0)["np_global"] if world > 1 else np_local
 
-    eng.line("run(%d)" % W)           # warm-up (>= 3 steps); includes step 1 with dt = 1e-16 like the reference
+    # Warm-up: W steps as asked, but never fewer than `prestrain` (default 40): the block yields at step ~25 (sigma_y / 3G = 0.26 % at
+    # a = 2.5e-4 and dt ~ 0.42), and the stress kernel is slower on the radial-return branch - the timed steps are all taken in the
+    # plastic steady state whatever W the caller passes (round 1 timed the elastic steps 6..25 and profiled plastic ones).
+    W_eff = max(W, args.prestrain)
+    eng.line("run(%d)" % W_eff)       # includes step 1 with dt = 1e-16 like the reference
     eng.stage_times(reset=True)
     sampler = ClockSampler(local)
+    eng.profile(True)                 # event pairs around every stage, recorded inside the timed region and read after it (no synchronisation per stage)
     barrier()
     if rank == 0:
         sampler.sample()
@@ -234,17 +294,14 @@ def run_ours(args):
     if rank == 0:
         sampler.sample()
     clocks = sampler.summary()
-    ms = max_over_ranks(ms)
-    counts = eng.stage_times(reset=True)
-    launches = int(sum(v[1] for v in counts.values()))
-    value = npart * K / (ms * 1e-3)
-
-    # per-stage device time (events around every stage, a few extra steps) -> rooflines of the stage kernels
-    eng.profile(True)
-    eng.line("run(3)")
-    st = eng.stage_times(reset=True)
+    st = eng.stage_times(reset=True)  # the same K steps
     eng.profile(False)
-    stage_ms = {k: max_over_ranks(v[0] / 3) for k, v in st.items()}
+    ms_local = ms
+    ms = max_over_ranks(ms)
+    launches = int(sum(v[1] for v in st.values()))
+    value = npart * K / (ms * 1e-3)
+    stage_ms = {k: max_over_ranks(v[0] / K) for k, v in st.items()}
+    stage_sum_local = sum(v[0] for v in st.values()) / K
     np_max = int(max_over_ranks(np_local))
     peak, peak_src = measured_peak()
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -262,7 +319,23 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "particles_per_launch": np_max,
                 "second_roof": "FP64 pipe (64 DFMA/clk/SM nominal = 18.6 T DFMA/s at 1965 MHz; tools/fp64_peak.cu measures 18.1 T, profiles/r1l_fp64_peak_microbenchmark.txt): "
                                "fp64_frac = minimal FP64 instructions / (time x nominal pipe rate), DESIGN.md section 3",
-                "per_stage": per_stage}
+                "per_stage": per_stage,
+                "stage_protocol": "CUDA event pairs around every stage INSIDE the timed region, read after the final synchronisation; per stage the max over ranks",
+                "stage_sum_ms_rank0": round(stage_sum_local, 4), "ms_per_step_rank0": round(ms_local / K, 4),
+                "comm_ms": {k: round(stage_ms.get(k, 0.0), 4) for k in ("halo", "migrate", "dt")}}
+
+    # regime of the timed steps + (N > 1) parity of the decomposed run with a single-GPU run of the same number of steps
+    steps_done = W_eff + K
+    eps = eng.download(0, P.EFF_PLASTIC_STRAIN)
+    n_plastic = int((eps > 0).sum())
+    del eps
+    parity = None
+    if world > 1:
+        tot = torch.tensor([n_plastic], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        n_plastic = int(tot.item())
+        if not args.no_check:
+            parity = check_against_single_gpu(eng, cells, steps_done, rank, world, local, dist)
 
     # end to end through the public API with HOST buffers: every step uploads the step's particle inputs from pinned
     # host memory (kml_solid_upload), runs one step, downloads the results (kml_solid_download)
@@ -303,13 +376,17 @@ def run_ours(args):
     if rank == 0:
         cb = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(tuple(args.ref_cells))
         cfg = {"workload": WORKLOAD, "cells": list(cells), "particles": npart, "particles_per_cell": 8, "l2": "inputs >> L2 (no flush needed)",
-               "setup_s": round(setup_s, 1)}
+               "setup_s": round(setup_s, 1), "warmup_effective": W_eff,
+               "regime": "plastic steady state: %.1f %% of the particles have yielded when the timed region ends (step %d)" % (100.0 * n_plastic / npart, steps_done)}
         if world > 1:
             cfg["parallelism"] = "x-slab x%d, NCCL halo sums + particle migration + dt all-reduce" % world
             cfg["particles_per_rank"] = nps
         line = {"metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks, "gpu_launches": launches, "error_flags": flags}
+        if parity is not None:
+            line["parity_ok"] = parity["ok"]
+            line["parity"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -325,6 +402,8 @@ def main():
     ap.add_argument("--cells", type=int, nargs=3, default=list(FULL_CELLS))
     ap.add_argument("--ref-cells", type=int, nargs=3, default=[24, 24, 24])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--prestrain", type=int, default=40, help="minimum number of untimed steps before the timed region (plastic steady state)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the comparison of a 1/1000 particle sample with a single-GPU run of the same steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -102,6 +102,7 @@ typedef struct kml_solid_desc {
   int64_t np;       /* particles owned by this rank */
   int64_t capacity; /* >= np; room for migration (0 = np) */
   int grid;         /* grid id from kml_grid_create */
+  int np_per_cell;  /* Solid::np_per_cell (src/solid.cpp:2027): selects the APIC inertia tensor of linear shape functions (src/solid.cpp:1453-1460); 0 = 2 */
   kml_material mat;
 } kml_solid_desc;
 
@@ -179,6 +180,13 @@ int kml_grid_download(kml_ctx *ctx, int grid_id, int field, void *dst);
 /* Solid::Solid / Solid::grow, src/solid.cpp:59-168,240-315: allocate device state. */
 int kml_solid_create(kml_ctx *ctx, const kml_solid_desc *desc, int *solid_id);
 int kml_solid_np(kml_ctx *ctx, int solid_id, int64_t *np);
+/* Changes whenever the solid's particle set or order may have changed behind a caller's back (upload of tags / reference positions /
+ * masks, delete_particles, migration between slabs, populate): hosts that mirror ptag / x0 / mask compare it before using the mirror. */
+int kml_solid_generation(kml_ctx *ctx, int solid_id, uint64_t *generation);
+/* The reference stores v_update, a and f = a m of every particle during grid_to_points (src/solid.cpp:576-635); the engine derives them in
+ * registers and drops them.  After this call they are kept (24 + 24 bytes per particle and step) so that KML_P_V_UPDATE / KML_P_A / KML_P_F
+ * can be downloaded (Group::internal_force / external_force, src/group.cpp:340-470; dump fields).  Must be called before the first step. */
+int kml_keep_particle_acceleration(kml_ctx *ctx);
 int kml_solid_upload(kml_ctx *ctx, int solid_id, int field, const void *src);
 int kml_solid_download(kml_ctx *ctx, int solid_id, int field, void *dst);
 /* DeleteParticles::command, src/delete_particles.cpp:51-80: dlist[np] flags the particles to remove.  For k ascending a flagged particle
@@ -270,9 +278,11 @@ int kml_comm_init(kml_ctx *ctx, const void *id128);
 
 /* ---- measurement ------------------------------------------------------------------------- */
 /* Per-stage device time (ms) accumulated with CUDA events on the context's stream since the last
- * reset: stage ids KML_STAGE_*.  Enabled with kml_profile(ctx, 1). */
+ * reset: stage ids KML_STAGE_*.  Enabled with kml_profile(ctx, 1).  The events are only recorded while the steps run and
+ * read here (one synchronisation), so the profile can stay on inside a timed region. */
 enum { KML_STAGE_REBIN = 0, KML_STAGE_P2G, KML_STAGE_GRID, KML_STAGE_G2P, KML_STAGE_V2G, KML_STAGE_STRESS,
-       KML_STAGE_CONTACT, KML_STAGE_OTHER, KML_STAGE_COUNT };
+       KML_STAGE_CONTACT, KML_STAGE_OTHER, KML_STAGE_HALO /* ghost-node sums between slabs */, KML_STAGE_MIGRATE /* exchange_particles */,
+       KML_STAGE_DT /* adjust_dt: reduction + readback */, KML_STAGE_COUNT };
 int kml_profile(kml_ctx *ctx, int enable);
 int kml_stage_times(kml_ctx *ctx, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset);
 /* CUDA-event bracket on the context's stream: start records an event, stop records a second one,

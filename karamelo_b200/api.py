@@ -66,7 +66,7 @@ class N:  # node fields (kml.h KML_N_*)
     QINT = (13, np.float64, ())
 
 
-STAGES = ["rebin", "p2g", "grid", "g2p", "v2g", "stress", "contact", "other"]
+STAGES = ["rebin", "p2g", "grid", "g2p", "v2g", "stress", "contact", "other", "halo", "migrate", "dt"]
 
 
 def load_host_library(path=None):

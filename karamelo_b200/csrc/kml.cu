@@ -34,6 +34,8 @@ struct Solid {
   CpdiDev cp{}; double *cpbuf = nullptr; int *cpibuf = nullptr; // CPDI neighbour lists and particle domains
   double *red = nullptr;  // device: [0] max wave speed, [1] min_h_ratio
   double dtCFL = 1.0e22;
+  unsigned long long gen = 1; // kml_solid_generation
+  double *accbuf = nullptr;   // kml_keep_particle_acceleration: a_p, v_update_p
 };
 
 struct kml_ctx {
@@ -46,20 +48,25 @@ struct kml_ctx {
   bool tl_mass_done = false, tl_wf_done = false;
   bool has_rigid = false; // some solid is rigid (ULMPM::rigid_solids, src/ulmpm.cpp:98-99)
   bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
+  bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
-  bool profile = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
+  // Per-stage device time: event pairs are recorded around every stage and only READ in kml_stage_times (one synchronisation for the
+  // whole timed region), so profiling does not serialise the host against the device and the stage sum stays inside the step time.
+  bool profile = false; cudaEvent_t evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
+  struct Pair { int stage; cudaEvent_t a, b; };
+  std::vector<Pair> ev_pending; std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t ev_get() { if (ev_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
 };
 
 namespace {
 struct StageTimer {
-  kml_ctx *c; int stage;
-  StageTimer(kml_ctx *c_, int st) : c(c_), stage(st) { if (c->profile) cudaEventRecord(c->ev0, c->stream); }
-  ~StageTimer() {
-    if (c->profile) { cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1); float t = 0; cudaEventElapsedTime(&t, c->ev0, c->ev1); c->ms[stage] += t; }
-  }
+  kml_ctx *c; int stage; cudaEvent_t a = nullptr;
+  StageTimer(kml_ctx *c_, int st) : c(c_), stage(st) { if (c->profile) { a = c->ev_get(); cudaEventRecord(a, c->stream); } }
+  void stop() { if (a) { cudaEvent_t b = c->ev_get(); cudaEventRecord(b, c->stream); c->ev_pending.push_back({stage, a, b}); a = nullptr; } }
+  ~StageTimer() { stop(); }
 };
 StepParams step_params(kml_ctx *c) {
   StepParams sp; sp.dt = c->dt; sp.alpha = c->c.PIC_FLIP;
@@ -70,12 +77,13 @@ StepParams step_params(kml_ctx *c) {
   return sp;
 }
 
-// Solid::compute_inertia_tensor, src/solid.cpp:1440-1478: Di = k / cellsize^2 on the active dimensions (linear TL: the
-// reference distinguishes 1 and 2 particles per cell; the ABI carries no lattice information, 2 per cell is assumed)
-void fill_inertia(kml_ctx *c, const Grid *G, StepParams &sp) {
+// Solid::compute_inertia_tensor, src/solid.cpp:1440-1478: Di = k / cellsize^2 on the active dimensions (linear TL: 16/4 with one
+// particle per cell, 16/3 with two; other lattices are refused by kml_solid_create like the reference does)
+void fill_inertia(kml_ctx *c, const Grid *G, const Solid *S, StepParams &sp) {
   if (!c->apic) return;
   const double cs = 1.0 / (G->d.cellsize * G->d.cellsize);
-  const double k = c->c.shape_function == KML_SHAPE_LINEAR ? 16.0 / 3.0 : (c->c.shape_function == KML_SHAPE_CUBIC_SPLINE ? 3.0 : 4.0);
+  const double klin = S->d.np_per_cell == 1 ? 16.0 / 4.0 : 16.0 / 3.0;
+  const double k = c->c.shape_function == KML_SHAPE_LINEAR ? klin : (c->c.shape_function == KML_SHAPE_CUBIC_SPLINE ? 3.0 : 4.0);
   for (int d = 0; d < 3; d++) sp.Di[d] = d < c->c.dimension ? k * cs : 1.0;
 }
 
@@ -162,7 +170,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
   CU(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
   CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
-  CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
+  CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
   memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
   const char *e = getenv("KML_P2G");
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
@@ -183,14 +191,16 @@ int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
-  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); delete s; }
+  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); cudaFree(s->accbuf); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
     cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
   }
   cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaStreamDestroy(c->stream);
+  for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaStreamDestroy(c->stream);
   delete c; return 0;
 }
 int kml_synchronize(kml_ctx *c) { CU(cudaSetDevice(c->dev)); CU(cudaStreamSynchronize(c->stream)); return 0; }
@@ -309,12 +319,16 @@ int kml_grid_download(kml_ctx *c, int gid, int field, void *dst) {
 static const int SOLID_NDBL_UL = 3 * 6 + 6 + 6 + 9 + 11;
 static const int SOLID_NDBL_TL = SOLID_NDBL_UL + 18;
 
+static int alloc_acc(kml_ctx *c, Solid *S);
 int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaSetDevice(c->dev));
   const bool rigid_ = d->mat.rigid || d->mat.type == KML_MAT_RIGID;
   if (rigid_ && c->c.is_CPDI) return fail("kml: rigid solids with CPDI are not implemented in the CUDA engine");
   if (rigid_ && c->c.nranks > 1) return fail("kml: rigid solids are single-GPU in the CUDA engine (Grid::reduce_rigid_ghost_nodes is not reproduced)");
+  if (c->apic && c->c.shape_function == KML_SHAPE_LINEAR && d->np_per_cell != 0 && d->np_per_cell != 1 && d->np_per_cell != 2)
+    return fail("Number of particle per cell not supported with linear shape functions and APIC."); // src/solid.cpp:1453-1460
   Solid *S = new Solid(); S->d = *d; S->rigid = rigid_; if (rigid_) c->has_rigid = true; SolidDev &s = S->s;
+  for (int k = 0; k < 3; k++) { s.acc[k] = nullptr; s.vup[k] = nullptr; }
   s.np = d->np; S->cap = std::max<long long>(d->capacity, d->np);
   long long cap = (S->cap + 31) / 32 * 32;
   { const char *pad = getenv("KML_CAP_PAD"); if (pad && *pad) cap += atoll(pad) / 32 * 32; } // experiment: de-alias the SoA component stride
@@ -354,10 +368,28 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
     for (int k = 0; k < 2; k++) for (int d2 = 0; d2 < 2; d2++) { cp.rp[k][d2] = takep(cap); cp.rp0[k][d2] = takep(cap); }
     for (int k = 0; k < 4; k++) for (int d2 = 0; d2 < 2; d2++) { cp.xpc[k][d2] = takep(cap); cp.xpc0[k][d2] = takep(cap); }
   }
+  if (c->keep_acc && alloc_acc(c, S)) return 1;
   CU(cudaStreamSynchronize(c->stream));
   c->solids.push_back(S); *sid = (int)c->solids.size() - 1; return 0;
 }
 int kml_solid_np(kml_ctx *c, int sid, int64_t *np) { *np = c->solids[sid]->s.np; return 0; }
+int kml_solid_generation(kml_ctx *c, int sid, uint64_t *gen) { *gen = c->solids[sid]->gen; return 0; }
+
+static int alloc_acc(kml_ctx *c, Solid *S) {
+  if (S->accbuf) return 0;
+  CU(cudaMalloc(&S->accbuf, sizeof(double) * 6 * S->cap)); CU(cudaMemsetAsync(S->accbuf, 0, sizeof(double) * 6 * S->cap, c->stream));
+  for (int k = 0; k < 3; k++) { S->s.acc[k] = S->accbuf + (size_t)k * S->cap; S->s.vup[k] = S->accbuf + (size_t)(3 + k) * S->cap; }
+  return 0;
+}
+int kml_keep_particle_acceleration(kml_ctx *c) {
+  CU(cudaSetDevice(c->dev));
+  if (c->keep_acc) return 0;
+  if (c->steps_started > 0) return fail("kml: particle accelerations / forces (internal_force, external_force, dump fields) must be requested before the first step");
+  if (c->c.nranks > 1) return fail("kml: stored particle accelerations are single-GPU in the CUDA engine (they do not migrate between slabs)");
+  c->keep_acc = true;
+  for (Solid *S : c->solids) if (alloc_acc(c, S)) return 1;
+  return 0;
+}
 
 // component pointers of a particle field; sym = stored as 6 symmetric components
 static int solid_field(kml_ctx *c, Solid *S, int field, double **comp, int *ncomp, bool *sym) {
@@ -377,6 +409,9 @@ static int solid_field(kml_ctx *c, Solid *S, int field, double **comp, int *ncom
   case KML_P_EFF_PLASTIC_STRAIN_RATE: comp[0] = s.epsdot; break; case KML_P_DAMAGE: comp[0] = s.dmg; break;
   case KML_P_DAMAGE_INIT: comp[0] = s.dmgi; break; case KML_P_IENERGY: comp[0] = s.ien; break; case KML_P_T: comp[0] = s.T; break;
   case KML_P_GAMMA: comp[0] = s.gamma; break;
+  case KML_P_A: case KML_P_V_UPDATE:
+    if (!s.acc[0]) return fail("kml: KML_P_A / KML_P_V_UPDATE / KML_P_F are kept only after kml_keep_particle_acceleration (called before the first step)");
+    v3(field == KML_P_A ? s.acc : s.vup); break;
   default: return fail("particle field " + std::to_string(field) + " is not materialised by the CUDA engine (derived in-kernel)");
   }
   return 0;
@@ -399,6 +434,8 @@ static bool cpdi_rowmap(Solid *S, int field, RowMap &rm) {
 int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   CU(cudaSetDevice(c->dev));
   Solid *S = c->solids[sid]; const long long np = S->s.np;
+  if (field == KML_P_PTAG || field == KML_P_MASK || field == KML_P_X0) S->gen++;
+  if (field == KML_P_A || field == KML_P_V_UPDATE || field == KML_P_F || field == KML_P_J || field == KML_P_RHO || field == KML_P_R) return fail("particle field " + std::to_string(field) + " is download-only");
   if (field == KML_P_PTAG) { CU(cudaMemcpyAsync(S->s.ptag, src, sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_P_MASK) { CU(cudaMemcpyAsync(S->s.mask, src, sizeof(int) * np, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   // KML_P_X between advance_particles and the next weight evaluation lands in the advanced positions (xn, see solid_field): the
@@ -432,6 +469,12 @@ int kml_solid_download(kml_ctx *c, int sid, int field, void *dst) {
   Solid *S = c->solids[sid]; const long long np = S->s.np;
   if (field == KML_P_PTAG) { CU(cudaMemcpyAsync(dst, S->s.ptag, sizeof(long long) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_P_MASK) { CU(cudaMemcpyAsync(dst, S->s.mask, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+  if (field == KML_P_F) { // f_p = a_p m_p, src/solid.cpp:615
+    std::vector<double> a(3 * np), m(np);
+    if (kml_solid_download(c, sid, KML_P_A, a.data()) || kml_solid_download(c, sid, KML_P_MASS, m.data())) return 1;
+    for (long long i = 0; i < np; i++) for (int d = 0; d < 3; d++) ((double *)dst)[3 * i + d] = a[3 * i + d] * m[i];
+    return 0;
+  }
   if (field == KML_P_J || field == KML_P_RHO) { // derived: J = det F, rho = rho0 / J (src/solid.cpp:1201-1217)
     std::vector<double> F(9 * np), r0(np);
     if (kml_solid_download(c, sid, KML_P_FDEF, F.data()) || kml_solid_download(c, sid, KML_P_RHO0, r0.data())) return 1;
@@ -483,6 +526,11 @@ int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
       k_gather_rows<double><<<nblocks(n, 256), 256, 0, c->stream>>>((double *)c->d_stage, arr, d_idx, n);
       CU(cudaMemcpyAsync(arr, c->d_stage, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     }
+    for (int a = 0; S->accbuf && a < 6; a++) {
+      double *arr = S->accbuf + (size_t)a * S->cap;
+      k_gather_rows<double><<<nblocks(n, 256), 256, 0, c->stream>>>((double *)c->d_stage, arr, d_idx, n);
+      CU(cudaMemcpyAsync(arr, c->d_stage, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
     k_gather_rows<long long><<<nblocks(n, 256), 256, 0, c->stream>>>((long long *)c->d_stage, S->s.ptag, d_idx, n);
     CU(cudaMemcpyAsync(S->s.ptag, c->d_stage, sizeof(long long) * n, cudaMemcpyDeviceToDevice, c->stream));
     k_gather_rows<int><<<nblocks(n, 256), 256, 0, c->stream>>>((int *)c->d_stage, S->s.mask, d_idx, n);
@@ -491,7 +539,7 @@ int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
   const int rc = check_launch("k_gather_rows");
   CU(cudaStreamSynchronize(c->stream));
   cudaFree(d_idx);
-  S->s.np = n; S->d.np = n;
+  S->s.np = n; S->d.np = n; S->gen++;
   c->tl_mass_done = false; // TL: node masses are computed once from the particle set (update_mass_nodes, src/tlmpm.cpp:345-351)
   return rc;
 }
@@ -512,6 +560,7 @@ int kml_get_dt(kml_ctx *c, double *dt) { *dt = c->dt; return 0; }
 // ---- stages -----------------------------------------------------------------------------------
 int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
+  c->steps_started++;
   // Weights are functions of the step-start positions: make the positions advanced by
   // the previous step current.  UL re-bins the particles by cell for the cell-centric P2G.
   if (!c->c.is_TL)
@@ -555,7 +604,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
       for (Solid *S : c->solids) {
         Grid *G = c->grids[S->d.grid];
         int nl = 0;
-        if (G->cl.build(S->s, G->g, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
+        if (G->cl.build(S->s, G->g, S->cap, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
         c->launches[KML_STAGE_REBIN] += nl;
         if (c->solids.size() > 1) break; // cell lists are per grid; several solids on one grid use the atomic path
       }
@@ -636,7 +685,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     }
     if (what == 0) continue;
     bool done = false;
-    fill_inertia(c, G, sp);
+    fill_inertia(c, G, S, sp);
     sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
     if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
@@ -659,7 +708,8 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (what & P2G_TEMP) G->T_is_weighted = true;
   }
   if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
-  if (c->comm.nranks > 1) for (Grid *G : active_grids(c)) if (halo_sum(c, G, what_in, stage)) return 1;
+  t.stop();
+  if (c->comm.nranks > 1) { StageTimer th(c, KML_STAGE_HALO); for (Grid *G : active_grids(c)) if (halo_sum(c, G, what_in, KML_STAGE_HALO)) return 1; }
   return 0;
 }
 
@@ -700,9 +750,9 @@ int kml_advance_particles(kml_ctx *c) {
     Grid *G = c->grids[S->d.grid];
     if (grid_normalize_if_needed(c, G)) return 1;
     int rc = -1;
-    fill_inertia(c, G, sp);
+    fill_inertia(c, G, S, sp);
     sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
-    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && !c->keep_acc && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell g2p launch failed");
     }
@@ -763,7 +813,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
-    fill_inertia(c, G, sp);
+    fill_inertia(c, G, S, sp);
     if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
@@ -781,7 +831,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
 
 int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
   CU(cudaSetDevice(c->dev));
-  StageTimer t(c, KML_STAGE_OTHER);
+  StageTimer t(c, KML_STAGE_DT);
   const int ns = (int)c->solids.size();
   if (ns * 2 + 1 > 64) return fail("too many solids");
   if (c->comm.nranks > 1) { // MPI_Allreduce(MIN) of dtCFL in the reference (src/ulmpm.cpp:547) == max of the wave speed here
@@ -812,7 +862,7 @@ int kml_exchange_particles(kml_ctx *c) {
   Comm &cm = c->comm;
   if (cm.nranks <= 1) return 0;
   CU(cudaSetDevice(c->dev));
-  StageTimer t(c, KML_STAGE_OTHER);
+  StageTimer t(c, KML_STAGE_MIGRATE);
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid]; SolidDev &s = S->s;
     if (S->moved) { for (int k = 0; k < 3; k++) std::swap(s.x[k], s.xn[k]); S->moved = false; }
@@ -820,7 +870,7 @@ int kml_exchange_particles(kml_ctx *c) {
     const int cap_mig = (int)std::min<long long>(std::max<long long>(s.np / 8, 1024), 1 << 24);
     if (cap_mig > cm.mig_cap) {
       cudaFree(cm.mig_list); cudaFree(cm.mig_send); cudaFree(cm.mig_recv); cudaFree(cm.mig_flag);
-      CU(cudaMalloc(&cm.mig_list, sizeof(int) * 4 * (size_t)cap_mig));
+      CU(cudaMalloc(&cm.mig_list, sizeof(int) * 6 * (size_t)cap_mig)); // leavers left | right (cap each), holes, fillers (2 cap each: up to nL + nR entries)
       CU(cudaMalloc(&cm.mig_flag, sizeof(int) * 2 * (size_t)cap_mig));
       cm.mig_bytes = sizeof(double) * (size_t)(narr + 2) * 2 * cap_mig;
       CU(cudaMalloc(&cm.mig_send, cm.mig_bytes)); CU(cudaMalloc(&cm.mig_recv, cm.mig_bytes));
@@ -837,7 +887,7 @@ int kml_exchange_particles(kml_ctx *c) {
     CU(cudaMemcpyAsync(cm.h_cnt, cm.mig_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const int nL = cm.h_cnt[0], nR = cm.h_cnt[1], rL = cm.h_cnt[2], rR = cm.h_cnt[3];
-    c->launches[KML_STAGE_OTHER]++;
+    c->launches[KML_STAGE_MIGRATE]++;
     if (nL > cm.mig_cap || nR > cm.mig_cap || rL > cm.mig_cap || rR > cm.mig_cap) return fail("particle migration buffer overflow");
     if (nL + nR + rL + rR == 0) continue;
     const long long np_new = s.np - nL - nR;
@@ -851,7 +901,7 @@ int kml_exchange_particles(kml_ctx *c) {
     if (right) { if (nR) NC(nccl().Send(sendR, (size_t)(narr + 2) * nR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); if (rR) NC(nccl().Recv(recvR, (size_t)(narr + 2) * rR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); }
     NC(nccl().GroupEnd());
     if (nL + nR) { // close the holes left by the leavers with stayers from the tail
-      int *holes = cm.mig_list + 2 * (size_t)cm.mig_cap, *fillers = cm.mig_list + 3 * (size_t)cm.mig_cap;
+      int *holes = cm.mig_list + 2 * (size_t)cm.mig_cap, *fillers = cm.mig_list + 4 * (size_t)cm.mig_cap;
       const int ntail = nL + nR; // the last ntail slots [np_new, np) are vacated
       CU(cudaMemsetAsync(cm.mig_flag, 0, sizeof(int) * ntail, c->stream));
       k_mig_flag<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_list, cm.mig_cap, nL, nR, cm.mig_flag, np_new);
@@ -864,8 +914,8 @@ int kml_exchange_particles(kml_ctx *c) {
     }
     if (rL) k_mig_unpack<<<nblocks(rL, 128), 128, 0, c->stream>>>(recvL, rL, np_new, S->buf, S->cap, narr, s.ptag, s.mask);
     if (rR) k_mig_unpack<<<nblocks(rR, 128), 128, 0, c->stream>>>(recvR, rR, np_new + rL, S->buf, S->cap, narr, s.ptag, s.mask);
-    s.np = np_new + rL + rR;
-    c->launches[KML_STAGE_OTHER] += 6;
+    s.np = np_new + rL + rR; S->gen++;
+    c->launches[KML_STAGE_MIGRATE] += 6;
     if (check_launch("migration")) return 1;
   }
   return 0;
@@ -1048,6 +1098,11 @@ int kml_timer_stop(kml_ctx *c, double *ms) {
   float t = 0; CU(cudaEventElapsedTime(&t, c->evA, c->evB)); *ms = t; return 0;
 }
 int kml_stage_times(kml_ctx *c, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset) {
+  if (!c->ev_pending.empty()) {
+    CU(cudaSetDevice(c->dev)); CU(cudaStreamSynchronize(c->stream));
+    for (auto &p : c->ev_pending) { float t = 0; cudaEventElapsedTime(&t, p.a, p.b); c->ms[p.stage] += t; c->ev_pool.push_back(p.a); c->ev_pool.push_back(p.b); }
+    c->ev_pending.clear();
+  }
   for (int i = 0; i < KML_STAGE_COUNT; i++) { ms[i] = c->ms[i]; launches[i] = c->launches[i]; }
   if (reset) { memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches); }
   return 0;

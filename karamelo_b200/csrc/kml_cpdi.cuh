@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) k_cpdi_g2p(SolidDev s, GridDev g, CpdiDev
 #pragma unroll
   for (int d = 0; d < 2; d++) {
     const double ad = a[d] * inv_dt;
+    if (s.acc[0]) { s.acc[d][ip] = ad; s.vup[d][ip] = vu[d]; }
     s.v[d][ip] = (1 - sp.alpha) * vu[d] + sp.alpha * (s.v[d][ip] + sp.dt * ad);
     if (TL) s.x[d][ip] = x[d]; else s.xn[d][ip] = x[d];
   }

@@ -86,7 +86,7 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
           acc[0] = fma(wf, r23.y, acc[0]); acc[1] = fma(wf, r45.x, acc[1]); acc[2] = fma(wf, r45.y, acc[2]);
         }
       }
-    particle_advance<false>(s, sp, ip, vu, acc, 0.0, vold);
+    particle_advance<false, false>(s, sp, ip, vu, acc, 0.0, vold); // kept accelerations (kml_keep_particle_acceleration) go through k_g2p
     p = pn; ip = ipn; px = nx; py = ny; pz = nz;
   }
 }

@@ -16,6 +16,7 @@ struct SolidDev {
   double *pk1[9], *R[9]; // TL only
   double *Lst[9];        // APIC family only: the velocity gradient of the previous step (UL: L, TL: Fdot), src/solid.cpp:392-426
   long long *ptag; int *mask;
+  double *acc[3], *vup[3]; // only after kml_keep_particle_acceleration: a_p and v_update_p of the last grid_to_points (src/solid.cpp:576-635)
 };
 
 struct StepParams {
@@ -230,7 +231,7 @@ __global__ void k_grid_zero_v(GridDev g, int zero_mass) {
 #endif // KML_MISC_KERNELS
 
 // tail of G2P for one particle: a_p, x_p += dt v~_p, FLIP/PIC blend (src/solid.cpp:613-616, :786-796)
-template <bool TL>
+template <bool TL, bool KEEP = true>
 __device__ __forceinline__ void particle_advance(const SolidDev &s, const StepParams &sp, long long ip, const double *vu, const double *a, double Tp,
                                                  const double *vold = nullptr) { // vold: the particle's velocity if the caller already loaded it
   const double inv_dt = 1.0 / sp.dt;
@@ -238,6 +239,7 @@ __device__ __forceinline__ void particle_advance(const SolidDev &s, const StepPa
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     const double ad = a[d] * inv_dt;
+    if (KEEP) { if (s.acc[0]) { s.acc[d][ip] = ad; s.vup[d][ip] = vu[d]; } }
     const double xo = s.x[d][ip];
     const double vnew = (1 - sp.alpha) * vu[d] + sp.alpha * ((vold ? vold[d] : s.v[d][ip]) + sp.dt * ad);
     // ASFLIP (UL): the position is advanced with the blended particle velocity, not with v~ (src/solid.cpp:637-694, :786-796)

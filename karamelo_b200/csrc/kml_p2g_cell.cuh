@@ -20,7 +20,7 @@ struct CellLists {
   int *start = nullptr;     // [ncells + 1] counts, then exclusive offsets
   int *order = nullptr;     // [np] particle ids grouped by cell
   void *scan_tmp = nullptr; size_t scan_bytes = 0;
-  int build(const SolidDev &s, const GridDev &g, cudaStream_t st, int *nlaunch);
+  int build(const SolidDev &s, const GridDev &g, long long capacity, cudaStream_t st, int *nlaunch);
   void release() {
     cudaFree(cell_of); cudaFree(rank); cudaFree(start); cudaFree(order); cudaFree(scan_tmp);
     cell_of = rank = start = order = nullptr; scan_tmp = nullptr; valid = false; ncells = cap_np = 0; scan_bytes = 0;
@@ -50,12 +50,13 @@ __global__ void k_cell_fill(long long np, const int *cell_of, const int *rank, c
   order[start[cell_of[ip]] + rank[ip]] = (int)ip;
 }
 
-inline int CellLists::build(const SolidDev &s, const GridDev &g, cudaStream_t st, int *nlaunch) {
+inline int CellLists::build(const SolidDev &s, const GridDev &g, long long capacity, cudaStream_t st, int *nlaunch) {
   *nlaunch = 0; valid = false;
   if (s.np >= (1ll << 31) || g.nn >= (1ll << 31)) return 0; // 32-bit particle ids / keys
   if (g.nn != ncells || s.np > cap_np) {
     release();
-    ncells = g.nn; cap_np = s.np;
+    // sized for the solid's capacity (the room left for migration): the lists are never re-allocated inside a step as a slab gains particles
+    ncells = g.nn; cap_np = s.np > capacity ? s.np : capacity;
     if (cudaMalloc(&cell_of, sizeof(int) * cap_np) || cudaMalloc(&rank, sizeof(int) * cap_np) || cudaMalloc(&order, sizeof(int) * cap_np) ||
         cudaMalloc(&start, sizeof(int) * (ncells + 1))) return 1;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, start, start, (int)(ncells + 1), st);

@@ -36,7 +36,7 @@ struct FixInitialVelocityParticles : Fix {
     const int solid = s.gsolid[igroup];
     for (size_t is = 0; is < s.solids.size(); is++) {
       if (solid != -1 && (int)is != solid) continue;
-      SolidH &S = *s.solids[is];
+      SolidH &S = *s.solids[is]; s.sync(S);
       std::vector<std::array<double, 3>> x(S.np), v(S.np);
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
@@ -78,7 +78,7 @@ static bool particle_dependent(const Var &v) {
 }
 template <class F> static void for_group_solids(Sim &s, int igroup, F f) { // "solid == -1: every solid" loops of the reference's fixes
   const int solid = s.gsolid[igroup];
-  for (size_t is = 0; is < s.solids.size(); is++) if (solid == -1 || (int)is == solid) f(*s.solids[is]);
+  for (size_t is = 0; is < s.solids.size(); is++) if (solid == -1 || (int)is == solid) { s.sync(*s.solids[is]); f(*s.solids[is]); }
 }
 
 // FixVelocityParticles, reference src/fix_velocity_particles.cpp:30-300: v = v(t - dt) before the step, v = v(t) and
@@ -102,7 +102,7 @@ struct FixVelocityParticles : Fix {
     const int solid = s.gsolid[igroup];
     for (size_t is = 0; is < s.solids.size(); is++) {
       if (solid != -1 && (int)is != solid) continue;
-      SolidH &S = *s.solids[is];
+      SolidH &S = *s.solids[is]; s.sync(S);
       std::vector<double> &x = xold[is]; x.resize(3 * S.np); std::vector<double> v(3 * S.np);
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
@@ -127,7 +127,7 @@ struct FixVelocityParticles : Fix {
     const int solid = s.gsolid[igroup];
     for (size_t is = 0; is < s.solids.size(); is++) {
       if (solid != -1 && (int)is != solid) continue;
-      SolidH &S = *s.solids[is];
+      SolidH &S = *s.solids[is]; s.sync(S);
       std::vector<double> x(3 * S.np), v(3 * S.np), mass(S.np); const std::vector<double> &xo = xold[is];
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_X, x.data()));
       s.check(kml_solid_download(s.ctx, S.dev, KML_P_V, v.data()));
@@ -634,7 +634,7 @@ static void write_particle_dump(Sim &s, const Dump &d) { // DumpParticle::write,
   std::string fn = d.filename; size_t star = fn.find('*');
   if (star != std::string::npos) fn = fn.substr(0, star) + std::to_string(s.ntimestep) + fn.substr(star + 1);
   std::ostringstream os;
-  int64_t total = 0; for (auto &S : s.solids) total += S->np;
+  int64_t total = 0; for (auto &S : s.solids) { s.sync(*S); total += S->np; }
   os << "ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n" << total << "\nITEM: BOX BOUNDS sm sm sm\n";
   for (int k = 0; k < 3; k++) os << s.boxlo[k] << " " << s.boxhi[k] << "\n";
   os << "ITEM: ATOMS id type tag ";
@@ -794,7 +794,7 @@ void Sim::write_restart(const std::string &pattern) {
   // solids: Domain::write_restart + Solid::write_restart, src/solid.cpp:2841-2887 (matrices in Eigen's column-major order)
   { const int n = (int)solids.size(); rput(os, n); }
   for (auto &Sp : solids) {
-    SolidH &S = *Sp; const int64_t n = S.np;
+    SolidH &S = *Sp; sync(S); const int64_t n = S.np;
     rput_str(os, S.id);
     for (int d = 0; d < 3; d++) rput(os, S.solidlo[d]);
     for (int d = 0; d < 3; d++) rput(os, S.solidhi[d]);

@@ -105,6 +105,7 @@ void Sim::register_commands() {
     if (gpon[ig] == "particles") {
       int64_t np = 0; check(kml_solid_np(ctx, s.dev, &np));
       std::vector<double> v(3 * np), m(np); std::vector<int> mask(np);
+      if (!com) check(kml_keep_particle_acceleration(ctx)); // f_p = a_p m_p is not state of the engine unless asked for (before the first step)
       check(kml_solid_download(ctx, s.dev, com ? KML_P_X : KML_P_F, v.data()));
       check(kml_solid_download(ctx, s.dev, KML_P_MASK, mask.data()));
       if (com) check(kml_solid_download(ctx, s.dev, KML_P_MASS, m.data()));
@@ -133,6 +134,7 @@ void Sim::register_commands() {
     SolidH &s = *solids[gsolid[ig]]; const int bit = gbitmask[ig];
     int64_t np = 0; check(kml_solid_np(ctx, s.dev, &np));
     std::vector<double> f(3 * np); std::vector<int> mask(np);
+    check(kml_keep_particle_acceleration(ctx));
     check(kml_solid_download(ctx, s.dev, KML_P_F, f.data())); check(kml_solid_download(ctx, s.dev, KML_P_MASK, mask.data()));
     double sum = 0; for (int64_t i = 0; i < np; i++) if (mask[i] & bit) sum += f[3 * i + dir];
     return Var("external_force(" + a[0] + "," + a[1] + ")", sum);
@@ -154,7 +156,7 @@ void Sim::register_commands() {
     for (int d = 0; d < 3; d++) { del[d] = input.parsev(a[3 + d]); set[d] = !(del[d].is_constant() && std::fabs(del[d].result()) <= 1.0e-12); }
     for (size_t is = 0; is < solids.size(); is++) {
       if (isolid >= 0 && (int)is != isolid) continue;
-      SolidH &S = *solids[is];
+      SolidH &S = *solids[is]; sync(S);
       std::vector<double> x(3 * S.np), x0(3 * S.np);
       check(kml_solid_download(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_download(ctx, S.dev, KML_P_X0, x0.data()));
       for (int64_t ip = 0; ip < S.np; ip++) {
@@ -164,6 +166,7 @@ void Sim::register_commands() {
         for (int d = 0; d < 3; d++) if (set[d]) { const double v = del[d].result(&input); x0[3 * ip + d] += v; x[3 * ip + d] += v; S.x0[ip][d] = x0[3 * ip + d]; }
       }
       check(kml_solid_upload(ctx, S.dev, KML_P_X, x.data())); check(kml_solid_upload(ctx, S.dev, KML_P_X0, x0.data()));
+      mirrors_current(S);
     }
     return Var(0);
   };
@@ -178,7 +181,7 @@ void Sim::register_commands() {
     if (ir < 0) fatal("Error: region " + a[2] + " unknown.\n");
     for (size_t is = 0; is < solids.size(); is++) {
       if (isolid >= 0 && (int)is != isolid) continue;
-      SolidH &S = *solids[is];
+      SolidH &S = *solids[is]; sync(S);
       std::vector<int> dl(S.np);
       for (int64_t ip = 0; ip < S.np; ip++) dl[ip] = regions[ir]->inside(S.x0[ip][0], S.x0[ip][1], S.x0[ip][2]) == 1;
       check(kml_solid_delete_particles(ctx, S.dev, dl.data()));
@@ -187,7 +190,7 @@ void Sim::register_commands() {
         if (dl[k]) { S.x0[k] = S.x0[n - 1]; S.mask[k] = S.mask[n - 1]; S.ptag[k] = S.ptag[n - 1]; dl[k] = dl[n - 1]; n--; } else k++;
       }
       np_total = n; // sic: the reference stores this solid's remaining count (domain->np_total = np_local_reduced, src/delete_particles.cpp:78)
-      S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n);
+      S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n); mirrors_current(S);
       std::vector<double> vol(n), mass(n);
       check(kml_solid_download(ctx, S.dev, KML_P_VOL, vol.data())); check(kml_solid_download(ctx, S.dev, KML_P_MASS, mass.data()));
       S.vtot = S.mtot = 0; for (int64_t i = 0; i < n; i++) { S.vtot += vol[i]; S.mtot += mass[i]; }
@@ -627,6 +630,7 @@ void Sim::read_restart(const std::string &pattern) {
     check(kml_solid_upload(ctx, S.dev, KML_P_DAMAGE, dmg.data())); check(kml_solid_upload(ctx, S.dev, KML_P_DAMAGE_INIT, dmgi.data()));
     if (temp) check(kml_solid_upload(ctx, S.dev, KML_P_T, T.data()));
     check(kml_solid_upload(ctx, S.dev, KML_P_IENERGY, ie.data()));
+    mirrors_current(S);
     S.vtot = S.mtot = 0; for (int64_t ip = 0; ip < np; ip++) { S.vtot += vol[ip]; S.mtot += mass[ip]; }
     solids.push_back(std::move(sp));
   }
@@ -760,6 +764,19 @@ Var Sim::cmd_material(std::vector<std::string> &a) {
   return Var(0);
 }
 
+void Sim::sync(SolidH &S) {
+  uint64_t g = 0; int64_t n = 0;
+  check(kml_solid_generation(ctx, S.dev, &g)); check(kml_solid_np(ctx, S.dev, &n));
+  if (g == S.mirror_gen && n == S.np && (int64_t)S.x0.size() == n) return;
+  S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n);
+  if (n > 0) {
+    check(kml_solid_download(ctx, S.dev, KML_P_PTAG, S.ptag.data())); check(kml_solid_download(ctx, S.dev, KML_P_X0, S.x0.data()));
+    check(kml_solid_download(ctx, S.dev, KML_P_MASK, S.mask.data()));
+  }
+  S.mirror_gen = g;
+}
+void Sim::mirrors_current(SolidH &S) { check(kml_solid_generation(ctx, S.dev, &S.mirror_gen)); check(kml_solid_np(ctx, S.dev, &S.np)); }
+
 // Domain::add_solid -> Solid::Solid / options / populate / init (src/solid.cpp:59-238, :1810-2336)
 Var Sim::cmd_solid(std::vector<std::string> &a) {
   if (!method_set) fatal("Error: a method should be defined before creating a solid!\n");
@@ -880,7 +897,7 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   np_global_last = np_global; tag_offset_last = tag_offset;
 
   // upload; everything not set here starts at the values of src/solid.cpp:2283-2321 (F = R = I, J = 1, mask = 1, rest 0)
-  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.mat = mat;
+  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
   check(kml_solid_create(ctx, &d, &s.dev));
   check(kml_solid_upload(ctx, s.dev, KML_P_PTAG, s.ptag.data()));
   check(kml_solid_upload(ctx, s.dev, KML_P_X, s.x0.data()));
@@ -904,6 +921,7 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
       check(kml_solid_upload(ctx, s.dev, KML_P_XPC0, xc.data())); check(kml_solid_upload(ctx, s.dev, KML_P_XPC, xc.data()));
     }
   }
+  mirrors_current(s);
   // Solid::init totals, src/solid.cpp:170-195
   s.vtot = s.mtot = 0; for (int64_t i = 0; i < s.np; i++) { s.vtot += vol[i]; s.mtot += mass[i]; }
   if (!quiet) std::cout << "Solid " << s.id << ": np=" << s.np << " total volume = " << s.vtot << " total mass = " << s.mtot << " grid " << s.grid->desc.n[0] << "x" << s.grid->desc.n[1] << "x" << s.grid->desc.n[2] << std::endl;
@@ -931,10 +949,10 @@ Var Sim::cmd_group(std::vector<std::string> &a) {
     for (size_t i = 5; i < a.size(); i++) { gsolid[ig] = find_solid(a[i]); if (gsolid[ig] == -1) fatal("Error: cannot find solid with ID " + a[i] + ".\n"); targets.push_back(gsolid[ig]); }
   } else fatal("Error: unknown keyword in group command: " + a[3] + ".\n");
   for (int is : targets) {
-    SolidH &s = *solids[is]; int n = 0;
+    SolidH &s = *solids[is]; sync(s); int n = 0;
     if (gpon[ig] == "particles") {
       for (int64_t ip = 0; ip < s.np; ip++) if (reg.match(s.x0[ip][0], s.x0[ip][1], s.x0[ip][2])) { s.mask[ip] |= bit; n++; }
-      check(kml_solid_upload(ctx, s.dev, KML_P_MASK, s.mask.data()));
+      check(kml_solid_upload(ctx, s.dev, KML_P_MASK, s.mask.data())); mirrors_current(s);
     } else {
       GridH &g = *s.grid; const kml_grid_desc &d = g.desc; int64_t l = 0;
       for (int i = 0; i < d.n[0]; i++) for (int j = 0; j < d.n[1]; j++) for (int k = 0; k < d.n[2]; k++, l++) {

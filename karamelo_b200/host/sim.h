@@ -59,9 +59,13 @@ struct SolidH {
   double solidlo[3], solidhi[3];
   double T0 = 0;
   double vtot = 0, mtot = 0;
-  std::vector<std::array<double, 3>> x0; // reference positions (group assignment uses x0)
+  // Host mirrors of the particle attributes the script side reads per particle (reference positions for regions / expressions, group
+  // masks, tags).  The engine may change the particle set behind the host's back (migration between slabs, uploads through the C ABI,
+  // populate on the device): Sim::sync compares kml_solid_generation before every use and downloads again when it moved.
+  std::vector<std::array<double, 3>> x0;
   std::vector<int> mask;
   std::vector<int64_t> ptag;
+  uint64_t mirror_gen = 0; // 0 = mirrors never filled
 };
 
 enum HookMask { INITIAL_INTEGRATE = 1, POST_PARTICLES_TO_GRID = 2, POST_UPDATE_GRID_STATE = 4, POST_GRID_TO_POINT = 8,
@@ -141,6 +145,8 @@ public:
   int find_region(const std::string &n) const; int find_solid(const std::string &n) const; int find_material(const std::string &n) const;
   int find_group(const std::string &n) const;
   void check(int rc) const; // kml_* return code -> fatal(kml_last_error())
+  void sync(SolidH &S);            // np + host mirrors (x0, mask, ptag) follow the engine's particle set
+  void mirrors_current(SolidH &S); // the host just wrote the same change to the mirrors and to the device
   void ensure_ctx();
   void init_grid(GridH &g, const double *lo, const double *hi); // Grid::init, src/grid.cpp:68-264
   void run(Var condition);        // Scheme::run, src/usl.cpp / src/musl.cpp / src/usf.cpp

@@ -145,7 +145,7 @@ struct OGrid {
 };
 
 struct OSolid {
-  int64_t np; int grid; kml_material mat;
+  int64_t np; int grid; kml_material mat; uint64_t gen = 1;
   std::vector<int64_t> ptag;
   std::vector<Vec3> x, x0, v, v_update, a, mbp, f, q, xold;
   std::vector<Mat3> sigma, strain_el, vol0PK1, L, F, R, D, Finv, Fdot;
@@ -288,7 +288,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   s->neigh_pn.resize(n); s->wf_pn.resize(n); s->wfd_pn.resize(n);
   int64_t nn = c->grids[d->grid]->nn;
   s->neigh_np.resize(nn); s->wf_np.resize(nn); s->wfd_np.resize(nn);
-  s->dtCFL = 1.0e22; s->max_p_wave_speed = 0; s->Di.setIdentity(); s->np_per_cell = 2;
+  s->dtCFL = 1.0e22; s->max_p_wave_speed = 0; s->Di.setIdentity(); s->np_per_cell = d->np_per_cell ? d->np_per_cell : 2; // Solid::np_per_cell, src/solid.cpp:2027
   if (c->c.is_CPDI) { // src/solid.cpp:83-88 (nc = 2^dim), :249-259, :299-300
     s->nc = 1 << c->c.dimension;
     s->rp.assign(c->c.dimension * n, z3); s->rp0.assign(c->c.dimension * n, z3);
@@ -298,9 +298,12 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   c->solids.push_back(s); *sid = (int)c->solids.size() - 1; return 0;
 }
 int kml_solid_np(kml_ctx *c, int sid, int64_t *np) { *np = c->solids[sid]->np; return 0; }
+int kml_solid_generation(kml_ctx *c, int sid, uint64_t *gen) { *gen = c->solids[sid]->gen; return 0; }
+int kml_keep_particle_acceleration(kml_ctx *) { return 0; } // the restatement stores v_update, a and f like the reference (src/solid.cpp:576-635)
 
 int kml_solid_upload(kml_ctx *c, int sid, int field, const void *src) {
   OSolid *s = c->solids[sid];
+  if (field == KML_P_PTAG || field == KML_P_MASK || field == KML_P_X0) s->gen++;
   switch (field) {
   case KML_P_PTAG: get1(s->ptag, src); break; case KML_P_X: get3(s->x, src); break; case KML_P_X0: get3(s->x0, src); break;
   case KML_P_V: get3(s->v, src); break; case KML_P_MBP: get3(s->mbp, src); break;
@@ -354,6 +357,7 @@ int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
   };
   int64_t n = s->np, k = 0;
   while (k < n) { if (dl[k]) { copy_particle(n - 1, k); dl[k] = dl[n - 1]; n--; } else k++; }
+  s->gen++;
   s->np = n; // the reference keeps its vectors at the old length and only lowers np_local; downloads here copy whole vectors, so shrink them
   s->ptag.resize(n); s->mask.resize(n);
   for (auto *v : {&s->x, &s->x0, &s->v, &s->v_update, &s->a, &s->mbp, &s->f, &s->q, &s->xold}) if (v->size() > (size_t)n) v->resize(n);

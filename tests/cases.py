@@ -93,9 +93,12 @@ dt_factor(0.25)
 # amplify a 1e-15 perturbation to 1e-5 in 100 steps, which no 1e-10 parity test can survive; this one amplifies
 # it to ~1e-11 (measured with the oracle).  The oblique impact of C4 exists for the same reason: in a head-on
 # collision the Coulomb friction direction v_t/|v_t| is rounding noise.
-def tensile(thermal=False, shape="Bernstein-quadratic", vgrip=40):
-    method = f"method(tlmpm, FLIP, {shape}, FLIP" + (", thermo-mechanical)" if thermal else ")")
-    tmat = "temperature(tpw, plastic_work, 0.9, 452e+6, 50, 0, Tr, Tm)\n" if thermal else ""
+def tensile(thermal=False, shape="Bernstein-quadratic", vgrip=40, kind="tlmpm", Gamma=0, cv=0, m=0, C=0.01, d4=0, d5=0, alpha=0, cp="452e+6", depsdot0=1):
+    """Gamma, cv: Mie-Gruneisen energy term e = cv rho0 (T - Tr) (src/eos_shock.cpp:99-133); m: JC thermal softening
+    (src/strength_jc.cpp:127-133); d4, d5: strain-rate and temperature factors of the JC failure strain
+    (src/damage_jc.cpp:120-129); alpha: thermal pressure alpha (T0 - T) (src/temperature_plastic_work.cpp:59-69, src/solid.cpp:1309-1312)"""
+    method = f"method({kind}, FLIP, {shape}, FLIP" + (", thermo-mechanical)" if thermal else ")")
+    tmat = f"temperature(tpw, plastic_work, 0.9, {cp}, 50, {alpha}, Tr, Tm)\n" if thermal else ""
     mat4 = "material(mat4, eos-strength, eoss, strengthjc, damagejc" + (", tpw)" if thermal else ")")
     return f"""
 E = 211
@@ -120,16 +123,16 @@ Q1 = 0.06
 Q2 = 0.1
 Tr = 25
 Tm = 1000
-cv = 0
-Gamma = 0
+cv = {cv}
+Gamma = {Gamma}
 eos(eoss,   shock, rho, K, c0, S, Gamma, cv, Tr, Q1, Q2)
-strength(strengthjc, johnson_cook, G, sigmay, B, n, 1, 0.01, 0, Tr, Tm)
+strength(strengthjc, johnson_cook, G, sigmay, B, n, 1, {C}, {m}, Tr, Tm)
 d1 = 0.0382
 d2 = 0.1162
 d3 = -2.969
-d4 = 0
-d5 = 0
-epsdot0 = 1
+d4 = {d4}
+d5 = {d5}
+epsdot0 = {depsdot0}
 damage(damagejc, damage_johnson_cook, d1, d2, d3, d4, d5, epsdot0, Tr, Tm)
 {tmat}{mat4}
 ppc = 2
@@ -360,8 +363,8 @@ fix(vn0, initial_velocity_nodes, gKick, 0.05*y0, -0.05, NULL)
 """
 
 
-def heated_bar():
-    return tensile(True) + """
+def heated_bar(**kw):
+    return tensile(True, **kw) + """
 region(rHot, block, INF, -hLx+cellsize, INF, INF, INF, INF)
 group(gHotN, nodes, region, rHot, solid, solid1)
 fix(fTn, temperature_nodes, gHotN, Tr+100*time/0.01)
@@ -409,6 +412,52 @@ fix(v0Ball2, initial_velocity_particles, gBall2, -v, -v, -0.8*v)
 dt_factor(0.1)
 """
 
+
+# Axisymmetric 2-D (axisymmetric(true), src/domain.cpp:554-569): x is the radius.  Hoop terms: f_I[0] -= vol sigma_22 wf / x_p
+# (src/solid.cpp:499-517, TL :472), L_22 += v_I[0] wf / x_p (src/solid.cpp:900-916, TL :818-828), mass = rho0 vol0 x0[0]
+# (src/solid.cpp:2292-2298).  A short Taylor bar hitting a wall along its axis; UL cubic / linear, TL linear.
+def axisym_bar(kind="ulmpm", shape="cubic-spline", scheme="musl"):
+    return f"""
+E   = 115
+nu  = 0.31
+K   = E/(3*(1-2*nu))
+G   = E/(2*(1+nu))
+rho = 8.94e-06
+sigmay  = 0.065
+B       = 0.356
+C       = 0.013
+n       = 0.37
+eps0dot = 1e-3
+Tm      = 1600
+S     = 1.5
+c0    = 3933
+Tr = 25
+FLIP = 0.99
+method({kind}, FLIP, {shape}, FLIP)
+scheme({scheme})
+axisymmetric(true)
+N        = 4
+cellsize = 1/N
+dimension(2, 0, 4, -cellsize, 6, cellsize)
+eos(eoss, shock, rho, K, c0, S, 0, 0, Tr, 0, 0)
+strength(strengthJC, johnson_cook, G, sigmay, B, n, eps0dot, C, 0, Tr, Tm)
+material(mat, eos-strength, eoss, strengthJC)
+region(cyl, block, 0, 1.6, {"cellsize" if kind == "ulmpm" else "0"}, 4)
+solid(solid1, region, cyl, 2, mat, cellsize, Tr)
+region(rWall, block, INF, INF, INF, cellsize/4)
+group(gWall, nodes, region, rWall, solid, solid1)
+region(rAxis, block, INF, cellsize/4, INF, INF)
+group(gAxis, nodes, region, rAxis, solid, solid1)
+group(gAll, particles, region, cyl, solid, solid1)
+v = 190
+fix(v0, initial_velocity_particles, gAll, NULL, -v, NULL)
+fix(BC_Wall, velocity_nodes, gWall, NULL, 0, NULL)
+fix(BC_Axis, velocity_nodes, gAxis, 0, NULL, NULL)
+dt_factor(0.25)
+"""
+
+
+FULL_THERMAL = dict(Gamma=1.2, cv=500, m=1.1, d4=0.02, d5=0.6, alpha="2e-3", depsdot0=0.01)
 
 # name -> (script, is_TL, thermal, steps)
 CASES = {
@@ -458,4 +507,16 @@ CASES = {
     "x_delete_particles_tl": (carved_disks(True), True, False, 100),
     "x_two_spheres_3d": (two_spheres(), False, False, 100),
     "x_tensile_tl_cubic": (tensile(False, shape="cubic-spline", vgrip=20), True, False, 100),
+    # functor branches no BASELINE example reaches: Swift and linear
+    # strength through the cell stress kernel; Mie-Gruneisen energy term (Gamma, cv != 0), JC thermal softening (m != 0), JC
+    # failure strain with the rate (d4) and temperature (d5) factors, thermal pressure alpha (T0 - T) - total- and updated-Lagrangian,
+    # thermo-mechanical, with temperatures imposed on both sides of Tr
+    "p_block_swift": (block((8, 8, 8), "musl", strength="swift"), False, False, 100),
+    "p_block_linear_strength": (block((8, 8, 8), "musl", strength="linear"), False, False, 100),
+    "p_thermal_full_tl": (heated_bar(**FULL_THERMAL), True, True, 100),
+    "p_thermal_full_ul": (heated_bar(kind="ulmpm", shape="cubic-spline", vgrip=20, **FULL_THERMAL), False, True, 100),
+    # axisymmetric 2-D (hoop terms of the scatter, the gradient and the lattice masses)
+    "p_axisym_ul_cubic_musl": (axisym_bar(), False, False, 100),
+    "p_axisym_ul_linear_usl": (axisym_bar("ulmpm", "linear", "usl"), False, False, 100),
+    "p_axisym_tl_linear": (axisym_bar("tlmpm", "linear"), True, False, 100),
 }

@@ -74,3 +74,14 @@ def compare_snaps(a, b, tol):
     bad = {k: v for k, v in worst.items() if v > tol}
     assert not bad, "fields beyond tolerance %g: %s (all: %s)" % (tol, bad, worst)
     return worst
+
+
+def permute_particles(e, seed=1, solid=0):
+    """Shuffle the particle arrays of a freshly populated solid in place (tags keep their identity): nothing in the step may depend on
+    the order particles were created in (the reference rebuilds its neighbour lists every step, src/ulmpm.cpp:140-156)."""
+    fields = [P.PTAG, P.X, P.X0, P.V, P.MASS, P.VOL0, P.VOL, P.RHO0, P.MASK]
+    data = [e.download(solid, f) for f in fields]
+    perm = np.random.default_rng(seed).permutation(len(data[0]))
+    for f, a in zip(fields, data):
+        e.upload(solid, f, np.ascontiguousarray(a[perm]))
+    return perm

@@ -1,0 +1,32 @@
+"""Particle order independence: the headline block with its particle arrays randomly permuted before step 1 must reproduce the
+reference's golden state (keyed by tag).  The cell-sorted kernels index particles through the re-bin order of every step, so a
+shuffled population turns every SoA stream into a gather - results must not change (SURVEY section 8d S0', VERDICT r1 missing #4)."""
+import pytest
+
+from cases import CASES
+from common import FIELDS, compare_to_golden, load_golden, permute_particles
+from karamelo_b200.api import Engine
+
+
+def _run(lib, name, seed):
+    script, is_tl, thermal, steps = CASES[name]
+    e = Engine(lib)
+    e.script(script)
+    perm = permute_particles(e, seed)
+    assert (perm != range(len(perm))).any()
+    e.line("run(%d)" % steps)
+    snap = e.snapshot(FIELDS)
+    e.close()
+    return snap
+
+
+def test_oracle_shuffled_block(oracle_lib):
+    golden, _ = load_golden("c5_block_musl")
+    print(compare_to_golden(_run(oracle_lib, "c5_block_musl", 3), golden, 1e-10))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c5_block_musl", "e_block_two_segments", "p_block_swift", "c2_taylor_cubic"])
+def test_cuda_shuffled(cuda_lib, name):
+    golden, _ = load_golden(name)
+    print(name, compare_to_golden(_run(cuda_lib, name, 7), golden, 1e-10))
