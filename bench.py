@@ -39,23 +39,10 @@ A_SQUEEZE = 2.5e-4
 WORKLOAD = "synthetic 3-D ULMPM elastoplastic block (configs[4]): cubic B-splines, MUSL, FLIP 0.99, linear EOS + plastic strength, adaptive dt"
 
 
-def block_script(cells, velocity_fix):
+def block_script(cells):
+    """SURVEY section 8d's script: the block, its material, the isochoric squeeze as fix initial_velocity_particles"""
     from cases import block
-    s = block(tuple(cells), "musl", "cubic-spline", fixed_dt=False, a=A_SQUEEZE)
-    if not velocity_fix:
-        s = "\n".join(ln for ln in s.splitlines() if not ln.startswith("fix(v0")) + "\n"
-    return s
-
-
-def squeeze_velocity(x, cells):
-    """isochoric uniaxial squeeze, linear in position; a goes through the script's float literal path"""
-    a = float(np.float32(2.5)) * 10.0 ** -4
-    c = np.array([4 + cells[0] / 2, 4 + cells[1] / 2, 4 + cells[2] / 2])
-    v = np.empty_like(x)
-    v[:, 0] = -a * (x[:, 0] - c[0])
-    v[:, 1] = 0.5 * a * (x[:, 1] - c[1])
-    v[:, 2] = 0.5 * a * (x[:, 2] - c[2])
-    return v
+    return block(tuple(cells), "musl", "cubic-spline", fixed_dt=False, a=A_SQUEEZE)
 
 
 class ClockSampler(threading.Thread):
@@ -137,7 +124,7 @@ def profiled_traffic(stage):
 def cpu_baseline(sample_cells=(24, 24, 24), nsteps=6):
     """The reference's CPU path on a bounded sample of the same workload, on this box's host cores.
     kind 'reference' = the unmodified reference binary (oracle/_ref), else 'port' = oracle/oracle_kml.cpp."""
-    script = block_script(sample_cells, velocity_fix=True)
+    script = block_script(sample_cells)
     npart = sample_cells[0] * sample_cells[1] * sample_cells[2] * 8
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "karamelo_ref")
     import tempfile
@@ -221,10 +208,7 @@ def check_against_single_gpu(eng, cells, steps_done, rank, world, local, dist):
         got = {f: v[order] for f, v in got.items()}
         t0 = time.perf_counter()
         ref_eng = Engine(None, device=local)
-        ref_eng.script(block_script(cells, velocity_fix=False))
-        x = ref_eng.download(0, P.X)
-        ref_eng.upload(0, P.V, squeeze_velocity(x, cells))
-        del x
+        ref_eng.script(block_script(cells))
         ref_eng.line("run(%d)" % steps_done)
         ref = _sample(ref_eng)
         ref_flags = ref_eng.error_flags()
@@ -267,11 +251,9 @@ def run_ours(args):
 
     eng = slab.make_engine(None)
     t0 = time.perf_counter()
-    eng.script(block_script(cells, velocity_fix=False))
-    x = eng.download(0, P.X)
-    eng.upload(0, P.V, squeeze_velocity(x, cells))
-    np_local = len(x)
-    del x
+    eng.script(block_script(cells))   # SURVEY 8d's script, unmodified: lattice, group mask and the initial_velocity_particles expressions run on the device
+    eng.synchronize()
+    np_local = eng.solid_info(0)["np"]
     setup_s = time.perf_counter() - t0
     npart = eng.slab_info(0)["np_global"] if world > 1 else np_local
 

@@ -197,6 +197,55 @@ int kml_solid_delete_particles(kml_ctx *ctx, int solid_id, const int *dlist);
  * (synthetic blocks): device pointer of the SoA component `comp` of `field`. */
 int kml_solid_device_ptr(kml_ctx *ctx, int solid_id, int field, int comp, void **dptr);
 
+/* ---- set-up on the device ------------------------------------------------------------------
+ * Region::inside of src/region_block.cpp:141-148, src/region_cylinder.cpp:140-161, src/region_sphere.cpp:120-127.
+ *   block: p = xlo, xhi, ylo, yhi, zlo, zhi;  cylinder (axis 0 x | 1 y | 2 z): p = c1, c2, R^2, lo, hi;  sphere: p = c1, c2, c3, R^2.
+ * interior = 0 inverts the test in Region::match (src/region.cpp:64-72). */
+enum { KML_REGION_BLOCK = 0, KML_REGION_CYLINDER = 1, KML_REGION_SPHERE = 2 };
+typedef struct kml_region { int style, interior, axis, pad_; double p[6]; } kml_region;
+/* The particle lattice of Solid::populate (src/solid.cpp:1927-2127, :2155-2183): cells i -> j -> k of the solid's bounding box, nip
+ * sub-points per cell at offsets ip (in cell units), position boundlo + delta (noffsetlo + i + 0.5 + ip); a point becomes a particle
+ * iff it lies in the sub-domain and in the region.  Particles are numbered in lattice order (src/solid.cpp:2322). */
+typedef struct kml_lattice {
+  double boundlo[3], delta;
+  int noffsetlo[3], nsub[3];
+  int nip, dim;
+  double ip[3 * 64];            /* nip <= 64 (4 particles per cell and direction) */
+  double sublo[3], subhi[3];    /* Domain::inside_subdomain */
+  double mass, vol, T0;         /* per particle; axisymmetric: mass x0[0], vol = mass / rho0 (src/solid.cpp:2292-2298) */
+  int axisymmetric, set_T;
+  double rho0;
+  int64_t tag_first;            /* tag of the first particle of the whole (undecomposed) lattice */
+  /* slab decomposition: keep the points whose global stencil base (int)((x - slab_lo) slab_ih [- 1]) lies in [base_lo, base_hi) */
+  int slab, slab_linear, base_lo, base_hi;
+  double slab_lo, slab_ih;
+} kml_lattice;
+/* 1 if this library can populate / assign groups / evaluate per-particle expressions itself (the CUDA engine), 0 otherwise. */
+int kml_has_device_setup(void);
+/* hist[b] = number of lattice points that become particles with clamped global stencil base b (0 <= b < nbins; every point goes to
+ * bin 0 when lat->slab == 0).  The host derives the particle count, the slab cuts and the tag offsets from it. */
+int kml_lattice_histogram(kml_ctx *ctx, const kml_lattice *lat, const kml_region *reg, int64_t *hist, int nbins);
+/* Solid::populate, src/solid.cpp:2283-2336: fills a solid created with desc.np = the number of accepted points (of this slab):
+ * ptag, x = x0, mass, vol0 = vol, T, F = R = I, mask = 1, everything else 0.  tag_offset = accepted points of lower slabs. */
+int kml_solid_populate(kml_ctx *ctx, int solid_id, const kml_lattice *lat, const kml_region *reg, int64_t tag_offset);
+/* Group::assign for a particle group, src/group.cpp:140-181: mask |= bit where the region matches the REFERENCE position. */
+int kml_solid_group_assign(kml_ctx *ctx, int solid_id, const kml_region *reg, int bit, int64_t *count);
+/* sum over the particles of component comp of a field (Solid::init totals, src/solid.cpp:170-195) */
+int kml_solid_sum(kml_ctx *ctx, int solid_id, int field, int comp, double *sum);
+
+/* Per-particle expressions of the script language, compiled by the host from the token stream of its parser into a postfix
+ * program (the reference re-parses the expression string for every particle, e.g. src/fix_initial_velocity_particles.cpp:99-161).
+ * Operands: constants, the particle variables x, y, z, x0, y0, z0.  +, -, *, /, sqrt are IEEE-exact on the device; pow, exp, log,
+ * sin, cos, tan, atan2 are the CUDA math library's (<= 2 ulp from the host's). */
+enum { KML_X_CONST = 0, KML_X_VAR /* val = 0..5: x y z x0 y0 z0 */, KML_X_ADD, KML_X_SUB, KML_X_MUL, KML_X_DIV, KML_X_POW, KML_X_NEG, KML_X_NOT,
+       KML_X_GT, KML_X_GE, KML_X_LT, KML_X_LE, KML_X_EQ, KML_X_NE, KML_X_EXP, KML_X_SQRT, KML_X_COS, KML_X_SIN, KML_X_TAN, KML_X_LOG, KML_X_ATAN2 };
+#define KML_EXPR_MAX 96
+typedef struct kml_expr { int n; int op[KML_EXPR_MAX]; double val[KML_EXPR_MAX]; } kml_expr;
+/* FixInitialVelocityParticles::initial_integrate (src/fix_initial_velocity_particles.cpp:99-161) and the other fixes that SET a
+ * particle vector per component: field (KML_P_V) component d of every particle of the group = prog[d](x, y, z, x0, y0, z0)
+ * for the components in set_mask.  solid = -1: every solid. */
+int kml_fix_set_particles_expr(kml_ctx *ctx, int solid, int groupbit, int field, int set_mask, const kml_expr prog[3]);
+
 /* Update::dt (src/update.h:29); Update::set_dt / ULMPM::adjust_dt write it. */
 int kml_set_dt(kml_ctx *ctx, double dt);
 int kml_get_dt(kml_ctx *ctx, double *dt);

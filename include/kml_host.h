@@ -27,6 +27,13 @@ int kmlh_nsolids(kmlh_sim *s, int *n);
 int kmlh_solid_info(kmlh_sim *s, int i, int64_t *np, int *solid_id, int *grid_id, int n[3]);
 int kmlh_state(kmlh_sim *s, int64_t *ntimestep, double *time, double *dt);
 kml_ctx *kmlh_ctx(kmlh_sim *s);
+/* Script expressions: evaluate one (Input::parsev + Var::result), publish a per-particle variable (x, y, z, x0, y0, z0) the way the fixes do
+ * before every evaluation, and compile an expression into the postfix program of include/kml.h (kml_expr). */
+int kmlh_eval(kmlh_sim *s, const char *expr, double *value);
+int kmlh_set_particle_var(kmlh_sim *s, const char *name, double value);
+int kmlh_compile_expr(kmlh_sim *s, const char *expr, int *n, int *ops, double *vals);
+/* Runs the fixes' initial_integrate hooks as step 1 would (initial_velocity_particles, initial_stress ...) without taking a step. */
+int kmlh_apply_initial_fixes(kmlh_sim *s);
 #ifdef __cplusplus
 }
 #endif

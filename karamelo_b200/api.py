@@ -97,6 +97,10 @@ def load_host_library(path=None):
         "kmlh_solid_info": (i32, [vp, i32, PL, PI, PI, PI]),
         "kmlh_state": (i32, [vp, PL, PD, PD]),
         "kmlh_ctx": (vp, [vp]),
+        "kmlh_apply_initial_fixes": (i32, [vp]),
+        "kmlh_eval": (i32, [vp, C.c_char_p, PD]),
+        "kmlh_set_particle_var": (i32, [vp, C.c_char_p, dbl]),
+        "kmlh_compile_expr": (i32, [vp, C.c_char_p, PI, PI, PD]),
         "kmlh_set_ranks": (i32, [vp, i32, i32, vp]),
         "kmlh_slab_info": (i32, [vp, i32, PL]),
         "kml_comm_unique_id": (i32, [vp]),
@@ -178,6 +182,14 @@ class Engine:
     # -- script -------------------------------------------------------------------------
     def line(self, text):
         self._ck(self.lib.kmlh_run_line(self.h, text.encode()))
+
+    def var_eval(self, expr):
+        v = C.c_double(0)
+        self._ck(self.lib.kmlh_eval(self.h, expr.encode(), C.byref(v)))
+        return v.value
+
+    def apply_initial_fixes(self):
+        self._ck(self.lib.kmlh_apply_initial_fixes(self.h))
 
     def script(self, text):
         for ln in text.splitlines():

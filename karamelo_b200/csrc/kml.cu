@@ -5,6 +5,7 @@
 #include "kml_gather_cell2.cuh"
 #include "kml_comm.cuh"
 #include "kml_cpdi.cuh"
+#include "kml_setup.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -36,6 +37,9 @@ struct Solid {
   double dtCFL = 1.0e22;
   unsigned long long gen = 1; // kml_solid_generation
   double *accbuf = nullptr;   // kml_keep_particle_acceleration: a_p, v_update_p
+  // physical re-ordering: second set of buffers, swapped with the current one by permute_solid
+  int nd = 0; double *buf2 = nullptr; long long *lbuf2 = nullptr; int *ibuf2 = nullptr; bool no_permute = false;
+  long long permutes = 0, last_permute_step = -1000000;
 };
 
 struct kml_ctx {
@@ -50,6 +54,7 @@ struct kml_ctx {
   bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
+  double permute_frac = 0.05; int permute_min_steps = 8; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
@@ -177,6 +182,8 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
   c->cell_mask = env_int("KML_CELL_MASK", 7);
+  { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
+  c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 8);
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
   auto seg_env = [&](const char *name, int dflt) { return std::min(std::max(env_int(name, env_int("KML_SEGLEN", dflt)), 8), 96); };
@@ -191,7 +198,7 @@ int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
-  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); cudaFree(s->accbuf); delete s; }
+  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
@@ -320,6 +327,55 @@ static const int SOLID_NDBL_UL = 3 * 6 + 6 + 6 + 9 + 11;
 static const int SOLID_NDBL_TL = SOLID_NDBL_UL + 18;
 
 static int alloc_acc(kml_ctx *c, Solid *S);
+// SoA component pointers of the solid's current buffers (the physical permute swaps buffers)
+static void bind_pointers(kml_ctx *c, Solid *S) {
+  SolidDev &s = S->s; const long long cap = S->cap;
+  double *p = S->buf; auto take = [&]() { double *r = p; p += cap; return r; };
+  for (int k = 0; k < 3; k++) s.x[k] = take(); for (int k = 0; k < 3; k++) s.xn[k] = take(); for (int k = 0; k < 3; k++) s.x0[k] = take();
+  for (int k = 0; k < 3; k++) s.v[k] = take(); for (int k = 0; k < 3; k++) s.mbp[k] = take(); for (int k = 0; k < 3; k++) s.q[k] = take();
+  for (int k = 0; k < 6; k++) s.sig[k] = take(); for (int k = 0; k < 6; k++) s.eel[k] = take(); for (int k = 0; k < 9; k++) s.F[k] = take();
+  s.vol0 = take(); s.vol = take(); s.rho0 = take(); s.mass = take(); s.eps = take(); s.epsdot = take(); s.dmg = take(); s.dmgi = take();
+  s.ien = take(); s.T = take(); s.gamma = take();
+  if (c->c.is_TL) { for (int k = 0; k < 9; k++) s.pk1[k] = take(); for (int k = 0; k < 9; k++) s.R[k] = take(); }
+  else { for (int k = 0; k < 9; k++) { s.pk1[k] = nullptr; s.R[k] = nullptr; } }
+  for (int k = 0; k < 9; k++) s.Lst[k] = (c->apic || c->c.ge) ? take() : nullptr;
+  s.ptag = S->lbuf; s.mask = S->ibuf;
+}
+
+// Physical re-ordering (SURVEY section 8d S0'): particle state gathered into cell order through the re-bin's order[], into the solid's second
+// buffer, which then becomes current.  The cell-sorted kernels read 31-55 SoA streams per particle through order[]; while order[] is close to
+// the identity those streams coalesce, but mixing (and, on a decomposed run, migration: arrivals are appended, holes are filled from the tail)
+// turns them into sector-granular gathers.  xn (scratch between grid_to_points and the next weight evaluation) is not copied.
+__global__ void k_permute(const double *__restrict__ src, double *__restrict__ dst, long long cap, int nd, const int *__restrict__ order, long long np,
+                          const long long *__restrict__ tsrc, long long *__restrict__ tdst, const int *__restrict__ msrc, int *__restrict__ mdst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const long long j = order[i];
+  for (int a = 0; a < nd; a++) { if (a >= 3 && a < 6) continue; dst[a * cap + i] = src[a * cap + j]; }
+  tdst[i] = tsrc[j]; mdst[i] = msrc[j];
+}
+__global__ void k_iota(int *a, long long n) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = (int)i; }
+
+static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
+  if (S->no_permute || S->accbuf || S->cpbuf) return 0;
+  if (!S->buf2) {
+    const size_t bytes = sizeof(double) * S->cap * S->nd;
+    if (cudaMalloc(&S->buf2, bytes) != cudaSuccess || cudaMalloc(&S->lbuf2, sizeof(long long) * S->cap) != cudaSuccess || cudaMalloc(&S->ibuf2, sizeof(int) * S->cap) != cudaSuccess) {
+      cudaGetLastError(); cudaFree(S->buf2); cudaFree(S->lbuf2); cudaFree(S->ibuf2); S->buf2 = nullptr; S->lbuf2 = nullptr; S->ibuf2 = nullptr;
+      S->no_permute = true; return 0; // not enough memory for the second buffer: keep the index-only order
+    }
+    CU(cudaMemsetAsync(S->buf2, 0, bytes, c->stream));
+  }
+  const long long np = S->s.np;
+  k_permute<<<nblocks(np, 128), 128, 0, c->stream>>>(S->buf, S->buf2, S->cap, S->nd, G->cl.order, np, S->lbuf, S->lbuf2, S->ibuf, S->ibuf2);
+  k_iota<<<nblocks(np, 256), 256, 0, c->stream>>>(G->cl.order, np);
+  if (check_launch("k_permute")) return 1;
+  std::swap(S->buf, S->buf2); std::swap(S->lbuf, S->lbuf2); std::swap(S->ibuf, S->ibuf2);
+  bind_pointers(c, S); S->gen++; S->permutes++;
+  c->launches[KML_STAGE_REBIN] += 2;
+  return 0;
+}
+
 int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaSetDevice(c->dev));
   const bool rigid_ = d->mat.rigid || d->mat.type == KML_MAT_RIGID;
@@ -338,24 +394,9 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaMalloc(&S->lbuf, sizeof(long long) * cap)); CU(cudaMemsetAsync(S->lbuf, 0, sizeof(long long) * cap, c->stream));
   CU(cudaMalloc(&S->ibuf, sizeof(int) * cap));
   CU(cudaMalloc(&S->red, sizeof(double) * 2));
-  double *p = S->buf; auto take = [&]() { double *r = p; p += cap; return r; };
-  for (int k = 0; k < 3; k++) s.x[k] = take(); for (int k = 0; k < 3; k++) s.xn[k] = take(); for (int k = 0; k < 3; k++) s.x0[k] = take();
-  for (int k = 0; k < 3; k++) s.v[k] = take(); for (int k = 0; k < 3; k++) s.mbp[k] = take(); for (int k = 0; k < 3; k++) s.q[k] = take();
-  for (int k = 0; k < 6; k++) s.sig[k] = take(); for (int k = 0; k < 6; k++) s.eel[k] = take(); for (int k = 0; k < 9; k++) s.F[k] = take();
-  s.vol0 = take(); s.vol = take(); s.rho0 = take(); s.mass = take(); s.eps = take(); s.epsdot = take(); s.dmg = take(); s.dmgi = take();
-  s.ien = take(); s.T = take(); s.gamma = take();
-  if (c->c.is_TL) { for (int k = 0; k < 9; k++) s.pk1[k] = take(); for (int k = 0; k < 9; k++) s.R[k] = take(); }
-  else { for (int k = 0; k < 9; k++) { s.pk1[k] = nullptr; s.R[k] = nullptr; } }
-  for (int k = 0; k < 9; k++) s.Lst[k] = (c->apic || c->c.ge) ? take() : nullptr;
-  s.ptag = S->lbuf; s.mask = S->ibuf;
+  S->nd = nd; bind_pointers(c, S);
   // initial values of Solid::populate, src/solid.cpp:2283-2321: F = R = I, rho0 = mat.rho0, mask = 1
-  std::vector<double> ones(d->np, 1.0), rho(d->np, d->mat.rho0); std::vector<int> m1(d->np, 1);
-  for (int k : {0, 4, 8}) {
-    CU(cudaMemcpyAsync(s.F[k], ones.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
-    if (c->c.is_TL) CU(cudaMemcpyAsync(s.R[k], ones.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
-  }
-  CU(cudaMemcpyAsync(s.rho0, rho.data(), sizeof(double) * d->np, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(s.mask, m1.data(), sizeof(int) * d->np, cudaMemcpyHostToDevice, c->stream));
+  if (d->np > 0) { k_solid_init<<<nblocks(d->np, 256), 256, 0, c->stream>>>(s, d->mat.rho0); if (check_launch("k_solid_init")) return 1; }
   if (c->c.is_CPDI) {
     CpdiDev &cp = S->cp; cp.style = c->c.cpdi_style; cp.cap = cap; cp.maxn = c->c.shape_function == KML_SHAPE_LINEAR ? 16 : CPDI_MAXN;
     const size_t per = (size_t)cp.maxn * cap;
@@ -554,6 +595,102 @@ int kml_solid_device_ptr(kml_ctx *c, int sid, int field, int comp_idx, void **dp
   *dptr = comp[comp_idx]; return 0;
 }
 
+// ---- set-up on the device ---------------------------------------------------------------------------
+int kml_has_device_setup(void) { return 1; }
+
+static long long lattice_points(const kml_lattice *l) { return (long long)l->nsub[0] * l->nsub[1] * l->nsub[2] * l->nip; }
+
+int kml_lattice_histogram(kml_ctx *c, const kml_lattice *lat, const kml_region *reg, int64_t *hist, int nbins) {
+  CU(cudaSetDevice(c->dev));
+  if (lat->nip > 64 || nbins < 1) return fail("kml_lattice_histogram: bad arguments");
+  const long long ntot = lattice_points(lat);
+  unsigned long long *d_hist = nullptr;
+  CU(cudaMalloc(&d_hist, sizeof(unsigned long long) * nbins)); CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, c->stream));
+  if (ntot > 0) k_lattice_hist<<<nblocks(ntot, 256), 256, 0, c->stream>>>(*lat, *reg, ntot, d_hist, nbins);
+  const int rc = check_launch("k_lattice_hist");
+  static_assert(sizeof(int64_t) == sizeof(unsigned long long), "64-bit histogram");
+  if (!rc) { CU(cudaMemcpyAsync(hist, d_hist, sizeof(int64_t) * nbins, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); }
+  cudaFree(d_hist);
+  return rc;
+}
+
+int kml_solid_populate(kml_ctx *c, int sid, const kml_lattice *lat, const kml_region *reg, int64_t tag_offset) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid];
+  if (c->c.is_CPDI) return fail("kml_solid_populate: CPDI particle domains are set up by the host");
+  const long long ntot = lattice_points(lat);
+  if (ntot <= 0) return fail("kml_solid_populate: empty lattice");
+  const long long nb = (ntot + LATTICE_BLOCK - 1) / LATTICE_BLOCK;
+  long long *d_cnt = nullptr; void *d_tmp = nullptr; size_t tmp_bytes = 0;
+  CU(cudaMalloc(&d_cnt, sizeof(long long) * (nb + 1)));
+  CU(cudaMemsetAsync(d_cnt + nb, 0, sizeof(long long), c->stream));
+  k_lattice_count<<<(unsigned)nb, LATTICE_BLOCK, 0, c->stream>>>(*lat, *reg, ntot, d_cnt);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_cnt, (int)(nb + 1), c->stream);
+  if (cudaMalloc(&d_tmp, tmp_bytes) != cudaSuccess) { cudaFree(d_cnt); return fail("kml_solid_populate: out of memory"); }
+  cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, d_cnt, (int)(nb + 1), c->stream);
+  long long total = 0;
+  CU(cudaMemcpyAsync(&total, d_cnt + nb, sizeof(long long), cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  int rc = 0;
+  if (total != S->s.np) rc = fail("kml_solid_populate: the lattice yields " + std::to_string(total) + " particles, the solid was created for " + std::to_string(S->s.np));
+  else {
+    k_lattice_fill<<<(unsigned)nb, LATTICE_BLOCK, 0, c->stream>>>(*lat, *reg, ntot, d_cnt, S->s, (long long)(lat->tag_first + tag_offset));
+    rc = check_launch("k_lattice_fill");
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(d_cnt); cudaFree(d_tmp);
+  S->gen++;
+  return rc;
+}
+
+int kml_solid_group_assign(kml_ctx *c, int sid, const kml_region *reg, int bit, int64_t *count) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid];
+  unsigned long long *cnt = (unsigned long long *)(c->d_scratch + 24);
+  CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+  if (S->s.np > 0) k_group_assign<<<nblocks(S->s.np, 256), 256, 0, c->stream>>>(S->s, *reg, bit, cnt);
+  if (check_launch("k_group_assign")) return 1;
+  CU(cudaMemcpyAsync(c->h_pinned + 56, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  unsigned long long n; memcpy(&n, c->h_pinned + 56, sizeof n);
+  if (count) *count = (int64_t)n;
+  S->gen++;
+  return 0;
+}
+
+int kml_solid_sum(kml_ctx *c, int sid, int field, int comp_idx, double *sum) {
+  CU(cudaSetDevice(c->dev));
+  Solid *S = c->solids[sid];
+  double *comp[9]; int nc; bool sym;
+  if (solid_field(c, S, field, comp, &nc, &sym)) return 1;
+  if (comp_idx < 0 || comp_idx >= nc) return fail("component out of range");
+  CU(cudaMemsetAsync(c->d_scratch + 8, 0, sizeof(double), c->stream));
+  if (S->s.np > 0) k_sum<<<std::min<unsigned>(nblocks(S->s.np, 256), 148 * 8), 256, 0, c->stream>>>(comp[comp_idx], S->s.np, c->d_scratch + 8);
+  if (check_launch("k_sum")) return 1;
+  CU(cudaMemcpyAsync(c->h_pinned + 40, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+  *sum = c->h_pinned[40]; return 0;
+}
+
+int kml_fix_set_particles_expr(kml_ctx *c, int solid, int groupbit, int field, int set_mask, const kml_expr prog[3]) {
+  CU(cudaSetDevice(c->dev));
+  for (int d = 0; d < 3; d++) if ((set_mask & (1 << d)) && (prog[d].n < 1 || prog[d].n > KML_EXPR_MAX)) return fail("kml_fix_set_particles_expr: bad program");
+  ExprSet *d_prog = nullptr;
+  CU(cudaMalloc(&d_prog, sizeof(ExprSet)));
+  CU(cudaMemcpyAsync(d_prog, prog, sizeof(ExprSet), cudaMemcpyHostToDevice, c->stream));
+  int rc = 0;
+  for (size_t is = 0; is < c->solids.size() && !rc; is++) {
+    if (solid != -1 && (int)is != solid) continue;
+    Solid *S = c->solids[is];
+    if (S->s.np == 0) continue;
+    double *comp[9]; int nc; bool sym;
+    if (solid_field(c, S, field, comp, &nc, &sym) || nc != 3) { rc = fail("kml_fix_set_particles_expr: the field must be a particle vector"); break; }
+    k_set_particles_expr<<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, groupbit, comp[0], comp[1], comp[2], set_mask, d_prog, (!c->c.is_TL && S->moved) ? 1 : 0);
+    c->launches[KML_STAGE_OTHER]++;
+    rc = check_launch("k_set_particles_expr");
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_prog);
+  return rc;
+}
+
 int kml_set_dt(kml_ctx *c, double dt) { c->dt = dt; return 0; }
 int kml_get_dt(kml_ctx *c, double *dt) { *dt = c->dt; return 0; }
 
@@ -606,6 +743,16 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
         int nl = 0;
         if (G->cl.build(S->s, G->g, S->cap, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
         c->launches[KML_STAGE_REBIN] += nl;
+        // physical re-ordering when too many particles sit far from their cell-sorted position (the count of the PREVIOUS re-bin, read
+        // without a synchronisation; the first re-bin waits for its own)
+        if (c->permute_frac >= 0 && G->cl.valid) {
+          if (c->steps_started == 1) { CU(cudaStreamSynchronize(c->stream)); }
+          const long long far = *G->cl.h_disorder;
+          if (far > c->permute_frac * (double)S->s.np && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
+            if (permute_solid(c, S, G)) return 1;
+            S->last_permute_step = c->steps_started; *G->cl.h_disorder = 0;
+          }
+        }
         if (c->solids.size() > 1) break; // cell lists are per grid; several solids on one grid use the atomic path
       }
     }

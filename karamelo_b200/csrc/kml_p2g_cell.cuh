@@ -20,10 +20,12 @@ struct CellLists {
   int *start = nullptr;     // [ncells + 1] counts, then exclusive offsets
   int *order = nullptr;     // [np] particle ids grouped by cell
   void *scan_tmp = nullptr; size_t scan_bytes = 0;
+  int *disorder = nullptr;  // device: particles whose cell-sorted slot is more than DISORDER_FAR entries away from their storage slot
+  int *h_disorder = nullptr; // pinned copy, refreshed asynchronously by every build
   int build(const SolidDev &s, const GridDev &g, long long capacity, cudaStream_t st, int *nlaunch);
   void release() {
-    cudaFree(cell_of); cudaFree(rank); cudaFree(start); cudaFree(order); cudaFree(scan_tmp);
-    cell_of = rank = start = order = nullptr; scan_tmp = nullptr; valid = false; ncells = cap_np = 0; scan_bytes = 0;
+    cudaFree(cell_of); cudaFree(rank); cudaFree(start); cudaFree(order); cudaFree(scan_tmp); cudaFree(disorder); if (h_disorder) cudaFreeHost(h_disorder);
+    cell_of = rank = start = order = nullptr; scan_tmp = nullptr; disorder = nullptr; h_disorder = nullptr; valid = false; ncells = cap_np = 0; scan_bytes = 0;
   }
 };
 
@@ -44,10 +46,17 @@ __global__ void k_cell_count(SolidDev s, GridDev g, int *cell_of, int *rank, int
   cell_of[ip] = key;
   rank[ip] = atomicAdd(&count[key], 1);
 }
-__global__ void k_cell_fill(long long np, const int *cell_of, const int *rank, const int *start, int *order) {
+constexpr int DISORDER_FAR = 64;
+__global__ void k_cell_fill(long long np, const int *cell_of, const int *rank, const int *start, int *order, int *disorder) {
   long long ip = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ip >= np) return;
-  order[start[cell_of[ip]] + rank[ip]] = (int)ip;
+  bool far = false;
+  if (ip < np) {
+    const int dst = start[cell_of[ip]] + rank[ip];
+    order[dst] = (int)ip;
+    far = abs(dst - (int)ip) > DISORDER_FAR; // this particle's state is not where the cell-sorted kernels stream
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, far);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(disorder, __popc(b));
 }
 
 inline int CellLists::build(const SolidDev &s, const GridDev &g, long long capacity, cudaStream_t st, int *nlaunch) {
@@ -61,12 +70,15 @@ inline int CellLists::build(const SolidDev &s, const GridDev &g, long long capac
         cudaMalloc(&start, sizeof(int) * (ncells + 1))) return 1;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, start, start, (int)(ncells + 1), st);
     if (cudaMalloc(&scan_tmp, scan_bytes)) return 1;
+    if (cudaMalloc(&disorder, sizeof(int)) || cudaMallocHost(&h_disorder, sizeof(int))) return 1;
+    *h_disorder = 0;
   }
-  if (cudaMemsetAsync(start, 0, sizeof(int) * (ncells + 1), st)) return 1;
+  if (cudaMemsetAsync(start, 0, sizeof(int) * (ncells + 1), st) || cudaMemsetAsync(disorder, 0, sizeof(int), st)) return 1;
   const unsigned nb = (unsigned)((s.np + 255) / 256);
   k_cell_count<<<nb, 256, 0, st>>>(s, g, cell_of, rank, start);
   if (cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, start, start, (int)(ncells + 1), st)) return 1;
-  k_cell_fill<<<nb, 256, 0, st>>>(s.np, cell_of, rank, start, order);
+  k_cell_fill<<<nb, 256, 0, st>>>(s.np, cell_of, rank, start, order, disorder);
+  if (cudaMemcpyAsync(h_disorder, disorder, sizeof(int), cudaMemcpyDeviceToHost, st)) return 1;
   *nlaunch = 4;
   if (cudaGetLastError() != cudaSuccess) return 1;
   valid = true; return 0;

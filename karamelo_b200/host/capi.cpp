@@ -42,4 +42,13 @@ int kmlh_solid_info(kmlh_sim *s, int i, int64_t *np, int *solid_id, int *grid_id
 }
 int kmlh_state(kmlh_sim *s, int64_t *nt, double *t, double *dt) { *nt = s->sim.ntimestep; *t = s->sim.atime; *dt = s->sim.dt; return 0; }
 kml_ctx *kmlh_ctx(kmlh_sim *s) { return s->sim.ctx; }
+int kmlh_eval(kmlh_sim *s, const char *expr, double *value) { GUARD(Var v = s->sim.input.parsev(expr); *value = v.result(&s->sim.input)) }
+int kmlh_set_particle_var(kmlh_sim *s, const char *name, double value) { GUARD(s->sim.input.vars[name] = Var(name, value)) }
+int kmlh_compile_expr(kmlh_sim *s, const char *expr, int *n, int *ops, double *vals) {
+  GUARD(kml_expr e; Var v = s->sim.input.parsev(expr); if (!s->sim.input.compile(v, &e)) fatal("expression does not fit a device program");
+        *n = e.n; for (int i = 0; i < e.n; i++) { ops[i] = e.op[i]; vals[i] = e.val[i]; })
+}
+int kmlh_apply_initial_fixes(kmlh_sim *s) { // the INITIAL_INTEGRATE hooks as the first step would run them (Scheme::run: ntimestep = 1)
+  GUARD(const int64_t keep = s->sim.ntimestep; s->sim.ntimestep = 1; try { s->sim.hooks(INITIAL_INTEGRATE); } catch (...) { s->sim.ntimestep = keep; throw; } s->sim.ntimestep = keep)
+}
 }

@@ -1,6 +1,7 @@
 // input.cpp - script interpreter; behaviour follows reference src/input.cpp (see input.h).
 #include "input.h"
 #include "sim.h"
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <fstream>
@@ -159,13 +160,18 @@ Var Input::parsev(std::string str) {
         if (at(i + 1) == '=' && at(i + 2) != '=' && i + 1 < n) {
           if (!values.empty() || !ops.empty()) fatal("Error: I do not understand when '=' is located in the middle of an expression\n");
           returnvar = word; i++;
-        } else if (i + 1 >= n && values.empty() && ops.empty()) {
+        } else if (i + 1 >= n && values.empty() && ops.empty() && !trace_active()) {
           Var r = negative ? -vars[word] : vars[word];
           if (!returnvar.empty()) { vars[returnvar] = r; announce(returnvar); }
           return r;
         } else {
-          if (negative) { values.push(-vars[word]); negative = false; }
-          else values.push(vars[word]);
+          Var leaf = vars[word];
+          if (trace_active()) { // particle variables become the leaves of the traced tree
+            static const char *pv[6] = {"x", "y", "z", "x0", "y0", "z0"};
+            for (int k = 0; k < 6; k++) if (word == pv[k]) leaf = Var(word, leaf.result(), false, xnode_make(KML_X_VAR, (double)k, nullptr, nullptr));
+          }
+          if (negative) { values.push(-leaf); negative = false; }
+          else values.push(leaf);
         }
       } else if (i + 1 < n && str[i + 1] == '=' && values.empty() && ops.empty()) {
         returnvar = word;
@@ -238,6 +244,29 @@ Var Input::evaluate_function(const std::string &func, const std::string &arg) {
   auto it = commands.find(func);
   if (it != commands.end()) return it->second(args);
   fatal("Error: Unknown function " + func + "\n");
+}
+
+// postorder emission; returns the evaluation stack depth the subtree needs (-1: the program does not fit)
+static int flatten(const XRef &n, kml_expr *out) {
+  if (!n) return -1;
+  int need = 1;
+  if (n->a) { need = flatten(n->a, out); if (need < 0) return -1; }
+  if (n->b) { const int nb = flatten(n->b, out); if (nb < 0) return -1; need = std::max(need, 1 + nb); }
+  if (out->n >= KML_EXPR_MAX) return -1;
+  out->op[out->n] = n->op; out->val[out->n] = n->val; out->n++;
+  return need;
+}
+
+bool Input::compile(const Var &v, kml_expr *out) {
+  out->n = 0;
+  if (v.is_constant()) { out->op[0] = KML_X_CONST; out->val[0] = v.result(); out->n = 1; return true; }
+  const bool was_echo = echo; echo = false;
+  trace_set(true);
+  Var r;
+  try { r = parsev(v.eq()); } catch (...) { trace_set(false); echo = was_echo; throw; }
+  trace_set(false); echo = was_echo;
+  const int need = flatten(r.xnode(), out);
+  return need > 0 && need <= 16; // the device evaluates on a 16-entry stack
 }
 
 Var Input::line(const std::string &text) {

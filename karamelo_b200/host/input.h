@@ -6,6 +6,7 @@
 // name(args...) dispatches to a command.  Commands are registered by the Sim.
 #pragma once
 #include "var.h"
+#include "../../include/kml.h"
 #include <functional>
 #include <map>
 #include <string>
@@ -22,6 +23,10 @@ public:
   Var line(const std::string &text);   // one script line (comments stripped)
   Var parsev(std::string str);         // src/input.cpp:374-735
   Var evaluate_function(const std::string &func, const std::string &arg); // src/input.cpp:242-349
+  // The expression of `v` as a postfix program over the particle variables (include/kml.h kml_expr): the equation string is parsed once
+  // more with tracing on, so literals take the same float path and the operations the same order as the per-particle re-parse of the
+  // reference.  Returns false when the program does not fit (the caller keeps the per-particle host evaluation).
+  bool compile(const Var &v, struct ::kml_expr *out);
 
   std::map<std::string, Var> vars;
   typedef std::function<Var(std::vector<std::string> &)> Command;

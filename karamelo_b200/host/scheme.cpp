@@ -34,6 +34,11 @@ struct FixInitialVelocityParticles : Fix {
   void initial_integrate(Sim &s) override {
     if (s.ntimestep != 1) return;
     const int solid = s.gsolid[igroup];
+    if (kml_has_device_setup()) { // the expressions as postfix programs, one kernel for the whole group
+      kml_expr prog[3]; int m = 0; bool ok = true;
+      for (int d = 0; d < 3; d++) { prog[d].n = 0; if (set[d]) { m |= 1 << d; ok = ok && s.input.compile(val[d], &prog[d]); } }
+      if (ok) { s.check(kml_fix_set_particles_expr(s.ctx, solid == -1 ? -1 : s.solids[solid]->dev, groupbit, KML_P_V, m, prog)); return; }
+    }
     for (size_t is = 0; is < s.solids.size(); is++) {
       if (solid != -1 && (int)is != solid) continue;
       SolidH &S = *s.solids[is]; s.sync(S);

@@ -2,6 +2,7 @@
 // Integer-deciding arithmetic is restated from the reference, cited inline.
 #include "sim.h"
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <iostream>
@@ -362,6 +363,7 @@ template <class T> void put(std::ostream &os, const T &v) { os.write(reinterpret
 struct Block : Region {
   int inside(double x, double y, double z) const override { return x >= lim[0] && x <= lim[1] && y >= lim[2] && y <= lim[3] && z >= lim[4] && z <= lim[5]; }
   void write_restart(std::ostream &os) const override { for (int k = 0; k < 6; k++) put(os, lim[k]); } // src/region_block.cpp:170-177
+  bool to_kml(kml_region &r) const override { r.style = KML_REGION_BLOCK; r.interior = interior; r.axis = 0; r.pad_ = 0; for (int k = 0; k < 6; k++) r.p[k] = lim[k]; return true; }
 };
 struct Cylinder : Region {
   char axis = 'z'; double c1 = 0, c2 = 0, R = 0, RSq = 0, lo = 0, hi = 0;
@@ -374,11 +376,18 @@ struct Cylinder : Region {
   void write_restart(std::ostream &os) const override { // src/region_cylinder.cpp:184-197
     put(os, c1); put(os, c2); put(os, R); put(os, lo); put(os, hi); put(os, axis); for (int k = 0; k < 6; k++) put(os, lim[k]);
   }
+  bool to_kml(kml_region &r) const override {
+    r.style = KML_REGION_CYLINDER; r.interior = interior; r.axis = axis == 'x' ? 0 : (axis == 'y' ? 1 : 2); r.pad_ = 0;
+    r.p[0] = c1; r.p[1] = c2; r.p[2] = RSq; r.p[3] = lo; r.p[4] = hi; r.p[5] = 0; return true;
+  }
 };
 struct Sphere : Region {
   double c1 = 0, c2 = 0, c3 = 0, R = 0, RSq = 0;
   int inside(double x, double y, double z) const override { return (x - c1) * (x - c1) + (y - c2) * (y - c2) + (z - c3) * (z - c3) <= RSq; }
   void write_restart(std::ostream &os) const override { put(os, c1); put(os, c2); put(os, c3); put(os, R); for (int k = 0; k < 6; k++) put(os, lim[k]); } // src/region_sphere.cpp:145-156
+  bool to_kml(kml_region &r) const override {
+    r.style = KML_REGION_SPHERE; r.interior = interior; r.axis = 0; r.pad_ = 0; r.p[0] = c1; r.p[1] = c2; r.p[2] = c3; r.p[3] = RSq; r.p[4] = r.p[5] = 0; return true;
+  }
 };
 } // namespace
 
@@ -847,6 +856,58 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   double lp = delta;
   if (ppc == 1) lp *= 0.5; else if (ppc == 2) lp *= 0.25; else if (ppc == 3) lp *= 1.0 / 6.0; else lp *= 1.0 / (2 * ppc);
 
+  // ---- populate on the device: the lattice is a pure function of (i, j, k, q); nothing of size np exists on the host
+  kml_region kreg;
+  if (kml_has_device_setup() && !is_CPDI && nip <= 64 && reg.to_kml(kreg) && !getenv("KML_HOST_POPULATE")) {
+    kml_lattice L; memset(&L, 0, sizeof L);
+    for (int d = 0; d < 3; d++) { L.boundlo[d] = boundlo[d]; L.noffsetlo[d] = noffsetlo[d]; L.nsub[d] = nsub[d]; L.sublo[d] = sublo[d]; L.subhi[d] = subhi[d]; }
+    L.delta = delta; L.nip = nip; L.dim = dimension;
+    for (int q = 0; q < 3 * nip; q++) L.ip[q] = ip[q];
+    L.mass = mass_; L.vol = vol_; L.T0 = s.T0; L.set_T = temp ? 1 : 0; L.axisymmetric = axisymmetric ? 1 : 0; L.rho0 = mat.rho0; L.tag_first = np_total + 1;
+    const bool slab = nranks > 1 && !is_TL;
+    GridH &g = *s.grid;
+    int nbins = 1;
+    if (slab) {
+      L.slab = 1; L.slab_linear = shape_function == KML_SHAPE_LINEAR; L.slab_lo = boxlo[0]; L.slab_ih = 1.0 / g.cellsize; L.base_lo = INT_MIN; L.base_hi = INT_MAX; nbins = g.nx_global + 1;
+      // tags must be contiguous per slab: every sub-point of a lattice column shares one stencil base, non-decreasing along x
+      int last = INT_MIN;
+      for (int i = 0; i < nsub[0]; i++) for (int q = 0; q < nip; q++) {
+        const double x = boundlo[0] + delta * (noffsetlo[0] + i + 0.5 + ip[3 * q]); const double t = (x - boxlo[0]) * L.slab_ih;
+        const int b = std::min(std::max(L.slab_linear ? (int)t : (int)(t - 1.0), 0), g.nx_global);
+        if (q > 0 ? b != last : b < last) fatal("slab decomposition: the particle lattice is not ordered along x\n");
+        last = b;
+      }
+    }
+    std::vector<int64_t> hist(nbins, 0);
+    check(kml_lattice_histogram(ctx, &L, &kreg, hist.data(), nbins));
+    int64_t np_global = 0, tag_offset = 0, np_local = 0;
+    for (int64_t h : hist) np_global += h;
+    if (slab) {
+      int base_lo, base_hi;
+      if (grid_pending) {
+        std::vector<int> cut(nranks + 1, 0); cut[nranks] = g.nx_global + 4;
+        int64_t cum = 0; int r = 1;
+        for (int b = 0; b <= g.nx_global && r < nranks; b++) { cum += hist[b]; while (r < nranks && cum >= (np_global * r) / nranks) cut[r++] = b + 1; }
+        base_lo = rank == 0 ? -4 : cut[rank]; base_hi = cut[rank + 1];
+        create_device_grid(g, base_lo, base_hi);
+      } else { base_lo = g.desc.base_lo; base_hi = g.desc.base_hi; }
+      for (int b = 0; b < nbins; b++) { if (b < base_lo) tag_offset += hist[b]; else if (b < base_hi) np_local += hist[b]; }
+      L.base_lo = base_lo; L.base_hi = base_hi;
+    } else np_local = np_global;
+    if (np_local == 0) fatal("Error: solid does not have any particles.\n");
+    s.np = np_local; s.np_created = np_global; s.mirror_gen = 0; s.x0.clear(); s.mask.clear(); s.ptag.clear();
+    kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
+    check(kml_solid_create(ctx, &d, &s.dev));
+    check(kml_solid_populate(ctx, s.dev, &L, &kreg, tag_offset));
+    np_total += np_global; np_global_last = np_global; tag_offset_last = tag_offset;
+    // Solid::init totals, src/solid.cpp:170-195: the reference adds particle after particle; every particle of a plane lattice carries the
+    // same volume and mass, so the same sequence of additions is repeated here (device reduction for axisymmetry and beyond 10^7 particles)
+    if (axisymmetric || s.np > 10000000) { check(kml_solid_sum(ctx, s.dev, KML_P_VOL, 0, &s.vtot)); check(kml_solid_sum(ctx, s.dev, KML_P_MASS, 0, &s.mtot)); }
+    else { s.vtot = s.mtot = 0; for (int64_t i = 0; i < s.np; i++) { s.vtot += vol_; s.mtot += mass_; } }
+    if (!quiet) std::cout << "Solid " << s.id << ": np=" << s.np << " total volume = " << s.vtot << " total mass = " << s.mtot << " grid " << s.grid->desc.n[0] << "x" << s.grid->desc.n[1] << "x" << s.grid->desc.n[2] << std::endl;
+    return;
+  }
+
   s.x0.clear();
   const int dim = dimension;
   auto lattice = [&](auto &&accept) {
@@ -949,8 +1010,12 @@ Var Sim::cmd_group(std::vector<std::string> &a) {
     for (size_t i = 5; i < a.size(); i++) { gsolid[ig] = find_solid(a[i]); if (gsolid[ig] == -1) fatal("Error: cannot find solid with ID " + a[i] + ".\n"); targets.push_back(gsolid[ig]); }
   } else fatal("Error: unknown keyword in group command: " + a[3] + ".\n");
   for (int is : targets) {
-    SolidH &s = *solids[is]; sync(s); int n = 0;
-    if (gpon[ig] == "particles") {
+    SolidH &s = *solids[is]; int n = 0;
+    kml_region kreg;
+    if (gpon[ig] == "particles" && kml_has_device_setup() && reg.to_kml(kreg) && !getenv("KML_HOST_POPULATE")) {
+      int64_t cnt = 0; check(kml_solid_group_assign(ctx, s.dev, &kreg, bit, &cnt)); n = (int)cnt; // Group::assign on the device (the mirrors follow lazily)
+    } else if (gpon[ig] == "particles") {
+      sync(s);
       for (int64_t ip = 0; ip < s.np; ip++) if (reg.match(s.x0[ip][0], s.x0[ip][1], s.x0[ip][2])) { s.mask[ip] |= bit; n++; }
       check(kml_solid_upload(ctx, s.dev, KML_P_MASK, s.mask.data())); mirrors_current(s);
     } else {

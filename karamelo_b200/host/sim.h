@@ -26,6 +26,7 @@ struct Region {
   virtual int inside(double x, double y, double z) const = 0;
   int match(double x, double y, double z) const { return interior ? inside(x, y, z) : !inside(x, y, z); } // src/region.cpp:64-72
   virtual void write_restart(std::ostream &) const {} // Region::write_restart of the style (src/region_block.cpp:170-177, ...)
+  virtual bool to_kml(kml_region &) const { return false; } // the predicate for the device kernels (block, cylinder, sphere)
 };
 
 struct MaterialH {

@@ -369,6 +369,18 @@ int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
 }
 int kml_solid_device_ptr(kml_ctx *, int, int, int, void **) { return fail("oracle: no device pointers"); }
 
+// set-up on the device is a feature of the CUDA engine; with this back end the host driver runs its own restated loops
+int kml_has_device_setup(void) { return 0; }
+int kml_lattice_histogram(kml_ctx *, const kml_lattice *, const kml_region *, int64_t *, int) { return fail("oracle: no device set-up"); }
+int kml_solid_populate(kml_ctx *, int, const kml_lattice *, const kml_region *, int64_t) { return fail("oracle: no device set-up"); }
+int kml_solid_group_assign(kml_ctx *, int, const kml_region *, int, int64_t *) { return fail("oracle: no device set-up"); }
+int kml_fix_set_particles_expr(kml_ctx *, int, int, int, int, const kml_expr *) { return fail("oracle: no device set-up"); }
+int kml_solid_sum(kml_ctx *c, int sid, int field, int comp, double *sum) {
+  OSolid *s = c->solids[sid]; double t = 0;
+  if (field == KML_P_VOL) for (double v : s->vol) t += v; else if (field == KML_P_MASS) for (double v : s->mass) t += v; else return fail("oracle: kml_solid_sum supports VOL and MASS");
+  (void)comp; *sum = t; return 0;
+}
+
 int kml_set_dt(kml_ctx *c, double dt) { c->dt = dt; return 0; }
 int kml_get_dt(kml_ctx *c, double *dt) { *dt = c->dt; return 0; }
 

@@ -27,6 +27,14 @@ def test_oracle_shuffled_block(oracle_lib):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["c5_block_musl", "e_block_two_segments", "p_block_swift", "c2_taylor_cubic"])
-def test_cuda_shuffled(cuda_lib, name):
+@pytest.mark.parametrize("policy", ["default", "never", "often"])
+def test_cuda_shuffled(cuda_lib, name, policy, monkeypatch):
+    """default: the engine re-orders the shuffled state physically at the first re-bin (kml.cu permute_solid); never: index-only order,
+    every stream a gather; often: a physical permute every third step whenever a single particle is out of place."""
+    if policy == "never":
+        monkeypatch.setenv("KML_PERMUTE_FRAC", "-1")
+    elif policy == "often":
+        monkeypatch.setenv("KML_PERMUTE_FRAC", "0")
+        monkeypatch.setenv("KML_PERMUTE_MIN_STEPS", "3")
     golden, _ = load_golden(name)
-    print(name, compare_to_golden(_run(cuda_lib, name, 7), golden, 1e-10))
+    print(name, policy, compare_to_golden(_run(cuda_lib, name, 7), golden, 1e-10))

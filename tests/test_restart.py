@@ -54,8 +54,11 @@ def test_write_restart_command_only_records_the_name(tmp_path):
 CONTINUE = ("read_restart(rst-20.restart)\nrestart(20, cont-*.restart)\n"
             "dump(d1, all, particle, 20, dump_p.*.LAMMPS, x, y, z, vx, vy, s11, s12, ep, damage)\nrun(20)\n")
 # cases whose restart files the reference itself can continue from: every updated-Lagrangian case without a rigid material and without CPDI
-# particle domains (the layout holds neither; total-Lagrangian runs stop in TLMPM because Domain::np_local is not restored)
-READABLE = [n for n, c in CASES.items() if not c[1] and "rigid" not in c[0] and "cpdi" not in c[0] and "velocity_particles" not in n]
+# particle domains (the layout holds neither; total-Lagrangian runs stop in TLMPM because Domain::np_local is not restored); the reference's
+# fix temperature_nodes cannot be re-created from a restart file either (it looks its group up by the name "restart",
+# src/fix_temperature_nodes.cpp:38)
+READABLE = [n for n, c in CASES.items() if not c[1] and "rigid" not in c[0] and "cpdi" not in c[0] and "velocity_particles" not in n
+            and "temperature_nodes" not in c[0]]
 
 
 @pytest.mark.parametrize("name", READABLE)
