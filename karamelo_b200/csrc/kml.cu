@@ -2,7 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a (see karamelo_b200/Makefile).
 #define KML_MISC_KERNELS
 #include "kml_launch.h"
-#include "kml_gather_cell2.cuh"
+#include "kml_gather_cell3.cuh"
 #include "kml_comm.cuh"
 #include "kml_cpdi.cuh"
 #include "kml_setup.cuh"
@@ -26,6 +26,9 @@ struct Grid {
   bool v_is_momentum = false, T_is_weighted = false;
   // cell lists for the cell-centric P2G (UL)
   CellLists cl;
+  // packed gather records {v_update, v_update - v} on a zero-padded grid for the TMA-fed G2P kernel (kml_gather_cell3.cuh); valid = they
+  // reflect the current nv / nvu (written by k_grid_update, invalidated by everything else that touches node velocities)
+  double *nvd = nullptr; bool nvd_valid = false;
 };
 struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
@@ -55,6 +58,7 @@ struct kml_ctx {
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   double permute_frac = 0.05; int permute_min_steps = 8; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
+  int g2p_tma = 0; int nsm = 148; // KML_G2P_TMA: persistent TMA-fed G2P kernel
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
@@ -184,6 +188,8 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
   c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 8);
+  c->g2p_tma = env_int("KML_G2P_TMA", 0);
+  { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, c->dev) == cudaSuccess) c->nsm = pr.multiProcessorCount; }
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
   auto seg_env = [&](const char *name, int dflt) { return std::min(std::max(env_int(name, env_int("KML_SEGLEN", dflt)), 8), 96); };
@@ -191,13 +197,14 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   c->gtune.seg_g2p = seg_env("KML_SEGLEN_G2P", 32);
   c->gtune.seg_stress = seg_env("KML_SEGLEN_STRESS", 24);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;
+  c->gtune.g2p_threads = env_int("KML_G2P_THREADS", c->gtune.threads) == 128 ? 128 : 64;
   *out = c; return 0;
 }
 
 int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
-  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); g->cl.release(); delete g; }
+  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); g->cl.release(); delete g; }
   for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
@@ -252,8 +259,8 @@ int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.n
 
 static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
   if (!G->v_is_momentum && !G->T_is_weighted) return 0;
-  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0);
-  G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr);
+  G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = false; c->launches[KML_STAGE_GRID]++;
   return check_launch("k_grid_update(normalize)");
 }
 
@@ -285,6 +292,7 @@ int kml_grid_upload(kml_ctx *c, int gid, int field, const void *src) {
   if (ic) { CU(cudaMemcpyAsync(ic, src, sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_N_V) G->v_is_momentum = false;
   if (field == KML_N_T) G->T_is_weighted = false;
+  G->nvd_valid = false;
   const double *s = (const double *)src;
   for (int k = 0; k < nc; k++) { // strided 2-D copy: host column k of [nn][nc] -> device component
     CU(cudaMemcpy2DAsync(comp[k], sizeof(double) * stride, s + k, sizeof(double) * nc, sizeof(double), nn, cudaMemcpyHostToDevice, c->stream));
@@ -747,10 +755,10 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
         // without a synchronisation; the first re-bin waits for its own)
         if (c->permute_frac >= 0 && G->cl.valid) {
           if (c->steps_started == 1) { CU(cudaStreamSynchronize(c->stream)); }
-          const long long far = *G->cl.h_disorder;
+          const long long far = G->cl.far_count();
           if (far > c->permute_frac * (double)S->s.np && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
             if (permute_solid(c, S, G)) return 1;
-            S->last_permute_step = c->steps_started; *G->cl.h_disorder = 0;
+            S->last_permute_step = c->steps_started; G->cl.far_reset();
           }
         }
         if (c->solids.size() > 1) break; // cell lists are per grid; several solids on one grid use the atomic path
@@ -853,6 +861,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (check_launch("k_p2g")) return 1;
     if (what & P2G_MOM) G->v_is_momentum = true;
     if (what & P2G_TEMP) G->T_is_weighted = true;
+    G->nvd_valid = false;
   }
   if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
   t.stop();
@@ -878,8 +887,13 @@ int kml_update_grid_state(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   StageTimer t(c, KML_STAGE_GRID);
   for (Grid *G : active_grids(c)) {
-    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid);
-    G->v_is_momentum = false; G->T_is_weighted = false; c->launches[KML_STAGE_GRID]++;
+    double *nvd = nullptr;
+    if (c->g2p_tma && !c->c.is_TL && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+      if (!G->nvd) { const size_t nb = sizeof(double) * nvd_doubles(G->g); CU(cudaMalloc(&G->nvd, nb)); CU(cudaMemsetAsync(G->nvd, 0, nb, c->stream)); }
+      nvd = G->nvd;
+    }
+    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid, nvd);
+    G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = nvd != nullptr; c->launches[KML_STAGE_GRID]++;
     if (check_launch("k_grid_update")) return 1;
   }
   return 0;
@@ -900,8 +914,14 @@ int kml_advance_particles(kml_ctx *c) {
     fill_inertia(c, G, S, sp);
     sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
     if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && !c->keep_acc && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
-      StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
-      if (rc > 0) return fail("cell g2p launch failed");
+      if (c->g2p_tma && G->nvd && !sp.axisymmetric && !sp.temp) {
+        if (!G->nvd_valid) { k_grid_pack_g2p<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, G->nvd); G->nvd_valid = true; c->launches[KML_STAGE_G2P]++; }
+        rc = cell_g2p_tma_launch(S->s, G->g, sp, G->nvd, G->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads, c->gtune.g2p_threads == 64 ? 8 : (c->g2p_tma == 3 ? 3 : 4), c->nsm);
+        if (rc > 0) return fail(std::string("cell g2p (TMA) launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      } else {
+        StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
+        if (rc > 0) return fail("cell g2p launch failed");
+      }
     }
     if (c->c.is_CPDI) {
       if (c->c.is_TL) k_cpdi_g2p<true><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp);
@@ -1085,6 +1105,7 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
   if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
   for (Grid *G : gs) {
     if (grid_normalize_if_needed(c, G)) return 1;
+    G->nvd_valid = false;
     k_fix_velocity_nodes<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, v[0], v[1], v[2], vprev ? vprev[0] : 0, vprev ? vprev[1] : 0,
                                                                         vprev ? vprev[2] : 0, which, 1.0 / c->dt, c->d_scratch);
     c->launches[KML_STAGE_GRID]++;

@@ -35,6 +35,7 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
   // first particle of this thread: index and position are in flight while the tile is staged
   int p = pbeg + threadIdx.x;
   int ip = p < pend ? order[p] : -1;
+  int ipn = p + THREADS < pend ? order[p + THREADS] : -1; // order[] runs two particles ahead, positions one (no address stall in the loop)
   double px = 0, py = 0, pz = 0;
   if (ip >= 0) { px = s.x[0][ip]; py = s.x[1][ip]; pz = s.x[2][ip]; }
 
@@ -59,7 +60,7 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
   while (ip >= 0) {
     // next particle of this thread
     const int pn = p + THREADS;
-    const int ipn = pn < pend ? order[pn] : -1;
+    const int ipnn = pn + THREADS < pend ? order[pn + THREADS] : -1;
     double nx = 0, ny = 0, nz = 0;
     if (ipn >= 0) { nx = s.x[0][ipn]; ny = s.x[1][ipn]; nz = s.x[2][ipn]; }
     double vold[3]; // in flight during the gather
@@ -87,7 +88,7 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
         }
       }
     particle_advance<false, false>(s, sp, ip, vu, acc, 0.0, vold); // kept accelerations (kml_keep_particle_acceleration) go through k_g2p
-    p = pn; ip = ipn; px = nx; py = ny; pz = nz;
+    p = pn; ip = ipn; ipn = ipnn; px = nx; py = ny; pz = nz;
   }
 }
 
@@ -191,7 +192,7 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
 }
 
 // measurement knobs (environment, see kml.cu): cells per segment and threads per block
-struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads = 64; }; // seg_target: P2G / re-projection
+struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads = 64, g2p_threads = 64; }; // seg_target: P2G / re-projection
 
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
 inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
@@ -217,7 +218,7 @@ inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, 
     if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
     else KML_GATHER_LAUNCH((k_stress_cell<128, 3>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
   } else {
-    if (tune.threads == 64) KML_GATHER_LAUNCH((k_g2p_cell<64, 8>), 64, s, g, sp, cl.start, cl.order, seglen, nseg);
+    if (tune.g2p_threads == 64) KML_GATHER_LAUNCH((k_g2p_cell<64, 8>), 64, s, g, sp, cl.start, cl.order, seglen, nseg);
     else KML_GATHER_LAUNCH((k_g2p_cell<128, 4>), 128, s, g, sp, cl.start, cl.order, seglen, nseg);
   }
 #undef KML_GATHER_LAUNCH

@@ -181,11 +181,13 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
   })
 }
 
+#define KML_NVD_PADK 102 /* kml_gather_cell3.cuh NVD_PADK */
 #ifdef KML_MISC_KERNELS  // non-template kernels: compiled once, in kml.cu
 // ---- grid kernels ----------------------------------------------------------------------------
 // normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
 // Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
-__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware) {
+// nvd (optional): packed gather records {v_update, v_update - v} on the zero-padded grid of kml_gather_cell3.cuh, written in the same pass
+__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware, double *nvd) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
   double4 rec = g.nv[i];
@@ -207,6 +209,11 @@ __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, i
     u.z = (m != 0 && free_node) ? v[2] + dt * (g.f[2][i] + g.mb[2][i]) / m : v[2];
     u.w = temp ? ((m != 0) ? T + dt * (g.Qint[i] + g.Qext[i]) / m : T) : 0.0;
     g.nvu[i] = u;
+    if (nvd) {
+      const int k = (int)(i % g.n[2]); const long long t = i / g.n[2]; const int j = (int)(t % g.n[1]), ii = (int)(t / g.n[1]);
+      double *d = nvd + (((long long)ii * (g.n[1] + 3) + j) * (g.n[2] + KML_NVD_PADK) + k) * 6;
+      *(double2 *)d = make_double2(u.x, u.y); *(double2 *)(d + 2) = make_double2(u.z, u.x - v[0]); *(double2 *)(d + 4) = make_double2(u.y - v[1], u.z - v[2]);
+    }
   }
 }
 
