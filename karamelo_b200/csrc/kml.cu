@@ -18,9 +18,12 @@ using namespace kml;
 
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }
+enum { KML_RED_BITS = 64 }; // d_red: [2 i] max wave speed, [2 i + 1] min_h_ratio of solid i; [KML_RED_BITS + b] bit b of the error word
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 #define CUV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); } } while (0)
 
+struct kml_ctx;
+extern "C" { static int resolve_dt(kml_ctx *c); }
 struct Grid {
   kml_grid_desc d; GridDev g; double *buf = nullptr; int *ibuf = nullptr;
   bool v_is_momentum = false, T_is_weighted = false;
@@ -56,6 +59,7 @@ struct kml_ctx {
   bool has_rigid = false; // some solid is rigid (ULMPM::rigid_solids, src/ulmpm.cpp:98-99)
   bool apic = false; // affine transfer: TL: APIC; UL: APIC, MLS, AFLIP, ASFLIP (src/ulmpm.cpp:79-85, src/tlmpm.cpp:83-85)
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
+  double *d_red = nullptr, *h_red = nullptr; cudaEvent_t ev_dt = nullptr; bool dt_pending = false; double dt_factor = 1.0; // deferred adjust_dt (resolve_dt)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   double permute_frac = 0.05; int permute_min_steps = 8; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   int g2p_tma = 0; int nsm = 148; // KML_G2P_TMA: persistent TMA-fed G2P kernel
@@ -179,6 +183,8 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
   CU(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
   CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
+  CU(cudaMalloc(&c->d_red, (KML_RED_BITS + 8) * sizeof(double))); CU(cudaMemset(c->d_red, 0, (KML_RED_BITS + 8) * sizeof(double)));
+  CU(cudaMallocHost(&c->h_red, (KML_RED_BITS + 8) * sizeof(double))); CU(cudaEventCreateWithFlags(&c->ev_dt, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
   memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
   const char *e = getenv("KML_P2G");
@@ -205,13 +211,13 @@ int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
   for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); g->cl.release(); delete g; }
-  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->red); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); delete s; }
+  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
     cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
   }
-  cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage);
+  cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage); cudaFree(c->d_red); cudaFreeHost(c->h_red); if (c->ev_dt) cudaEventDestroy(c->ev_dt);
   for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaStreamDestroy(c->stream);
@@ -259,7 +265,7 @@ int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.n
 
 static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
   if (!G->v_is_momentum && !G->T_is_weighted) return 0;
-  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr);
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, 0.0 /* dt is not used without the update */, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr);
   G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = false; c->launches[KML_STAGE_GRID]++;
   return check_launch("k_grid_update(normalize)");
 }
@@ -354,12 +360,14 @@ static void bind_pointers(kml_ctx *c, Solid *S) {
 // buffer, which then becomes current.  The cell-sorted kernels read 31-55 SoA streams per particle through order[]; while order[] is close to
 // the identity those streams coalesce, but mixing (and, on a decomposed run, migration: arrivals are appended, holes are filled from the tail)
 // turns them into sector-granular gathers.  xn (scratch between grid_to_points and the next weight evaluation) is not copied.
-__global__ void k_permute(const double *__restrict__ src, double *__restrict__ dst, long long cap, int nd, const int *__restrict__ order, long long np,
+// xslot: the buffer slot (0 or 3) that holds the CURRENT positions - x and xn trade places after every step (kml_compute_grid_weight_...);
+// they land in slot 0 of the destination, whose pointers are bound in the canonical order
+__global__ void k_permute(const double *__restrict__ src, double *__restrict__ dst, long long cap, int nd, int xslot, const int *__restrict__ order, long long np,
                           const long long *__restrict__ tsrc, long long *__restrict__ tdst, const int *__restrict__ msrc, int *__restrict__ mdst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= np) return;
   const long long j = order[i];
-  for (int a = 0; a < nd; a++) { if (a >= 3 && a < 6) continue; dst[a * cap + i] = src[a * cap + j]; }
+  for (int a = 0; a < nd; a++) { if (a >= 3 && a < 6) continue; const int sa = a < 3 ? xslot + a : a; dst[a * cap + i] = src[sa * cap + j]; }
   tdst[i] = tsrc[j]; mdst[i] = msrc[j];
 }
 __global__ void k_iota(int *a, long long n) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = (int)i; }
@@ -375,7 +383,9 @@ static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
     CU(cudaMemsetAsync(S->buf2, 0, bytes, c->stream));
   }
   const long long np = S->s.np;
-  k_permute<<<nblocks(np, 128), 128, 0, c->stream>>>(S->buf, S->buf2, S->cap, S->nd, G->cl.order, np, S->lbuf, S->lbuf2, S->ibuf, S->ibuf2);
+  const int xslot = (int)((S->s.x[0] - S->buf) / S->cap); // 0, or 3 after an odd number of x <-> xn swaps
+  if (xslot != 0 && xslot != 3) return fail("permute_solid: unexpected position slot");
+  k_permute<<<nblocks(np, 128), 128, 0, c->stream>>>(S->buf, S->buf2, S->cap, S->nd, xslot, G->cl.order, np, S->lbuf, S->lbuf2, S->ibuf, S->ibuf2);
   k_iota<<<nblocks(np, 256), 256, 0, c->stream>>>(G->cl.order, np);
   if (check_launch("k_permute")) return 1;
   std::swap(S->buf, S->buf2); std::swap(S->lbuf, S->lbuf2); std::swap(S->ibuf, S->ibuf2);
@@ -401,7 +411,8 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaMalloc(&S->buf, sizeof(double) * cap * nd)); CU(cudaMemsetAsync(S->buf, 0, sizeof(double) * cap * nd, c->stream));
   CU(cudaMalloc(&S->lbuf, sizeof(long long) * cap)); CU(cudaMemsetAsync(S->lbuf, 0, sizeof(long long) * cap, c->stream));
   CU(cudaMalloc(&S->ibuf, sizeof(int) * cap));
-  CU(cudaMalloc(&S->red, sizeof(double) * 2));
+  if (2 * (c->solids.size() + 1) > (size_t)KML_RED_BITS) return fail("too many solids");
+  S->red = c->d_red + 2 * c->solids.size(); // slots of the context's reduction buffer (one all-reduce for all solids)
   S->nd = nd; bind_pointers(c, S);
   // initial values of Solid::populate, src/solid.cpp:2283-2321: F = R = I, rho0 = mat.rho0, mask = 1
   if (d->np > 0) { k_solid_init<<<nblocks(d->np, 256), 256, 0, c->stream>>>(s, d->mat.rho0); if (check_launch("k_solid_init")) return 1; }
@@ -699,8 +710,8 @@ int kml_fix_set_particles_expr(kml_ctx *c, int solid, int groupbit, int field, i
   return rc;
 }
 
-int kml_set_dt(kml_ctx *c, double dt) { c->dt = dt; return 0; }
-int kml_get_dt(kml_ctx *c, double *dt) { *dt = c->dt; return 0; }
+int kml_set_dt(kml_ctx *c, double dt) { if (resolve_dt(c)) return 1; c->dt = dt; return 0; }
+int kml_get_dt(kml_ctx *c, double *dt) { if (resolve_dt(c)) return 1; *dt = c->dt; return 0; }
 
 // ---- stages -----------------------------------------------------------------------------------
 int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
@@ -885,6 +896,7 @@ int kml_particles_to_grid_USF_2(kml_ctx *c) {
 
 int kml_update_grid_state(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   StageTimer t(c, KML_STAGE_GRID);
   for (Grid *G : active_grids(c)) {
     double *nvd = nullptr;
@@ -903,6 +915,7 @@ int kml_grid_to_points(kml_ctx *c) { c->pending_g2p = true; return 0; }
 
 int kml_advance_particles(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   if (!c->pending_g2p) return fail("advance_particles called without grid_to_points");
   c->pending_g2p = false;
   StageTimer t(c, KML_STAGE_G2P);
@@ -948,6 +961,7 @@ int kml_velocities_to_grid(kml_ctx *c) {
 int kml_update_grid_positions(kml_ctx *c) {
   if (!c->c.is_TL) return 0;
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   StageTimer t(c, KML_STAGE_GRID);
   for (Grid *G : active_grids(c)) {
     if (grid_normalize_if_needed(c, G)) return 1;
@@ -969,6 +983,7 @@ int kml_update_deformation_gradient(kml_ctx *c) {
 
 int kml_update_stress(kml_ctx *c, int doublemapping) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   if (!c->pending_F || c->pending_grad < 0) return fail("update_stress called without compute_rate_deformation_gradient + update_deformation_gradient");
   StageTimer t(c, KML_STAGE_STRESS);
   StepParams sp = step_params(c);
@@ -996,30 +1011,50 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
   return 0;
 }
 
-int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
-  CU(cudaSetDevice(c->dev));
-  StageTimer t(c, KML_STAGE_DT);
+// bit b of the device error word -> slot b of a double array (1.0 / 0.0): a max all-reduce of the slots is the union of the words
+__global__ void k_flag_bits(const unsigned *flags, double *bits) { if (threadIdx.x < 8) bits[threadIdx.x] = ((*flags >> threadIdx.x) & 1u) ? 1.0 : 0.0; }
+__global__ void k_bits_flag(const double *bits, unsigned *flags) { unsigned f = 0; for (int b = 0; b < 8; b++) if (bits[b] != 0.0) f |= 1u << b; *flags = f; }
+
+// The dt of the next step is needed first by the grid update of the next step, a re-bin and a scatter later.  adjust_dt therefore only
+// ENQUEUES the reduction and the read-back; the value is resolved (one event wait, normally long satisfied) when something asks for it:
+// a kernel that takes dt, kml_get_dt, or a caller that passes dt_out.  The device error word travels with it.
+static int resolve_dt(kml_ctx *c) {
+  if (!c->dt_pending) return 0;
+  c->dt_pending = false;
+  CU(cudaEventSynchronize(c->ev_dt));
   const int ns = (int)c->solids.size();
-  if (ns * 2 + 1 > 64) return fail("too many solids");
-  if (c->comm.nranks > 1) { // MPI_Allreduce(MIN) of dtCFL in the reference (src/ulmpm.cpp:547) == max of the wave speed here
-    for (int i = 0; i < ns; i++) NC(nccl().AllReduce(c->solids[i]->red, c->solids[i]->red, 1, ncclDouble, ncclMax, c->comm.comm, c->stream));
-    NC(nccl().AllReduce(c->d_flags, c->d_flags, 1, ncclUint32, ncclMax, c->comm.comm, c->stream));
-  }
-  for (int i = 0; i < ns; i++) CU(cudaMemcpyAsync(c->h_pinned + 2 * i, c->solids[i]->red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_pinned + 2 * ns, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  unsigned flags; memcpy(&flags, c->h_pinned + 2 * ns, sizeof flags);
+  unsigned flags = 0; for (int b = 0; b < 8; b++) if (c->h_red[KML_RED_BITS + b] != 0.0) flags |= 1u << b;
   if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
     Solid *S = c->solids[i]; Grid *G = c->grids[S->d.grid];
-    const double wave = c->h_pinned[2 * i], hr = c->c.is_TL ? c->h_pinned[2 * i + 1] : 1.0;
-    S->dtCFL = std::min(S->dtCFL, G->d.cellsize * hr / wave);
+    const double wave = c->h_red[2 * i], hr = c->c.is_TL ? c->h_red[2 * i + 1] : 1.0;
+    S->dtCFL = std::min(1.0e22, G->d.cellsize * hr / wave);
     dtCFL = std::min(dtCFL, S->dtCFL);
   }
   if (dtCFL == 0 || std::isnan(dtCFL)) return fail("dtCFL == 0 or NaN");
-  c->dt = dtCFL * dt_factor;
-  if (dt_out) *dt_out = c->dt;
+  c->dt = dtCFL * c->dt_factor;
+  return 0;
+}
+
+int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
+  CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1; // an adjust_dt nobody consumed (two calls in a row)
+  {
+    StageTimer t(c, KML_STAGE_DT);
+    const int ns = (int)c->solids.size();
+    if (2 * ns > KML_RED_BITS) return fail("too many solids");
+    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, c->d_red + KML_RED_BITS);
+    if (c->comm.nranks > 1) { // MPI_Allreduce(MIN) of dtCFL in the reference (src/ulmpm.cpp:547) == max of the wave speeds here; ONE collective for all solids + the error word
+      NC(nccl().AllReduce(c->d_red, c->d_red, KML_RED_BITS + 8, ncclDouble, ncclMax, c->comm.comm, c->stream));
+      k_bits_flag<<<1, 1, 0, c->stream>>>(c->d_red + KML_RED_BITS, c->d_flags);
+    }
+    CU(cudaMemcpyAsync(c->h_red, c->d_red, (KML_RED_BITS + 8) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev_dt, c->stream));
+    c->launches[KML_STAGE_DT] += 1;
+  }
+  c->dt_pending = true; c->dt_factor = dt_factor;
+  if (dt_out) { if (resolve_dt(c)) return 1; *dt_out = c->dt; }
   return 0;
 }
 
@@ -1033,6 +1068,7 @@ int kml_exchange_particles(kml_ctx *c) {
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid]; SolidDev &s = S->s;
     if (S->moved) { for (int k = 0; k < 3; k++) std::swap(s.x[k], s.xn[k]); S->moved = false; }
+    const int xs = (int)((s.x[0] - S->buf) / S->cap); // buffer slot of the current positions (0 or 3), see k_mig_pack
     const int narr = SOLID_NDBL_UL + (s.Lst[0] ? 9 : 0); // the stored velocity gradient of the APIC family / gradient-enhanced projection follows the UL block
     const int cap_mig = (int)std::min<long long>(std::max<long long>(s.np / 8, 1024), 1 << 24);
     if (cap_mig > cm.mig_cap) {
@@ -1061,8 +1097,8 @@ int kml_exchange_particles(kml_ctx *c) {
     if (np_new + rL + rR > S->cap) return fail("particle capacity exceeded by migration");
     double *sendL = cm.mig_send, *sendR = cm.mig_send + (size_t)(narr + 2) * cm.mig_cap;
     double *recvL = cm.mig_recv, *recvR = cm.mig_recv + (size_t)(narr + 2) * cm.mig_cap;
-    if (nL) k_mig_pack<<<nblocks(nL, 128), 128, 0, c->stream>>>(sendL, cm.mig_list, nL, S->buf, S->cap, narr, s.ptag, s.mask);
-    if (nR) k_mig_pack<<<nblocks(nR, 128), 128, 0, c->stream>>>(sendR, cm.mig_list + cm.mig_cap, nR, S->buf, S->cap, narr, s.ptag, s.mask);
+    if (nL) k_mig_pack<<<nblocks(nL, 128), 128, 0, c->stream>>>(sendL, cm.mig_list, nL, S->buf, S->cap, narr, xs, s.ptag, s.mask);
+    if (nR) k_mig_pack<<<nblocks(nR, 128), 128, 0, c->stream>>>(sendR, cm.mig_list + cm.mig_cap, nR, S->buf, S->cap, narr, xs, s.ptag, s.mask);
     NC(nccl().GroupStart());
     if (left) { if (nL) NC(nccl().Send(sendL, (size_t)(narr + 2) * nL, ncclDouble, cm.rank - 1, cm.comm, c->stream)); if (rL) NC(nccl().Recv(recvL, (size_t)(narr + 2) * rL, ncclDouble, cm.rank - 1, cm.comm, c->stream)); }
     if (right) { if (nR) NC(nccl().Send(sendR, (size_t)(narr + 2) * nR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); if (rR) NC(nccl().Recv(recvR, (size_t)(narr + 2) * rR, ncclDouble, cm.rank + 1, cm.comm, c->stream)); }
@@ -1079,8 +1115,8 @@ int kml_exchange_particles(kml_ctx *c) {
       if (cm.h_cnt[4] != cm.h_cnt[5]) return fail("migration: hole / filler count mismatch");
       if (cm.h_cnt[4]) k_mig_move<<<nblocks(cm.h_cnt[4], 128), 128, 0, c->stream>>>(holes, fillers, cm.h_cnt[4], S->buf, S->cap, narr, s.ptag, s.mask);
     }
-    if (rL) k_mig_unpack<<<nblocks(rL, 128), 128, 0, c->stream>>>(recvL, rL, np_new, S->buf, S->cap, narr, s.ptag, s.mask);
-    if (rR) k_mig_unpack<<<nblocks(rR, 128), 128, 0, c->stream>>>(recvR, rR, np_new + rL, S->buf, S->cap, narr, s.ptag, s.mask);
+    if (rL) k_mig_unpack<<<nblocks(rL, 128), 128, 0, c->stream>>>(recvL, rL, np_new, S->buf, S->cap, narr, xs, s.ptag, s.mask);
+    if (rR) k_mig_unpack<<<nblocks(rR, 128), 128, 0, c->stream>>>(recvR, rR, np_new + rL, S->buf, S->cap, narr, xs, s.ptag, s.mask);
     s.np = np_new + rL + rR; S->gen++;
     c->launches[KML_STAGE_MIGRATE] += 6;
     if (check_launch("migration")) return 1;
@@ -1099,6 +1135,7 @@ static int read_scratch3(kml_ctx *c, double out[3]) {
 
 int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which, double ftot[3]) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   StageTimer t(c, KML_STAGE_GRID);
   if (which == 0) CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
   std::vector<Grid *> gs;
@@ -1117,6 +1154,7 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
 
 int kml_fix_velocity_particles(kml_ctx *c, int solid, int groupbit, int set_mask, const double v[3], const double vprev[3], int which, double ftot[3]) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   StageTimer t(c, KML_STAGE_OTHER);
   if (c->c.is_CPDI) return fail("kml: fix velocity_particles on the device is not implemented for CPDI (particle domains are not moved)");
   if (which == 1) CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
@@ -1194,6 +1232,7 @@ int kml_fix_force_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const
 
 static int contact(kml_ctx *c, int s1, int s2, int hertz, double mu, double ftot[3]) {
   CU(cudaSetDevice(c->dev));
+  if (resolve_dt(c)) return 1;
   StageTimer t(c, KML_STAGE_CONTACT);
   Solid *A = c->solids[s1], *B = c->solids[s2];
   if (c->c.dimension == 1) return 0;
@@ -1233,9 +1272,14 @@ static int energy(kml_ctx *c, int solid, int groupbit, int kinetic, double *out)
 int kml_compute_kinetic_energy(kml_ctx *c, int solid, int groupbit, double *ek) { return energy(c, solid, groupbit, 1, ek); }
 int kml_compute_strain_energy(kml_ctx *c, int solid, int groupbit, double *es) { return energy(c, solid, groupbit, 0, es); }
 
-int kml_error_flags(kml_ctx *c, unsigned *flags) { // collective on a decomposed run: every rank sees every rank's bits
+int kml_error_flags(kml_ctx *c, unsigned *flags) { // collective on a decomposed run: every rank sees the UNION of every rank's bits
   CU(cudaSetDevice(c->dev));
-  if (c->comm.nranks > 1) NC(nccl().AllReduce(c->d_flags, c->d_flags, 1, ncclUint32, ncclMax, c->comm.comm, c->stream));
+  if (c->comm.nranks > 1) {
+    double *bits = c->d_scratch + 40;
+    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, bits);
+    NC(nccl().AllReduce(bits, bits, 8, ncclDouble, ncclMax, c->comm.comm, c->stream));
+    k_bits_flag<<<1, 1, 0, c->stream>>>(bits, c->d_flags);
+  }
   CU(cudaMemcpyAsync(c->h_pinned + 48, c->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   memcpy(flags, c->h_pinned + 48, sizeof(unsigned)); return 0;

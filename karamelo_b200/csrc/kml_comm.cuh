@@ -72,20 +72,23 @@ __global__ void k_mig_mark(const double *x0, long long np, double lo, double ih,
   else if (b >= base_hi && rank < nranks - 1) side = 1;
   if (side >= 0) { const int slot = atomicAdd(&cnt[side], 1); if (slot < cap) list[side * cap + slot] = (int)ip; }
 }
-// rows = [narr + 2][n]: the double arrays, then ptag (bit pattern) and mask
-__global__ void k_mig_pack(double *rows, const int *list, int n, double *const base, long long cap, int narr, const long long *ptag, const int *mask) {
+// rows = [narr + 2][n]: the double arrays, then ptag (bit pattern) and mask.  The wire order is canonical (current positions x first, then
+// the scratch xn): the positions trade buffer slots after every step and a rank that re-ordered its particles physically starts over at
+// slot 0, so sender and receiver need not agree on where x lives (xs = buffer slot of x: 0 or 3).
+__device__ __forceinline__ int mig_slot(int a, int xs) { return a < 3 ? xs + a : (a < 6 ? (3 - xs) + (a - 3) : a); }
+__global__ void k_mig_pack(double *rows, const int *list, int n, double *const base, long long cap, int narr, int xs, const long long *ptag, const int *mask) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int ip = list[j];
-  for (int a = 0; a < narr; a++) rows[(long long)a * n + j] = base[a * cap + ip];
+  for (int a = 0; a < narr; a++) rows[(long long)a * n + j] = base[mig_slot(a, xs) * cap + ip];
   rows[(long long)narr * n + j] = __longlong_as_double(ptag[ip]);
   rows[(long long)(narr + 1) * n + j] = (double)mask[ip];
 }
-__global__ void k_mig_unpack(const double *rows, int n, long long at, double *base, long long cap, int narr, long long *ptag, int *mask) {
+__global__ void k_mig_unpack(const double *rows, int n, long long at, double *base, long long cap, int narr, int xs, long long *ptag, int *mask) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const long long ip = at + j;
-  for (int a = 0; a < narr; a++) base[a * cap + ip] = rows[(long long)a * n + j];
+  for (int a = 0; a < narr; a++) base[mig_slot(a, xs) * cap + ip] = rows[(long long)a * n + j];
   ptag[ip] = __double_as_longlong(rows[(long long)narr * n + j]);
   mask[ip] = (int)rows[(long long)(narr + 1) * n + j];
 }

@@ -31,6 +31,7 @@ void rput_sets(std::ostream &os, const bool *set, const Var *val, const Var *pre
 // does (vars x,y,z,x0,y0,z0 set per particle, expression re-parsed), once, at step 1.
 struct FixInitialVelocityParticles : Fix {
   bool set[3] = {false, false, false}; Var val[3];
+  bool needs_time(const Sim &s) const override { return s.ntimestep < 1; } // acts in step 1 only
   void initial_integrate(Sim &s) override {
     if (s.ntimestep != 1) return;
     const int solid = s.gsolid[igroup];
@@ -899,8 +900,18 @@ void Sim::run(Var condition) {
       check(kml_update_grid_positions(ctx));
     }
     check(kml_exchange_particles(ctx));
+    if (dt_stale) { check(kml_get_dt(ctx, &dt)); input.vars["dt"] = Var("dt", dt); dt_stale = false; } // resolved long ago by this step's grid update: no stall
     atime += (ntimestep - atimestep) * dt; atimestep = ntimestep; input.vars["time"] = Var("time", atime); // Update::update_time
-    if (!dt_constant) { check(kml_adjust_dt(ctx, dt_factor, &dt)); input.vars["dt"] = Var("dt", dt); }       // Method::adjust_dt
+    if (!dt_constant) { // Method::adjust_dt
+      // The engine only enqueues the reduction; the value is read back when somebody needs it (kml_get_dt below, or the engine's own grid
+      // update of the next step).  Nothing on the host needs it before the next step's stages unless a fix or the output evaluates
+      // expressions at the start of the step - then it is fetched here like the reference does.
+      const bool due_next = ntimestep == next_log || ntimestep == nsteps || (restart_every && next_restart == ntimestep);
+      bool need_now = due_next || !dumps.empty() || maxtime != -1;
+      for (auto &f : fixes) if (f->needs_time(*this)) need_now = true;
+      check(kml_adjust_dt(ctx, dt_factor, need_now ? &dt : nullptr));
+      if (need_now) input.vars["dt"] = Var("dt", dt); else dt_stale = true;
+    }
     else { // set_dt: adjust_dt (which returns the device error word) is skipped, so ask for it - the reference stops inside the failing step
       unsigned fl = 0; check(kml_error_flags(ctx, &fl));
       if (fl) fatal("device error flags set: " + std::to_string(fl) + " (bit0 particle left the domain, bit1 J<=0, bit2 dtCFL invalid, bit3 polar decomposition failed)\n");
@@ -911,6 +922,7 @@ void Sim::run(Var condition) {
     for (auto &d : dumps) due = due || d.next == ntimestep;
     if (due) output_write(ntimestep);
   }
+  if (dt_stale) { check(kml_get_dt(ctx, &dt)); input.vars["dt"] = Var("dt", dt); dt_stale = false; }
   unsigned flags = 0; check(kml_error_flags(ctx, &flags));
   if (flags) fatal("device error flags set: " + std::to_string(flags) + " (bit0 particle left the domain, bit1 J<=0, bit2 dtCFL invalid, bit3 polar decomposition failed)\n");
 }

@@ -84,6 +84,9 @@ struct Fix {
   virtual void post_velocities_to_grid(Sim &) {}
   virtual void final_integrate(Sim &) {}
   virtual void write_restart(std::ostream &) const {} // Fix::write_restart of the style (src/fix_velocity_nodes.cpp:270-292, ...)
+  // does one of this fix's hooks evaluate script expressions (time, dt, ...) during the NEXT step?  The one-shot fixes answer no after step 1,
+  // which lets the scheme leave the new dt on the device until the engine itself needs it (Sim::run).
+  virtual bool needs_time(const Sim &) const { return true; }
 };
 struct Compute {
   std::string id, style;
@@ -102,6 +105,7 @@ public:
 
   // ---- Update (src/update.h) ----
   double dt = 1e-16, dt_factor = 0.9; bool dt_constant = false;       // src/update.cpp:38-40
+  bool dt_stale = false; // the engine holds a newer dt than `dt` (deferred adjust_dt, see Sim::run)
   int64_t ntimestep = 0, atimestep = 0, firststep = 0, laststep = 0; double atime = 0, maxtime = -1; int64_t nsteps = 0;
   std::string method_type, scheme_style = "musl";                    // default scheme MUSL, src/update.cpp:42-45
   bool method_set = false, is_TL = false, is_CPDI = false, temp = false, ge = false; int cpdi_style = 0;

@@ -77,11 +77,21 @@ def step(args):
     assert torch.cuda.is_available()
     cells = tuple(args.cells)
     script = block(cells, args.scheme, args.shape, a=args.a, drift=args.drift)
+    if args.variant == "velocity_nodes":  # node boundary condition across every slab + its reaction force (an all-reduced total)
+        m = 4
+        script += ("region(rlow, block, INF, INF, INF, %g, INF, INF)\ngroup(gn, nodes, region, rlow, solid, blk)\n"
+                   "fix(bc, velocity_nodes, gn, NULL, 0, NULL)\n" % (m + 1.5))
+    elif args.variant == "thermal":  # thermo-mechanical: temperature and heat-source node fields join the halo sums
+        script = script.replace("method(ulmpm, FLIP, %s, 0.99)" % args.shape, "method(ulmpm, FLIP, %s, 0.99, thermo-mechanical)" % args.shape)
+        script = script.replace("material(m, eos-strength, e, s)", "temperature(tpw, plastic_work, 0.9, 50, 2, 0, 0, 500)\nmaterial(m, eos-strength, e, s, tpw)")
+        script = script.replace("solid(blk, region, box, 2, m, h, 0)", "solid(blk, region, box, 2, m, h, 10)")
+        script += "region(rhot, block, INF, %g, INF, INF, INF, INF)\ngroup(ghot, particles, region, rhot, solid, blk)\nfix(ft, temperature_particles, ghot, 10+20*time)\n" % (4 + cells[0] / 3)
+        assert "thermo-mechanical" in script and "tpw)" in script
     if args.method:  # e.g. "APIC, cubic-spline" or "FLIP, cubic-spline, 0.99, mechanical, gradient-enhanced"
         line = [ln for ln in script.splitlines() if ln.startswith("method(ulmpm")]
         assert len(line) == 1, line
         script = script.replace(line[0], "method(ulmpm, %s)" % args.method)
-    fields = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "VOL")
+    fields = ("PTAG", "X", "V", "SIGMA", "FDEF", "EFF_PLASTIC_STRAIN", "EFF_PLASTIC_STRAIN_RATE", "VOL") + (("T",) if args.variant == "thermal" else ())
     eng = slab.make_engine(None)
     eng.script(script)
     np0 = eng.solid_info(0)["np"]
@@ -121,6 +131,7 @@ if __name__ == "__main__":
     ap.add_argument("--drift", type=float, default=0.0)
     ap.add_argument("--method", default="", help="arguments of method(ulmpm, ...) replacing the block's FLIP cubic-spline default")
     ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
+    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal"])
     a = ap.parse_args()
     try:
         {"partition": partition, "step": step}[a.mode](a)
