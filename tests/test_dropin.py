@@ -1,0 +1,62 @@
+"""The drop-in, COMPILED into the reference (oracle/dropin/b200_ulmpm.cpp, oracle/Makefile targets ref_b200 / ref_b200_cpu): the
+reference's own `class ULMPM` (src/ulmpm.h, method style "ulmpm", src/update.cpp:119-124) re-implemented on top of the C ABI of
+include/kml.h and linked with every other UNMODIFIED reference object.  `method(ulmpm, ...)` of an unmodified script then runs the
+engine while input parsing, populate, groups, fixes, computes, dumps, log and restart files stay the reference's code.
+
+CPU: the binding over the CPU restatement of the ABI (liboracle_kml.so) writes byte-identical dump and restart files to the stock
+reference binary.  GPU: the binding over libkml.so (CUDA) reproduces the stock reference's restart state within 1e-10."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from cases import CASES
+from refio import REF_BIN, read_restart_solids
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B200_CPU = os.path.join(ROOT, "oracle", "_ref", "karamelo_ref_b200_cpu")
+B200_GPU = os.path.join(ROOT, "oracle", "_ref", "karamelo_ref_b200")
+NAMES = ["c1_two_disks_usl", "c1_two_disks_musl", "c2_taylor_cubic", "c2_taylor_linear", "c5_block_musl", "x_neo_hookean_usf", "x_fluid_column",
+         "x_apic_ul_cubic", "x_mls_ul_cubic", "x_two_spheres_3d", "x_fix_velocity_particles", "p_block_swift", "p_thermal_full_ul", "p_axisym_ul_cubic_musl"]
+TAIL = "\ndump(d1, all, particle, 25, dump_p.*.LAMMPS, x, y, z, vx, vy, vz, s11, s22, s12, ep, damage)\nrestart(50, r-*.restart)\nlog(10)\nrun(50)\n"
+
+
+def _run(exe, script, d):
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "in.mpm"), "w").write(script + TAIL)
+    p = subprocess.run([exe, "-i", "in.mpm"], cwd=d, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (exe, p.stdout[-600:], p.stderr[-300:])
+    return p.stdout
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_binding_over_the_cpu_abi_is_byte_identical(name, tmp_path):
+    if not (os.path.exists(REF_BIN) and os.path.exists(B200_CPU)):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference: make -C oracle ref ref_b200_cpu)")
+    script = CASES[name][0]
+    out_r, out_b = _run(REF_BIN, script, str(tmp_path / "ref")), _run(B200_CPU, script, str(tmp_path / "b200"))
+    for f in ("r-50.restart", "dump_p.25.LAMMPS", "dump_p.50.LAMMPS"):
+        a, b = open(tmp_path / "ref" / f, "rb").read(), open(tmp_path / "b200" / f, "rb").read()
+        assert a == b, "%s differs between the stock reference and the reference with the kml binding" % f
+    rows = lambda o: [ln for ln in o.splitlines() if ln[:1].isdigit()]
+    assert rows(out_r) == rows(out_b)  # the log table (step, dt, time)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_two_disks_musl", "c2_taylor_cubic", "c5_block_musl", "x_fluid_column", "p_thermal_full_ul"])
+def test_binding_over_cuda_matches_the_stock_reference(name, tmp_path):
+    if not (os.path.exists(REF_BIN) and os.path.exists(B200_GPU)):
+        pytest.skip("oracle/_ref binaries not built")
+    script, is_tl, thermal, _ = CASES[name]
+    out_r, out_b = _run(REF_BIN, script, str(tmp_path / "ref")), _run(B200_GPU, script, str(tmp_path / "b200"))
+    nps = [int(m) for m in re.findall(r"^np_local=(\d+)", out_r, flags=re.M)]
+    ref = read_restart_solids(str(tmp_path / "ref" / "r-50.restart"), nps, is_tl, thermal)
+    got = read_restart_solids(str(tmp_path / "b200" / "r-50.restart"), nps, is_tl, thermal)
+    for a, b in zip(got, ref):
+        assert (a["ptag"] == b["ptag"]).all()
+        for k in ("x", "v", "sigma", "F", "eps", "epsdot", "damage"):
+            scale = max(float(np.abs(b[k]).max()), 1e-300)
+            assert float(np.abs(a[k] - b[k]).max()) <= 1e-10 * scale, (name, k, float(np.abs(a[k] - b[k]).max()) / scale)
