@@ -334,6 +334,9 @@ enum { KML_STAGE_REBIN = 0, KML_STAGE_P2G, KML_STAGE_GRID, KML_STAGE_G2P, KML_ST
        KML_STAGE_DT /* adjust_dt: reduction + readback */, KML_STAGE_COUNT };
 int kml_profile(kml_ctx *ctx, int enable);
 int kml_stage_times(kml_ctx *ctx, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int reset);
+/* HOST wall-clock time (ms) spent inside the calls of each stage since the last reset (launch overhead, waits on events / NCCL): the
+ * difference between a step's wall time and the device stage sum is looked for here. */
+int kml_stage_host_times(kml_ctx *ctx, double ms[KML_STAGE_COUNT], int reset);
 /* CUDA-event bracket on the context's stream: start records an event, stop records a second one,
  * synchronises and returns the elapsed device time in milliseconds. */
 int kml_timer_start(kml_ctx *ctx);

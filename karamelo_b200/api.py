@@ -116,6 +116,7 @@ def load_host_library(path=None):
         "kml_synchronize": (i32, [vp]),
         "kml_profile": (i32, [vp, i32]),
         "kml_stage_times": (i32, [vp, PD, PL, i32]),
+        "kml_stage_host_times": (i32, [vp, PD, i32]),
         "kml_error_flags": (i32, [vp, C.POINTER(C.c_uint)]),
         "kml_get_dt": (i32, [vp, PD]),
         "kml_timer_start": (i32, [vp]),
@@ -272,6 +273,11 @@ class Engine:
         ln = (C.c_int64 * len(STAGES))()
         self._ckk(self.lib.kml_stage_times(self.ctx, ms, ln, 1 if reset else 0))
         return {s: (ms[i], ln[i]) for i, s in enumerate(STAGES)}
+
+    def stage_host_times(self, reset=True):
+        ms = (C.c_double * len(STAGES))()
+        self._ckk(self.lib.kml_stage_host_times(self.ctx, ms, 1 if reset else 0))
+        return {s: ms[i] for i, s in enumerate(STAGES)}
 
     def timer_start(self):
         self._ckk(self.lib.kml_timer_start(self.ctx))

@@ -8,6 +8,7 @@
 #include "kml_setup.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -68,7 +69,7 @@ struct kml_ctx {
   // profiling
   // Per-stage device time: event pairs are recorded around every stage and only READ in kml_stage_times (one synchronisation for the
   // whole timed region), so profiling does not serialise the host against the device and the stage sum stays inside the step time.
-  bool profile = false; cudaEvent_t evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT];
+  bool profile = false; cudaEvent_t evA = nullptr, evB = nullptr; double ms[KML_STAGE_COUNT]; long long launches[KML_STAGE_COUNT]; double host_ms[KML_STAGE_COUNT] = {0};
   struct Pair { int stage; cudaEvent_t a, b; };
   std::vector<Pair> ev_pending; std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t ev_get() { if (ev_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
@@ -76,9 +77,14 @@ struct kml_ctx {
 
 namespace {
 struct StageTimer {
-  kml_ctx *c; int stage; cudaEvent_t a = nullptr;
-  StageTimer(kml_ctx *c_, int st) : c(c_), stage(st) { if (c->profile) { a = c->ev_get(); cudaEventRecord(a, c->stream); } }
-  void stop() { if (a) { cudaEvent_t b = c->ev_get(); cudaEventRecord(b, c->stream); c->ev_pending.push_back({stage, a, b}); a = nullptr; } }
+  kml_ctx *c; int stage; cudaEvent_t a = nullptr; std::chrono::steady_clock::time_point h0;
+  StageTimer(kml_ctx *c_, int st) : c(c_), stage(st) { if (c->profile) { a = c->ev_get(); cudaEventRecord(a, c->stream); h0 = std::chrono::steady_clock::now(); } }
+  void stop() {
+    if (a) {
+      cudaEvent_t b = c->ev_get(); cudaEventRecord(b, c->stream); c->ev_pending.push_back({stage, a, b}); a = nullptr;
+      c->host_ms[stage] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); // host time spent inside the call (launches, waits)
+    }
+  }
   ~StageTimer() { stop(); }
 };
 StepParams step_params(kml_ctx *c) {
@@ -1317,6 +1323,11 @@ int kml_stage_times(kml_ctx *c, double ms[KML_STAGE_COUNT], int64_t launches[KML
   }
   for (int i = 0; i < KML_STAGE_COUNT; i++) { ms[i] = c->ms[i]; launches[i] = c->launches[i]; }
   if (reset) { memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches); }
+  return 0;
+}
+int kml_stage_host_times(kml_ctx *c, double ms[KML_STAGE_COUNT], int reset) {
+  for (int i = 0; i < KML_STAGE_COUNT; i++) ms[i] = c->host_ms[i];
+  if (reset) memset(c->host_ms, 0, sizeof c->host_ms);
   return 0;
 }
 

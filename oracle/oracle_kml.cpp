@@ -1371,6 +1371,7 @@ static double g_t0;
 static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 int kml_timer_start(kml_ctx *) { g_t0 = now_ms(); return 0; }
 int kml_timer_stop(kml_ctx *, double *ms) { *ms = now_ms() - g_t0; return 0; }
+int kml_stage_host_times(kml_ctx *, double ms[KML_STAGE_COUNT], int) { for (int i = 0; i < KML_STAGE_COUNT; i++) ms[i] = 0; return 0; }
 int kml_stage_times(kml_ctx *, double ms[KML_STAGE_COUNT], int64_t launches[KML_STAGE_COUNT], int) {
   for (int i = 0; i < KML_STAGE_COUNT; i++) { ms[i] = 0; launches[i] = 0; }
   return 0;
