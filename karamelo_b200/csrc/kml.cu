@@ -774,6 +774,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
           if (c->steps_started == 1) { CU(cudaStreamSynchronize(c->stream)); }
           const long long far = G->cl.far_count();
           if (far > c->permute_frac * (double)S->s.np && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
+            if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] step %lld: physical permute, %lld of %lld particles far from their cell-sorted slot\n", c->c.rank, c->steps_started, far, (long long)S->s.np);
             if (permute_solid(c, S, G)) return 1;
             S->last_permute_step = c->steps_started; G->cl.far_reset();
           }
