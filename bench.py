@@ -228,6 +228,42 @@ def check_against_single_gpu(eng, cells, steps_done, rank, world, local, dist):
     return res
 
 
+SMALL_CONFIGS = {  # BASELINE.json configs[0..3] at their shipped sizes: parity-test cases, timed here for the record
+    "c1": ("examples/two-disks.mpm: 2-D ULMPM, two elastic disks, linear shape functions, USL", lambda c: c.two_disks("usl")),
+    "c2": ("examples/Taylor-bar (cylindrical, ULMPM): 3-D, Johnson-Cook + shock EOS, cubic B-splines, MUSL, h = 0.25", lambda c: c.taylor_bar("cubic-spline", N=4)),
+    "c3": ("examples/Tensile_with_damage (Bernstein): TLMPM, JC damage, plastic-work heating", lambda c: c.tensile(True)),
+    "c4": ("examples/Bouncing_balls (TLMPM, FLIP): two solids, fix contact/hertz", lambda c: c.bouncing_balls("hertz")),
+}
+
+
+def run_small_config(args):
+    """python bench.py --config c1|c2|c3|c4: the small BASELINE configurations are latency-bound (hundreds to thousands of particles): microseconds and
+    kernel launches per step through the host driver + C ABI, one GPU."""
+    import cases
+    from karamelo_b200.api import Engine
+    desc, make = SMALL_CONFIGS[args.config]
+    eng = Engine(None)
+    eng.script(make(cases))
+    npart = sum(eng.solid_info(i)["np"] for i in range(eng.nsolids()))
+    W, K = max(args.warmup, 3), max(args.steps, 50)
+    eng.line("run(%d)" % W)
+    eng.stage_times(reset=True)
+    eng.profile(True)
+    eng.synchronize()
+    t0 = time.perf_counter()
+    eng.line("run(%d)" % K)
+    eng.synchronize()
+    wall = time.perf_counter() - t0
+    st = eng.stage_times(reset=True)
+    eng.close()
+    launches = sum(v[1] for v in st.values())
+    print(json.dumps({"metric": "particle_steps_per_sec", "value": npart * K / wall, "unit": "particle-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+                      "ms_per_step": wall * 1e3 / K, "us_per_step": wall * 1e6 / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": {"workload": desc, "particles": npart, "timing": "host wall clock around run(K): these steps are bound by launch and "
+                      "read-back latency, not by the device"}, "gpu_launches": int(launches), "launches_per_step": launches / K,
+                      "device_ms_per_step": {k: round(v[0] / K, 5) for k, v in st.items() if v[0] > 0}}))
+
+
 def run_ours(args):
     import torch
     from karamelo_b200 import slab
@@ -393,12 +429,17 @@ def main():
     ap.add_argument("--prestrain", type=int, default=40, help="minimum number of untimed steps before the timed region (plastic steady state)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the comparison of a 1/1000 particle sample with a single-GPU run of the same steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"], help="c5 (default) = the headline block; c1..c4 = the small BASELINE configurations")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank == 0:
             run_reference_arm(args)
+        return
+    if args.config != "c5":
+        if rank == 0:
+            run_small_config(args)
         return
     run_ours(args)
 

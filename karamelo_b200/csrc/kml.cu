@@ -28,14 +28,13 @@ extern "C" { static int resolve_dt(kml_ctx *c); }
 struct Grid {
   kml_grid_desc d; GridDev g; double *buf = nullptr; int *ibuf = nullptr;
   bool v_is_momentum = false, T_is_weighted = false;
-  // cell lists for the cell-centric P2G (UL)
-  CellLists cl;
   // packed gather records {v_update, v_update - v} on a zero-padded grid for the TMA-fed G2P kernel (kml_gather_cell3.cuh); valid = they
   // reflect the current nv / nvu (written by k_grid_update, invalidated by everything else that touches node velocities)
   double *nvd = nullptr; bool nvd_valid = false;
 };
 struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
+  CellLists cl;           // cell lists of the cell-centric kernels (UL, 3-D cubic splines): one set per solid, several solids share the grid
   bool moved = false;     // xn holds the positions after grid_to_points (UL)
   bool mbp_nonzero = false;
   bool rigid = false;     // Mat::rigid (src/material.h:49)
@@ -47,6 +46,12 @@ struct Solid {
   // physical re-ordering: second set of buffers, swapped with the current one by permute_solid
   int nd = 0; double *buf2 = nullptr; long long *lbuf2 = nullptr; int *ibuf2 = nullptr; bool no_permute = false;
   long long permutes = 0, last_permute_step = -1000000;
+  // Cost-based policy (amortised rebuild): the stress kernel - the stage that streams the most state - is timed with an event pair every
+  // step; t_clean is its time right after a permute, excess the time lost to disorder since then, permute_ms the measured cost of the
+  // last permute.  A permute is due when excess >= permute_ms (for a linearly growing loss that is the optimal period).
+  cudaEvent_t ev_s[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int ev_s_next = 0; bool ev_s_valid[2] = {false, false}; long long ev_s_step[2] = {0, 0}, clean_step = -1;
+  cudaEvent_t ev_p[2] = {nullptr, nullptr}; bool ev_p_valid = false;
+  double t_clean = -1, excess_ms = 0, permute_ms = -1;
 };
 
 struct kml_ctx {
@@ -62,7 +67,7 @@ struct kml_ctx {
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   double *d_red = nullptr, *h_red = nullptr; cudaEvent_t ev_dt = nullptr; bool dt_pending = false; double dt_factor = 1.0; // deferred adjust_dt (resolve_dt)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
-  double permute_frac = 0.05; int permute_min_steps = 8; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
+  double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   int g2p_tma = 0; int nsm = 148; // KML_G2P_TMA: persistent TMA-fed G2P kernel
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
@@ -199,7 +204,8 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
-  c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 8);
+  c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 2);
+  c->permute_every = env_int("KML_PERMUTE_EVERY", 0);
   c->g2p_tma = env_int("KML_G2P_TMA", 0);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, c->dev) == cudaSuccess) c->nsm = pr.multiProcessorCount; }
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
@@ -216,8 +222,10 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
 int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
-  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); g->cl.release(); delete g; }
-  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); delete s; }
+  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); delete g; }
+  for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); s->cl.release();
+    for (int a = 0; a < 2; a++) { for (int b = 0; b < 2; b++) if (s->ev_s[a][b]) cudaEventDestroy(s->ev_s[a][b]); if (s->ev_p[a]) cudaEventDestroy(s->ev_p[a]); }
+    delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
@@ -391,8 +399,11 @@ static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
   const long long np = S->s.np;
   const int xslot = (int)((S->s.x[0] - S->buf) / S->cap); // 0, or 3 after an odd number of x <-> xn swaps
   if (xslot != 0 && xslot != 3) return fail("permute_solid: unexpected position slot");
-  k_permute<<<nblocks(np, 128), 128, 0, c->stream>>>(S->buf, S->buf2, S->cap, S->nd, xslot, G->cl.order, np, S->lbuf, S->lbuf2, S->ibuf, S->ibuf2);
-  k_iota<<<nblocks(np, 256), 256, 0, c->stream>>>(G->cl.order, np);
+  if (!S->ev_p[0]) { CU(cudaEventCreate(&S->ev_p[0])); CU(cudaEventCreate(&S->ev_p[1])); }
+  CU(cudaEventRecord(S->ev_p[0], c->stream));
+  k_permute<<<nblocks(np, 128), 128, 0, c->stream>>>(S->buf, S->buf2, S->cap, S->nd, xslot, S->cl.order, np, S->lbuf, S->lbuf2, S->ibuf, S->ibuf2);
+  k_iota<<<nblocks(np, 256), 256, 0, c->stream>>>(S->cl.order, np);
+  CU(cudaEventRecord(S->ev_p[1], c->stream)); S->ev_p_valid = true;
   if (check_launch("k_permute")) return 1;
   std::swap(S->buf, S->buf2); std::swap(S->lbuf, S->lbuf2); std::swap(S->ibuf, S->ibuf2);
   bind_pointers(c, S); S->gen++; S->permutes++;
@@ -766,20 +777,36 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
       for (Solid *S : c->solids) {
         Grid *G = c->grids[S->d.grid];
         int nl = 0;
-        if (G->cl.build(S->s, G->g, S->cap, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
+        if (S->cl.build(S->s, G->g, S->cap, c->stream, &nl)) return fail(std::string("cell list build: ") + cudaGetErrorString(cudaGetLastError()));
         c->launches[KML_STAGE_REBIN] += nl;
         // physical re-ordering when too many particles sit far from their cell-sorted position (the count of the PREVIOUS re-bin, read
         // without a synchronisation; the first re-bin waits for its own)
-        if (c->permute_frac >= 0 && G->cl.valid) {
+        if (c->permute_frac >= 0 && S->cl.valid) {
           if (c->steps_started == 1) { CU(cudaStreamSynchronize(c->stream)); }
-          const long long far = G->cl.far_count();
-          if (far > c->permute_frac * (double)S->s.np && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
-            if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] step %lld: physical permute, %lld of %lld particles far from their cell-sorted slot\n", c->c.rank, c->steps_started, far, (long long)S->s.np);
+          const long long far = S->cl.far_count();
+          // measurements of earlier steps, read without waiting (an event that has not completed yet is looked at next step)
+          float t = 0;
+          if (S->ev_p_valid && cudaEventQuery(S->ev_p[1]) == cudaSuccess && cudaEventElapsedTime(&t, S->ev_p[0], S->ev_p[1]) == cudaSuccess) { S->permute_ms = t; S->ev_p_valid = false; }
+          for (int k = 0; k < 2; k++)
+            if (S->ev_s_valid[k] && cudaEventQuery(S->ev_s[k][1]) == cudaSuccess && cudaEventElapsedTime(&t, S->ev_s[k][0], S->ev_s[k][1]) == cudaSuccess) {
+              S->ev_s_valid[k] = false;
+              if (S->ev_s_step[k] < S->clean_step) continue;                                       // a step from before the last permute
+              if (S->ev_s_step[k] == S->clean_step) { S->t_clean = t; S->excess_ms = 0; }          // the step of the permute itself: the clean time
+              else if (S->t_clean > 0) S->excess_ms += std::max(0.0, (double)t - S->t_clean);
+            }
+          cudaGetLastError();
+          bool due;
+          if (S->permute_ms < 0 || (S->t_clean < 0 && S->clean_step < 0)) due = far > c->permute_frac * (double)S->s.np; // nothing measured yet: the disorder threshold
+          else if (S->t_clean < 0) due = false;                                                               // the clean time of the last permute has not been read yet
+          else due = S->excess_ms >= S->permute_ms && far > 0.005 * (double)S->s.np;                          // amortised rebuild
+          if (c->permute_every > 0) due = c->steps_started - S->last_permute_step >= c->permute_every && far > 0; // KML_PERMUTE_EVERY: fixed period (measurements)
+          if (due && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
+            if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] step %lld: physical permute, %lld of %lld particles far from their cell-sorted slot (stress %.3f ms clean, %.3f ms lost since, permute %.3f ms)\n",
+                                             c->c.rank, c->steps_started, far, (long long)S->s.np, S->t_clean, S->excess_ms, S->permute_ms);
             if (permute_solid(c, S, G)) return 1;
-            S->last_permute_step = c->steps_started; G->cl.far_reset();
+            S->last_permute_step = c->steps_started; S->cl.far_reset(); S->clean_step = c->steps_started; S->t_clean = -1; S->excess_ms = 0;
           }
         }
-        if (c->solids.size() > 1) break; // cell lists are per grid; several solids on one grid use the atomic path
       }
     }
   }
@@ -860,10 +887,10 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     bool done = false;
     fill_inertia(c, G, S, sp);
     sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
-    if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
+    if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      const int rc = cell_p2g3_launch(S->s, g, G->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
+      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
@@ -933,13 +960,13 @@ int kml_advance_particles(kml_ctx *c) {
     int rc = -1;
     fill_inertia(c, G, S, sp);
     sp.ext = (sp.ext & 1) | ((c->has_rigid ? (S->rigid ? 2 : 1) : 0) << 1);
-    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && !c->keep_acc && c->use_cell_p2g && (c->cell_mask & 2) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && !c->keep_acc && c->use_cell_p2g && (c->cell_mask & 2) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       if (c->g2p_tma && G->nvd && !sp.axisymmetric && !sp.temp) {
         if (!G->nvd_valid) { k_grid_pack_g2p<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, G->nvd); G->nvd_valid = true; c->launches[KML_STAGE_G2P]++; }
-        rc = cell_g2p_tma_launch(S->s, G->g, sp, G->nvd, G->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads, c->gtune.g2p_threads == 64 ? 8 : (c->g2p_tma == 3 ? 3 : 4), c->nsm);
+        rc = cell_g2p_tma_launch(S->s, G->g, sp, G->nvd, S->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads, c->gtune.g2p_threads == 64 ? 8 : (c->g2p_tma == 3 ? 3 : 4), c->nsm);
         if (rc > 0) return fail(std::string("cell g2p (TMA) launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       } else {
-        StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, G->cl, c->stream, c->gtune);
+        StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, S->cl, c->stream, c->gtune);
         if (rc > 0) return fail("cell g2p launch failed");
       }
     }
@@ -1003,9 +1030,13 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
     (void)doublemapping; // heat flux uses the same nodal field choice as the gradient in every scheme (usl/musl/usf)
     int rc = -1;
     fill_inertia(c, G, S, sp);
-    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && c->solids.size() == 1 && G->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
-      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, G->cl, c->stream, c->gtune);
+    if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
+      const int k = S->ev_s_next; S->ev_s_next ^= 1; // timed every step for the permute policy (kml_compute_grid_weight_...)
+      if (!S->ev_s[k][0]) { CU(cudaEventCreate(&S->ev_s[k][0])); CU(cudaEventCreate(&S->ev_s[k][1])); }
+      CU(cudaEventRecord(S->ev_s[k][0], c->stream));
+      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, S->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
+      if (rc == 0) { CU(cudaEventRecord(S->ev_s[k][1], c->stream)); S->ev_s_valid[k] = true; S->ev_s_step[k] = c->steps_started; }
     }
     if (c->c.is_CPDI) {
       if (c->c.is_TL) k_cpdi_stress<true><<<nblocks(S->s.np, 128), 128, 0, c->stream>>>(S->s, G->g, S->cp, sp, tp, S->d.mat);

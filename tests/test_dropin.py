@@ -55,8 +55,11 @@ def test_binding_over_cuda_matches_the_stock_reference(name, tmp_path):
     nps = [int(m) for m in re.findall(r"^np_local=(\d+)", out_r, flags=re.M)]
     ref = read_restart_solids(str(tmp_path / "ref" / "r-50.restart"), nps, is_tl, thermal)
     got = read_restart_solids(str(tmp_path / "b200" / "r-50.restart"), nps, is_tl, thermal)
+    # the Tait fluid's pressure K ((rho / rho0)^7 - 1) with K = 1.4e6 cancels seven digits: the atomic summation order of the node masses
+    # shows up at 2e-10 of the stress magnitude after 50 steps (measured); every other field of that case and all other cases hold 1e-10
+    tol = {"sigma": 1e-9} if name == "x_fluid_column" else {}
     for a, b in zip(got, ref):
         assert (a["ptag"] == b["ptag"]).all()
         for k in ("x", "v", "sigma", "F", "eps", "epsdot", "damage"):
             scale = max(float(np.abs(b[k]).max()), 1e-300)
-            assert float(np.abs(a[k] - b[k]).max()) <= 1e-10 * scale, (name, k, float(np.abs(a[k] - b[k]).max()) / scale)
+            assert float(np.abs(a[k] - b[k]).max()) <= tol.get(k, 1e-10) * scale, (name, k, float(np.abs(a[k] - b[k]).max()) / scale)
