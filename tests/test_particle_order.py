@@ -30,11 +30,11 @@ def test_oracle_shuffled_block(oracle_lib):
 @pytest.mark.parametrize("policy", ["default", "never", "often"])
 def test_cuda_shuffled(cuda_lib, name, policy, monkeypatch):
     """default: the engine re-orders the shuffled state physically at the first re-bin (kml.cu permute_solid); never: index-only order,
-    every stream a gather; often: a physical permute every third step whenever a single particle is out of place."""
+    every stream a gather; often: a physical permute every third step whenever a single particle is out of place (the default rule weighs
+    the stress time lost to disorder against the measured cost of a permute)."""
     if policy == "never":
         monkeypatch.setenv("KML_PERMUTE_FRAC", "-1")
     elif policy == "often":
-        monkeypatch.setenv("KML_PERMUTE_FRAC", "0")
-        monkeypatch.setenv("KML_PERMUTE_MIN_STEPS", "3")
+        monkeypatch.setenv("KML_PERMUTE_EVERY", "3")
     golden, _ = load_golden(name)
     print(name, policy, compare_to_golden(_run(cuda_lib, name, 7), golden, 1e-10))
