@@ -1062,7 +1062,7 @@ static int resolve_dt(kml_ctx *c) {
   CU(cudaEventSynchronize(c->ev_dt));
   const int ns = (int)c->solids.size();
   unsigned flags = 0; for (int b = 0; b < 8; b++) if (c->h_red[KML_RED_BITS + b] != 0.0) flags |= 1u << b;
-  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow)");
+  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow, 32: particle migration bookkeeping)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
     Solid *S = c->solids[i]; Grid *G = c->grids[S->d.grid];
@@ -1148,10 +1148,7 @@ int kml_exchange_particles(kml_ctx *c) {
       k_mig_flag<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_list, cm.mig_cap, nL, nR, cm.mig_flag, np_new);
       k_mig_holes<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_list, cm.mig_cap, nL, nR, np_new, cm.mig_cnt, holes);
       k_mig_fillers<<<nblocks(ntail, 128), 128, 0, c->stream>>>(cm.mig_flag, np_new, ntail, cm.mig_cnt, fillers);
-      CU(cudaMemcpyAsync(cm.h_cnt + 4, cm.mig_cnt + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      if (cm.h_cnt[4] != cm.h_cnt[5]) return fail("migration: hole / filler count mismatch");
-      if (cm.h_cnt[4]) k_mig_move<<<nblocks(cm.h_cnt[4], 128), 128, 0, c->stream>>>(holes, fillers, cm.h_cnt[4], S->buf, S->cap, narr, s.ptag, s.mask);
+      k_mig_move<<<nblocks(ntail, 128), 128, 0, c->stream>>>(holes, fillers, cm.mig_cnt, c->d_flags, S->buf, S->cap, narr, s.ptag, s.mask); // no read-back: at most ntail moves
     }
     if (rL) k_mig_unpack<<<nblocks(rL, 128), 128, 0, c->stream>>>(recvL, rL, np_new, S->buf, S->cap, narr, xs, s.ptag, s.mask);
     if (rR) k_mig_unpack<<<nblocks(rR, 128), 128, 0, c->stream>>>(recvR, rR, np_new + rL, S->buf, S->cap, narr, xs, s.ptag, s.mask);

@@ -110,8 +110,11 @@ __global__ void k_mig_fillers(const int *flag, long long np_new, int ntail, int 
   if (j >= ntail) return;
   if (!flag[j]) fillers[atomicAdd(&cnt[5], 1)] = (int)(np_new + j);
 }
-__global__ void k_mig_move(const int *holes, const int *fillers, int n, double *base, long long cap, int narr, long long *ptag, int *mask) {
+// the hole / filler counts stay on the device (cnt[4], cnt[5]; equal by construction - a mismatch raises bit 5 of the error word)
+__global__ void k_mig_move(const int *holes, const int *fillers, const int *cnt, unsigned *flags, double *base, long long cap, int narr, long long *ptag, int *mask) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(cnt[4], cnt[5]);
+  if (j == 0 && cnt[4] != cnt[5]) atomicOr(flags, 32u);
   if (j >= n) return;
   const int h = holes[j], f = fillers[j];
   for (int a = 0; a < narr; a++) base[a * cap + h] = base[a * cap + f];
