@@ -49,6 +49,11 @@ __device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, doub
 #pragma unroll
     for (int a = 0; a < 4; a++) cubic_node(xp, lo, h, ih, i0 + a, n, goff, gn, w[a], dw[a]);
   }
+  // The reference keeps a node in a particle's neighbour list only `if (wf != 0)` (src/ulmpm.cpp:252-263): a stencil node whose weight ROUNDS
+  // to exactly zero is dropped together with its gradient, which is not zero there (a particle 6e-6 h short of leaving node a has
+  // w = 4e-17 -> 0 in the Horner form, dw = 2e-11 / h).  Mirrored here: no weight, no gradient (tests/test_weight_zero_skip.py).
+#pragma unroll
+  for (int a = 0; a < 4; a++) dw[a] = (w[a] == 0.0) ? 0.0 : dw[a];
 }
 __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) {
   const int ig = i0 + goff;

@@ -516,6 +516,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
     const double *lo = g->d.lo; // UL: domain->boxlo; TL: solidlo (the grid origin in both cases)
     for (int64_t in = 0; in < nnodes; in++) { s->neigh_np[in].clear(); s->wf_np[in].clear(); s->wfd_np[in].clear(); }
     std::vector<int> n_neigh;
+    const bool keep_zero = getenv("KML_ORACLE_KEEP_ZERO_WEIGHT") != nullptr; // read at every re-bin: a test can switch it between runs
     for (int64_t ip = 0; ip < s->np; ip++) {
       s->neigh_pn[ip].clear(); s->wf_pn[ip].clear(); s->wfd_pn[ip].clear();
       n_neigh.clear();
@@ -573,6 +574,9 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
             if (dim == 3 && wf != 0) { sv[2] = c->bf(r[2], g->ntype[in][2]); wf *= sv[2]; } else sv[2] = 1;
           }
           keep = wf != 0;
+          // diagnostic knob of the test suite (tests/test_weight_zero_skip.py): keep nodes whose weight rounds to exactly zero, i.e. drop the
+          // reference's `if (wf != 0)` membership test, to measure how much of a disagreement that test alone explains
+          if (keep_zero) { if (dim >= 2 && sv[0] == 0) sv[1] = c->bf(r[1], g->ntype[in][1]); if (dim == 3 && (sv[0] == 0 || sv[1] == 0)) sv[2] = c->bf(r[2], g->ntype[in][2]); keep = true; }
         } else { // tlmpm.cpp:275-297
           sv[0] = c->bf(r[0], g->ntype[in][0]);
           sv[1] = dim >= 2 ? c->bf(r[1], g->ntype[in][1]) : 1;

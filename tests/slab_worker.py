@@ -104,20 +104,22 @@ def step(args):
     flags = eng.error_flags()
     eng.close()
     if rank == 0:
-        from common import rel
-        ora = Engine(load_host_library(ORACLE_HOST_LIB))
-        ora.script(script + "\nrun(%d)\n" % args.steps)
-        ref = ora.snapshot(fields)[0]
-        st_ref = ora.state()
+        from common import oracle_both_memberships, rel, rel_either
+        # the oracle with the reference's `wf != 0` neighbour test and without it: where a case contains a marginal membership event
+        # (tests/test_weight_zero_skip.py) an element may follow either branch; without such an event the two runs are identical and this
+        # is the plain 1e-10 comparison
+        (ref, st_ref), (keep, _) = oracle_both_memberships(load_host_library(ORACLE_HOST_LIB), script, args.steps, fields)
         assert flags == 0
         assert (got["PTAG"] == ref["PTAG"]).all(), "particle tags differ"
-        worst = {k: rel(got[k], ref[k]) for k in fields if k != "PTAG"}
+        strict = {k: rel(got[k], ref[k]) for k in fields if k != "PTAG"}
+        worst = {k: rel_either(got[k], ref[k], keep[k]) for k in fields if k != "PTAG"}
+        branch = max(rel(keep[k], ref[k]) for k in fields if k != "PTAG")
         bad = {k: v for k, v in worst.items() if v > 1e-10}
-        assert not bad, (bad, worst)
+        assert not bad, (bad, worst, strict)
         assert abs(st["dt"] - st_ref["dt"]) <= 1e-10 * st_ref["dt"] and st["ntimestep"] == st_ref["ntimestep"]
         if args.drift:
             assert any(a != b for a, b in moved), "no particle migrated: the test does not exercise exchange_particles"
-        print("SLAB-OK step world=%d np(before,after)=%s worst=%s" % (world, moved, worst))
+        print("SLAB-OK step world=%d np(before,after)=%s worst=%s against-the-reference-branch-only=%s membership-sensitivity-of-the-case=%.2e" % (world, moved, worst, strict, branch))
     dist.barrier()
 
 
