@@ -324,6 +324,11 @@ def run_ours(args):
     value = npart * K / (ms * 1e-3)
     stage_ms = {k: max_over_ranks(v[0] / K) for k, v in st.items()}
     stage_sum_local = sum(v[0] for v in st.values()) / K
+    per_rank = None
+    if world > 1:  # who waits for whom: every rank's own stage means and step time (the comm stages contain the wait for the neighbours)
+        rows = [None] * world
+        dist.all_gather_object(rows, dict({k: round(v[0] / K, 3) for k, v in st.items() if v[0] > 0}, step=round(ms_local / K, 3), permutes=max(0, (int(st["rebin"][1]) - 4 * K) // 2)))
+        per_rank = {k: [r.get(k, 0.0) for r in rows] for k in rows[0]}
     np_max = int(max_over_ranks(np_local))
     peak, peak_src = measured_peak()
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -347,6 +352,8 @@ def run_ours(args):
                 "comm_ms": {k: round(stage_ms.get(k, 0.0), 4) for k in ("halo", "migrate", "dt")},
                 "host_ms_in_calls_rank0": host_ms, "wall_ms_per_step_rank0": round(wall_ms, 4),
                 "physical_permutes_in_timed_region_rank0": max(0, (int(st["rebin"][1]) - 4 * K) // 2)}
+    if per_rank:
+        roofline["per_rank_stage_ms"] = per_rank
 
     # regime of the timed steps + (N > 1) parity of the decomposed run with a single-GPU run of the same number of steps
     steps_done = W_eff + K

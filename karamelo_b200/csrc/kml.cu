@@ -3,7 +3,6 @@
 #define KML_MISC_KERNELS
 #include "kml_launch.h"
 #include "kml_gather_cell3.cuh"
-#include "kml_p2g_cell4.cuh"
 #include "kml_comm.cuh"
 #include "kml_cpdi.cuh"
 #include "kml_setup.cuh"
@@ -70,7 +69,7 @@ struct kml_ctx {
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   int g2p_tma = 0; int nsm = 148; // KML_G2P_TMA: persistent TMA-fed G2P kernel
-  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2, p2g_v = 4, p2g_minb = 4; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
+  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
   // Per-stage device time: event pairs are recorded around every stage and only READ in kml_stage_times (one synchronisation for the
@@ -203,7 +202,6 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
-  c->p2g_v = env_int("KML_P2G_V", 4); c->p2g_minb = env_int("KML_P2G_MINB", 4); // 4: kml_p2g_cell4.cuh (cp.async raw prefetch, 4 blocks per SM), 3: kml_p2g_cell3.cuh
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
   c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 2);
@@ -892,8 +890,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      const int rc = c->p2g_v == 4 ? cell_p2g4_launch(S->s, g, S->cl, what, c->v2g_nb, c->p2g_minb, c->gtune.seg_target, c->stream, &nl)
-                                   : cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
+      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }

@@ -18,6 +18,20 @@ namespace kml {
 // ------------------------------------------------------------------------------------------
 template <int SHAPE> struct Basis;
 
+// Neighbour membership is decided by the reference's arithmetic.  The reference drops a (particle, node) pair whose weight is exactly 0
+// (src/ulmpm.cpp:252-263, src/tlmpm.cpp:282) and its weights are Horner forms with separately rounded products and sums (a stock x86-64
+// build has no FMA contraction).  Near the end of a spline's support the true weight is far below one ulp of the constant term, so
+// whether the computed weight IS zero depends on that operation sequence, while the gradient there is not small at all.  The kernels
+// evaluate the polynomials with FMAs; for a tiny result they replay the reference's sequence, which makes the weight the reference's bit
+// for bit in exactly the regime where its zero-ness matters (tests/test_weight_zero_skip.py).
+__device__ __forceinline__ bool weight_tiny(double w) { return (__double2hiint(w) & 0x7fffffff) < 0x3cd00000; } // |w| < 2^-50
+__device__ __forceinline__ double horner3_unfused(double c3, double c2, double c1, double c0, double r) { // ((c3 r + c2) r + c1) r + c0
+  return __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c3, r), c2), r), c1), r), c0);
+}
+__device__ __forceinline__ double horner2_unfused(double c2, double c1, double c0, double r) { // (c2 r + c1) r + c0
+  return __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(c2, r), c1), r), c0);
+}
+
 template <> struct Basis<KML_SHAPE_LINEAR> {
   static constexpr int SPAN = 2;
   __device__ __forceinline__ static void eval(double r, int, double ih, double &s, double &sd) {
@@ -33,7 +47,7 @@ template <> struct Basis<KML_SHAPE_CUBIC_SPLINE> {
   __device__ __forceinline__ static void eval(double r, int nt, double ih, double &s, double &sd) {
     if (r >= 1 && r < 2) {
       if (nt == 1) { s = 0; sd = -ih; }
-      else { s = ((-1.0 / 6.0 * r + 1) * r - 2) * r + 4.0 / 3.0; sd = ih * ((-0.5 * r + 2) * r - 2); }
+      else { s = ((-1.0 / 6.0 * r + 1) * r - 2) * r + 4.0 / 3.0; sd = ih * ((-0.5 * r + 2) * r - 2); if (weight_tiny(s)) s = horner3_unfused(-1.0 / 6.0, 1.0, -2.0, 4.0 / 3.0, r); }
     } else if (r >= 0 && r < 1) {
       if (nt == -2) { s = (1.0 / 6.0 * r * r - 1) * r + 1; sd = ih * (0.5 * r * r - 1); }
       else if (nt == 2) { s = 1; sd = ih; }
@@ -44,7 +58,7 @@ template <> struct Basis<KML_SHAPE_CUBIC_SPLINE> {
       else if (nt == -1) { s = (-1.0 / 3.0 * r - 1) * r * r + 2.0 / 3.0; sd = ih * (-r - 2) * r; }
       else { s = (-0.5 * r - 1) * r * r + 2.0 / 3.0; sd = ih * (-3.0 / 2.0 * r - 2) * r; }
     } else if (r >= -2 && r < -1) {
-      s = ((1.0 / 6.0 * r + 1) * r + 2) * r + 4.0 / 3.0; sd = ih * ((0.5 * r + 2) * r + 2);
+      s = ((1.0 / 6.0 * r + 1) * r + 2) * r + 4.0 / 3.0; sd = ih * ((0.5 * r + 2) * r + 2); if (weight_tiny(s)) s = horner3_unfused(1.0 / 6.0, 1.0, 2.0, 4.0 / 3.0, r);
     } else { s = 0; sd = 0; }
     if (s == 0) sd = 0;
   }
@@ -72,6 +86,10 @@ template <> struct Basis<KML_SHAPE_QUADRATIC_SPLINE> { // incl. the interval qui
     } else {
       if (r >= -1.5 && r < -0.5) { s = (0.5 * r + 1.5) * r + 1.125; sd = ih * (r + 1.5); }
       else if (r >= -0.5 && r <= 0.) { s = 1 + r; sd = ih; }
+    }
+    if (weight_tiny(s)) { // the outer polynomial pieces near +-1.5 (a tiny value anywhere else is exact)
+      if (r >= 0.5 && r < 1.5 && !(nt == 1)) s = horner2_unfused(0.5, -1.5, 1.125, r);
+      else if (r < -0.5 && r >= -1.5 && nt != -2 && nt != -1) s = horner2_unfused(0.5, 1.5, 1.125, r);
     }
     if (s == 0) sd = 0;
   }

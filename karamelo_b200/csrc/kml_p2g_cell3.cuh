@@ -36,6 +36,17 @@ __device__ __forceinline__ void cubic_piece(int a, double r, double ih, double &
   else { w = ((1.0 / 6.0 * r + 1) * r + 2) * r + 4.0 / 3.0; dw = ih * ((0.5 * r + 2) * r + 2); }
 }
 
+// Neighbour membership (kml_device.cuh weight_tiny): the branch-free pieces use FMAs; a tiny weight of one of the two outer nodes is
+// recomputed with the reference's operation sequence, and no weight means no gradient.
+__device__ __forceinline__ void cubic_membership(double xp, double lo, double h, double ih, int ig, bool upper, double &w, double &dw) { // ig: GLOBAL node index
+  if (weight_tiny(w)) {
+    const double xn = __dadd_rn(lo, __dmul_rn((double)ig, h));
+    const double r = __dmul_rn(__dsub_rn(xp, xn), ih);
+    w = upper ? horner3_unfused(1.0 / 6.0, 1.0, 2.0, 4.0 / 3.0, r) : horner3_unfused(-1.0 / 6.0, 1.0, -2.0, 4.0 / 3.0, r);
+    if (w == 0.0) dw = 0.0;
+  }
+}
+
 // (w, dw) of the 4 stencil nodes i0..i0+3 (LOCAL indices) of one axis; interior = all four nodes exist and have ntype 0
 __device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, double ih, int i0, int n, int goff, int gn, bool interior, double (&w)[4], double (&dw)[4]) {
   if (interior) {
@@ -45,15 +56,12 @@ __device__ __forceinline__ void cubic_axis4(double xp, double lo, double h, doub
       const double r = __dmul_rn(__dsub_rn(xp, xn), ih);
       cubic_piece(a, r, ih, w[a], dw[a]);
     }
+    cubic_membership(xp, lo, h, ih, i0 + goff, false, w[0], dw[0]);    // node 0 sees r in [1, 2), node 3 r in [-2, -1); the inner two carry at least 1/6
+    cubic_membership(xp, lo, h, ih, i0 + 3 + goff, true, w[3], dw[3]);
   } else {
 #pragma unroll
-    for (int a = 0; a < 4; a++) cubic_node(xp, lo, h, ih, i0 + a, n, goff, gn, w[a], dw[a]);
+    for (int a = 0; a < 4; a++) cubic_node(xp, lo, h, ih, i0 + a, n, goff, gn, w[a], dw[a]); // Basis<>::eval: membership included
   }
-  // The reference keeps a node in a particle's neighbour list only `if (wf != 0)` (src/ulmpm.cpp:252-263): a stencil node whose weight ROUNDS
-  // to exactly zero is dropped together with its gradient, which is not zero there (a particle 6e-6 h short of leaving node a has
-  // w = 4e-17 -> 0 in the Horner form, dw = 2e-11 / h).  Mirrored here: no weight, no gradient (tests/test_weight_zero_skip.py).
-#pragma unroll
-  for (int a = 0; a < 4; a++) dw[a] = (w[a] == 0.0) ? 0.0 : dw[a];
 }
 __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) {
   const int ig = i0 + goff;

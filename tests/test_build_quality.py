@@ -10,9 +10,8 @@ from conftest import ROOT
 
 LOG = os.path.join(ROOT, "karamelo_b200", "lib", "ptxas.log")
 HEADLINE = {
-    "k_p2g_cell4ILb1ELb1ELi1ELi4E": 128,  # full P2G (4 blocks of 128 threads per SM)
-    "k_p2g_cell4ILb0ELb0ELi2ELi4E": 128,  # MUSL momentum re-projection
-    "k_p2g_cell3ILb1ELb1ELi1E": 164,  # previous generation, kept for A/B runs (KML_P2G_V=3)
+    "k_p2g_cell3ILb1ELb1ELi1E": 164,  # full P2G
+    "k_p2g_cell3ILb0ELb0ELi2E": 128,  # MUSL momentum re-projection
     "k_g2p_cellILi64ELi8E": 128,      # G2P + advance
     "k_stress_cellILi64ELi6E": 168,   # gradient + F + stress
 }

@@ -23,6 +23,53 @@ __global__ void k_dfma(double *out, int iters, long long *clocks) {
   if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
 }
 
+// Mixed issue: every DFMA is followed by NI independent integer IMADs (and NL shared-memory loads per 8 DFMAs).  If a DFMA occupied only
+// its own pipe, the integer work would hide in the pipe's second cycle and the DFMA rate would not move until NI > 1; what the B200
+// does is the measurement behind the "issue slots" column of DESIGN.md section 3.
+template <int ILP, int NI, int NL>
+__global__ void k_mixed(double *out, int iters, long long *clocks) {
+  __shared__ double sh[256];
+  sh[threadIdx.x & 255] = threadIdx.x;
+  __syncthreads();
+  double a[ILP], x = 1.0000001 + threadIdx.x * 1e-9, y = 0.9999999, ld = 0;
+  int k[ILP * (NI > 0 ? NI : 1)];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) a[i] = i + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < ILP * (NI > 0 ? NI : 1); i++) k[i] = i + threadIdx.x;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) {
+      a[i] = fma(a[i], x, y);
+#pragma unroll
+      for (int j = 0; j < NI; j++) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(k[i * NI + j]) : "r"(blockDim.x), "r"(it)); // one IMAD, not foldable
+    }
+#pragma unroll
+    for (int j = 0; j < NL; j++) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(sh) + 8u * ((threadIdx.x + j * 32) & 255))); ld += v; }
+  }
+  long long t1 = clock64();
+  double s = ld;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s += a[i];
+#pragma unroll
+  for (int i = 0; i < ILP * (NI > 0 ? NI : 1); i++) s += k[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+}
+template <int ILP, int NI, int NL> void run_mixed(int nsm, int threads, int blocks_per_sm, int iters) {
+  const int nb = nsm * blocks_per_sm;
+  double *out; long long *clk; cudaMalloc(&out, sizeof(double) * nb * threads); cudaMalloc(&clk, sizeof(long long) * nb);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_mixed<ILP, NI, NL><<<nb, threads>>>(out, iters / 8, clk); cudaDeviceSynchronize();
+  cudaEventRecord(e0); k_mixed<ILP, NI, NL><<<nb, threads>>>(out, iters, clk); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  const double dfma = (double)nb * threads * ILP * iters;
+  printf("mixed: %d IMAD per DFMA, %d LDS per %d DFMA, %d warps/sub-partition: %.2f T DFMA/s, %.2f T warp-instr/s issued (%.3f ms)\n", NI, NL, ILP,
+         threads * blocks_per_sm / 128, dfma / (ms * 1e-3) * 1e-12, dfma * (1 + NI + (double)NL / ILP + 2.0 / ILP) / 32 / (ms * 1e-3) * 1e-12, ms);
+  cudaFree(out); cudaFree(clk);
+}
+
 template <int ILP> void run(int nsm, int threads, int blocks_per_sm, int iters) {
   const int nb = nsm * blocks_per_sm;
   double *out; long long *clk; cudaMalloc(&out, sizeof(double) * nb * threads); cudaMalloc(&clk, sizeof(long long) * nb);
@@ -47,5 +94,12 @@ int main() {
   run<8>(nsm, 256, 4, iters);   // 8 warps per sub-partition
   run<16>(nsm, 128, 3, iters);
   run<2>(nsm, 1024, 2, iters);  // 16 warps per sub-partition, little ILP
+  // what shares the issue port with the FP64 pipe (3 warps per sub-partition, the occupancy of the P2G / stress kernels)
+  run_mixed<8, 0, 0>(nsm, 128, 3, iters);
+  run_mixed<8, 1, 0>(nsm, 128, 3, iters);
+  run_mixed<8, 2, 0>(nsm, 128, 3, iters);
+  run_mixed<8, 0, 2>(nsm, 128, 3, iters);
+  run_mixed<8, 1, 2>(nsm, 128, 3, iters);
+  run_mixed<8, 1, 0>(nsm, 128, 4, iters);
   return 0;
 }
