@@ -19,7 +19,7 @@ using namespace kml;
 
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }
-enum { KML_RED_BITS = 64 }; // d_red: [2 i] max wave speed, [2 i + 1] min_h_ratio of solid i; [KML_RED_BITS + b] bit b of the error word
+enum { KML_RED_BITS = 64, KML_RED_N = KML_RED_BITS + 16 }; // d_red: [2 i] max wave speed, [2 i + 1] min_h_ratio of solid i; [KML_RED_BITS + b] bit b of the error word; [KML_RED_BITS + 8] a rank asks for a physical permute
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 #define CUV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); } } while (0)
 
@@ -31,6 +31,7 @@ struct Grid {
   // packed gather records {v_update, v_update - v} on a zero-padded grid for the TMA-fed G2P kernel (kml_gather_cell3.cuh); valid = they
   // reflect the current nv / nvu (written by k_grid_update, invalidated by everything else that touches node velocities)
   double *nvd = nullptr; bool nvd_valid = false;
+  double *nvs = nullptr; bool nvs_valid = false; // padded copy of the node records {v, mass} for the bulk-copied stress tile; valid = it holds the current nv
 };
 struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
@@ -67,9 +68,10 @@ struct kml_ctx {
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   double *d_red = nullptr, *h_red = nullptr; cudaEvent_t ev_dt = nullptr; bool dt_pending = false; double dt_factor = 1.0; // deferred adjust_dt (resolve_dt)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
+  bool permute_want = false, permute_go = false, dt_collective = false; // decomposed runs: a rank's wish travels with the dt all-reduce and all ranks re-order in the same step (no rank waits for another's permute)
   double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
-  int g2p_tma = 0; int nsm = 148; // KML_G2P_TMA: persistent TMA-fed G2P kernel
-  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
+  int g2p_tma = 4, stress_bulk = 1; int nsm = 148; // KML_G2P_TMA: 0 = tile through registers, 1 / 3 = persistent TMA-fed kernel, 4 = one block per segment with a bulk-copied tile (default); KML_STRESS_BULK
+  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2, p2g_pipe = 1; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
   // Per-stage device time: event pairs are recorded around every stage and only READ in kml_stage_times (one synchronisation for the
@@ -194,19 +196,20 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   CU(cudaMalloc(&c->d_flags, sizeof(unsigned))); CU(cudaMemset(c->d_flags, 0, sizeof(unsigned)));
   CU(cudaMalloc(&c->d_scratch, 64 * sizeof(double)));
   CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
-  CU(cudaMalloc(&c->d_red, (KML_RED_BITS + 8) * sizeof(double))); CU(cudaMemset(c->d_red, 0, (KML_RED_BITS + 8) * sizeof(double)));
-  CU(cudaMallocHost(&c->h_red, (KML_RED_BITS + 8) * sizeof(double))); CU(cudaEventCreateWithFlags(&c->ev_dt, cudaEventDisableTiming));
+  CU(cudaMalloc(&c->d_red, KML_RED_N * sizeof(double))); CU(cudaMemset(c->d_red, 0, KML_RED_N * sizeof(double)));
+  CU(cudaMallocHost(&c->h_red, KML_RED_N * sizeof(double))); CU(cudaEventCreateWithFlags(&c->ev_dt, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB));
   memset(c->ms, 0, sizeof c->ms); memset(c->launches, 0, sizeof c->launches);
   const char *e = getenv("KML_P2G");
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
+  c->p2g_pipe = env_int("KML_P2G_PIPE", 1);
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
   c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 2);
   c->permute_every = env_int("KML_PERMUTE_EVERY", 0);
-  c->g2p_tma = env_int("KML_G2P_TMA", 0);
+  c->g2p_tma = env_int("KML_G2P_TMA", 4); c->stress_bulk = env_int("KML_STRESS_BULK", 1);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, c->dev) == cudaSuccess) c->nsm = pr.multiProcessorCount; }
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
@@ -222,7 +225,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
 int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
-  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); delete g; }
+  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); cudaFree(g->nvs); delete g; }
   for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); s->cl.release();
     for (int a = 0; a < 2; a++) { for (int b = 0; b < 2; b++) if (s->ev_s[a][b]) cudaEventDestroy(s->ev_s[a][b]); if (s->ev_p[a]) cudaEventDestroy(s->ev_p[a]); }
     delete s; }
@@ -277,9 +280,15 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
 }
 int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.nn; return 0; }
 
-static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
+static int grid_normalize_if_needed(kml_ctx *c, Grid *G, bool want_nvs = false) {
   if (!G->v_is_momentum && !G->T_is_weighted) return 0;
-  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, 0.0 /* dt is not used without the update */, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr);
+  double *nvs = nullptr;
+  if (want_nvs) {
+    if (!G->nvs) { const size_t nb = sizeof(double) * nvd_doubles(G->g) / 6 * 4; CU(cudaMalloc(&G->nvs, nb)); CU(cudaMemsetAsync(G->nvs, 0, nb, c->stream)); }
+    nvs = G->nvs;
+  }
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, 0.0 /* dt is not used without the update */, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr, nvs);
+  G->nvs_valid = nvs != nullptr;
   G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = false; c->launches[KML_STAGE_GRID]++;
   return check_launch("k_grid_update(normalize)");
 }
@@ -312,7 +321,7 @@ int kml_grid_upload(kml_ctx *c, int gid, int field, const void *src) {
   if (ic) { CU(cudaMemcpyAsync(ic, src, sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_N_V) G->v_is_momentum = false;
   if (field == KML_N_T) G->T_is_weighted = false;
-  G->nvd_valid = false;
+  G->nvd_valid = false; G->nvs_valid = false;
   const double *s = (const double *)src;
   for (int k = 0; k < nc; k++) { // strided 2-D copy: host column k of [nn][nc] -> device component
     CU(cudaMemcpy2DAsync(comp[k], sizeof(double) * stride, s + k, sizeof(double) * nc, sizeof(double), nn, cudaMemcpyHostToDevice, c->stream));
@@ -800,7 +809,12 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
           else if (S->t_clean < 0) due = false;                                                               // the clean time of the last permute has not been read yet
           else due = S->excess_ms >= S->permute_ms && far > 0.005 * (double)S->s.np;                          // amortised rebuild
           if (c->permute_every > 0) due = c->steps_started - S->last_permute_step >= c->permute_every && far > 0; // KML_PERMUTE_EVERY: fixed period (measurements)
-          if (due && c->steps_started - S->last_permute_step >= c->permute_min_steps) {
+          if (c->comm.nranks > 1 && c->dt_collective && c->permute_every <= 0) { // collective decision (one step late): ask now, act when the all-reduce said so
+            if (due && c->steps_started - S->last_permute_step >= c->permute_min_steps && c->steps_started > 1) c->permute_want = true;
+            due = c->permute_go || (c->steps_started == 1 && due);
+            if (due) c->permute_go = false;
+          }
+          if (due && c->steps_started - S->last_permute_step >= (c->comm.nranks > 1 && c->dt_collective ? 0 : c->permute_min_steps)) {
             if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] step %lld: physical permute, %lld of %lld particles far from their cell-sorted slot (stress %.3f ms clean, %.3f ms lost since, permute %.3f ms)\n",
                                              c->c.rank, c->steps_started, far, (long long)S->s.np, S->t_clean, S->excess_ms, S->permute_ms);
             if (permute_solid(c, S, G)) return 1;
@@ -890,7 +904,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
+      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl, c->p2g_pipe != 0); // -1: combination not covered -> atomic kernel
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
@@ -906,7 +920,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (check_launch("k_p2g")) return 1;
     if (what & P2G_MOM) G->v_is_momentum = true;
     if (what & P2G_TEMP) G->T_is_weighted = true;
-    G->nvd_valid = false;
+    G->nvd_valid = false; G->nvs_valid = false;
   }
   if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
   t.stop();
@@ -938,8 +952,8 @@ int kml_update_grid_state(kml_ctx *c) {
       if (!G->nvd) { const size_t nb = sizeof(double) * nvd_doubles(G->g); CU(cudaMalloc(&G->nvd, nb)); CU(cudaMemsetAsync(G->nvd, 0, nb, c->stream)); }
       nvd = G->nvd;
     }
-    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid, nvd);
-    G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = nvd != nullptr; c->launches[KML_STAGE_GRID]++;
+    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid, nvd, nullptr);
+    G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = nvd != nullptr; G->nvs_valid = false; c->launches[KML_STAGE_GRID]++;
     if (check_launch("k_grid_update")) return 1;
   }
   return 0;
@@ -963,7 +977,8 @@ int kml_advance_particles(kml_ctx *c) {
     if (!c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && !c->keep_acc && c->use_cell_p2g && (c->cell_mask & 2) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       if (c->g2p_tma && G->nvd && !sp.axisymmetric && !sp.temp) {
         if (!G->nvd_valid) { k_grid_pack_g2p<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, G->nvd); G->nvd_valid = true; c->launches[KML_STAGE_G2P]++; }
-        rc = cell_g2p_tma_launch(S->s, G->g, sp, G->nvd, S->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads, c->gtune.g2p_threads == 64 ? 8 : (c->g2p_tma == 3 ? 3 : 4), c->nsm);
+        if (c->g2p_tma == 4) rc = cell_g2p_bulk_launch(S->s, G->g, sp, G->nvd, S->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads); // one block per segment, bulk-copied tile
+        else rc = cell_g2p_tma_launch(S->s, G->g, sp, G->nvd, S->cl, c->stream, c->gtune.seg_g2p, c->gtune.g2p_threads, c->gtune.g2p_threads == 64 ? 8 : (c->g2p_tma == 3 ? 3 : 4), c->nsm);
         if (rc > 0) return fail(std::string("cell g2p (TMA) launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       } else {
         StressParams none{}; rc = cell_gather_launch(false, S->s, G->g, sp, none, S->d.mat, S->cl, c->stream, c->gtune);
@@ -1023,7 +1038,9 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
   StepParams sp = step_params(c);
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
-    if (grid_normalize_if_needed(c, G)) return 1;
+    const bool cell_stress = !c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function);
+    const bool bulk = cell_stress && c->stress_bulk && c->pending_grad == 1 && !sp.axisymmetric && !sp.temp; // the MUSL gradient reads nv: the normalisation pass also writes its padded copy
+    if (grid_normalize_if_needed(c, G, bulk)) return 1;
     if (S->rigid) continue; // src/solid.cpp:799,862,1157,1248: the gradient, F and stress updates return at once for a rigid material
     sp.inv_tav = S->d.mat.signal_velocity / (1000 * G->d.cellsize);
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
@@ -1034,7 +1051,11 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
       const int k = S->ev_s_next; S->ev_s_next ^= 1; // timed every step for the permute policy (kml_compute_grid_weight_...)
       if (!S->ev_s[k][0]) { CU(cudaEventCreate(&S->ev_s[k][0])); CU(cudaEventCreate(&S->ev_s[k][1])); }
       CU(cudaEventRecord(S->ev_s[k][0], c->stream));
-      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, S->cl, c->stream, c->gtune);
+      if (bulk && !G->nvs_valid) { // nv was normalised by an earlier call: copy it
+        if (!G->nvs) { const size_t nb = sizeof(double) * nvd_doubles(G->g) / 6 * 4; CU(cudaMalloc(&G->nvs, nb)); CU(cudaMemsetAsync(G->nvs, 0, nb, c->stream)); }
+        k_grid_pack_v<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, G->g.nv, G->nvs); G->nvs_valid = true; c->launches[KML_STAGE_STRESS]++;
+      }
+      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, S->cl, c->stream, c->gtune, bulk ? G->nvs : nullptr);
       if (rc > 0) return fail("cell stress launch failed");
       if (rc == 0) { CU(cudaEventRecord(S->ev_s[k][1], c->stream)); S->ev_s_valid[k] = true; S->ev_s_step[k] = c->steps_started; }
     }
@@ -1050,7 +1071,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
 }
 
 // bit b of the device error word -> slot b of a double array (1.0 / 0.0): a max all-reduce of the slots is the union of the words
-__global__ void k_flag_bits(const unsigned *flags, double *bits) { if (threadIdx.x < 8) bits[threadIdx.x] = ((*flags >> threadIdx.x) & 1u) ? 1.0 : 0.0; }
+__global__ void k_flag_bits(const unsigned *flags, double *bits, double want_permute) { if (threadIdx.x < 8) bits[threadIdx.x] = ((*flags >> threadIdx.x) & 1u) ? 1.0 : 0.0; if (threadIdx.x == 8) bits[8] = want_permute; }
 __global__ void k_bits_flag(const double *bits, unsigned *flags) { unsigned f = 0; for (int b = 0; b < 8; b++) if (bits[b] != 0.0) f |= 1u << b; *flags = f; }
 
 // The dt of the next step is needed first by the grid update of the next step, a re-bin and a scatter later.  adjust_dt therefore only
@@ -1062,6 +1083,7 @@ static int resolve_dt(kml_ctx *c) {
   CU(cudaEventSynchronize(c->ev_dt));
   const int ns = (int)c->solids.size();
   unsigned flags = 0; for (int b = 0; b < 8; b++) if (c->h_red[KML_RED_BITS + b] != 0.0) flags |= 1u << b;
+  if (c->comm.nranks > 1 && c->h_red[KML_RED_BITS + 8] != 0.0) c->permute_go = true; // some rank asked: every rank re-orders at its next re-bin
   if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow, 32: particle migration bookkeeping)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
@@ -1082,16 +1104,17 @@ int kml_adjust_dt(kml_ctx *c, double dt_factor, double *dt_out) {
     StageTimer t(c, KML_STAGE_DT);
     const int ns = (int)c->solids.size();
     if (2 * ns > KML_RED_BITS) return fail("too many solids");
-    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, c->d_red + KML_RED_BITS);
+    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, c->d_red + KML_RED_BITS, c->permute_want ? 1.0 : 0.0);
+    c->permute_want = false;
     if (c->comm.nranks > 1) { // MPI_Allreduce(MIN) of dtCFL in the reference (src/ulmpm.cpp:547) == max of the wave speeds here; ONE collective for all solids + the error word
-      NC(nccl().AllReduce(c->d_red, c->d_red, KML_RED_BITS + 8, ncclDouble, ncclMax, c->comm.comm, c->stream));
+      NC(nccl().AllReduce(c->d_red, c->d_red, KML_RED_N, ncclDouble, ncclMax, c->comm.comm, c->stream));
       k_bits_flag<<<1, 1, 0, c->stream>>>(c->d_red + KML_RED_BITS, c->d_flags);
     }
-    CU(cudaMemcpyAsync(c->h_red, c->d_red, (KML_RED_BITS + 8) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_red, c->d_red, KML_RED_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev_dt, c->stream));
     c->launches[KML_STAGE_DT] += 1;
   }
-  c->dt_pending = true; c->dt_factor = dt_factor;
+  c->dt_pending = true; c->dt_factor = dt_factor; c->dt_collective = true;
   if (dt_out) { if (resolve_dt(c)) return 1; *dt_out = c->dt; }
   return 0;
 }
@@ -1177,7 +1200,7 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
   if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
   for (Grid *G : gs) {
     if (grid_normalize_if_needed(c, G)) return 1;
-    G->nvd_valid = false;
+    G->nvd_valid = false; G->nvs_valid = false;
     k_fix_velocity_nodes<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, v[0], v[1], v[2], vprev ? vprev[0] : 0, vprev ? vprev[1] : 0,
                                                                         vprev ? vprev[2] : 0, which, 1.0 / c->dt, c->d_scratch);
     c->launches[KML_STAGE_GRID]++;
@@ -1248,7 +1271,8 @@ int kml_fix_body_force(kml_ctx *c, int solid, int groupbit, int set_mask, const 
 
 int kml_fix_force_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const double f[3], double ftot[3]) {
   CU(cudaSetDevice(c->dev));
-  if (c->comm.nranks > 1) return fail("kml: fix force_nodes is single-GPU in the CUDA engine (the node count of the group is not reduced across slabs)");
+  // Decomposed runs divide by the GLOBAL node count of the group, i.e. they reproduce the undecomposed run.  (The reference divides by each
+  // rank's local + ghost count without reducing it, src/fix_force_nodes.cpp:128-150, so its total depends on the MPI decomposition.)
   StageTimer t(c, KML_STAGE_GRID);
   CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
   std::vector<Grid *> gs;
@@ -1257,6 +1281,7 @@ int kml_fix_force_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, const
   for (Grid *G : gs) {
     CU(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
     k_fix_force_count<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, cnt);
+    if (c->comm.nranks > 1) NC(nccl().AllReduce(cnt, cnt, 1, ncclInt, ncclSum, c->comm.comm, c->stream));
     k_fix_force_apply<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, f[0], f[1], f[2], cnt, c->d_scratch);
     c->launches[KML_STAGE_GRID] += 2;
   }
@@ -1311,7 +1336,7 @@ int kml_error_flags(kml_ctx *c, unsigned *flags) { // collective on a decomposed
   CU(cudaSetDevice(c->dev));
   if (c->comm.nranks > 1) {
     double *bits = c->d_scratch + 40;
-    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, bits);
+    k_flag_bits<<<1, 32, 0, c->stream>>>(c->d_flags, bits, 0.0); // d_scratch has 64 doubles: bits[8] is inside it
     NC(nccl().AllReduce(bits, bits, 8, ncclDouble, ncclMax, c->comm.comm, c->stream));
     k_bits_flag<<<1, 1, 0, c->stream>>>(bits, c->d_flags);
   }

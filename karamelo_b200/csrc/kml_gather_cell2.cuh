@@ -16,8 +16,40 @@
 // Arithmetic: src/solid.cpp:576-635,786-796 (G2P + advance), :860-936 (gradient), :1155-1438 (F, stress).
 #pragma once
 #include "kml_p2g_cell3.cuh"
+#include <cstdint>
 
 namespace kml {
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KML_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KML_MBAR_DONE;\n"
+      "bra KML_MBAR_WAIT;\n"
+      "KML_MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (1-D TMA); bytes a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Packed gather records.  nvd is indexed on a PADDED grid (n1 + 3) x (n2 + NVD_PADK) with zero planes behind every axis, so a tile row
+// (i, j, kbeg .. kbeg + seglen + 2) is always one in-bounds contiguous range, zero where no node exists.
+constexpr int NVD_PADK = KML_NVD_PADK; // the longest segment (96 cells) + the stencil span + slack
+static_assert(NVD_PADK >= 96 + 3, "tile rows of the longest segment must stay inside the padded grid");
+__host__ __device__ __forceinline__ long long nvd_index(const GridDev &g, int i, int j, int k) { return ((long long)i * (g.n[1] + 3) + j) * (g.n[2] + NVD_PADK) + k; }
+inline size_t nvd_doubles(const GridDev &g) { return (size_t)(g.n[0] + 3) * (g.n[1] + 3) * (g.n[2] + NVD_PADK) * 6; }
+
 
 // ---- G2P + advance ------------------------------------------------------------------------------------------------
 template <int THREADS, int MINB>
@@ -98,11 +130,14 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
 // private shared-memory slot (8-byte cp.async) while it runs the constitutive update of the current one.  The register file only holds
 // the weights, the gather accumulators and the constitutive update, so the kernel fits 168 registers (3 x 128 or
 // 6 x 64 threads per SM); prefetching the state into registers instead costs 60 more and halves the occupancy.
-template <int THREADS, int MINB>
+// BULK: the tile arrives as 16 bulk copies (TMA, SASS UBLKCP) of rows of the padded copy `nvs` of the node records (written by the
+// normalisation pass of k_grid_update) onto an mbarrier, requested by one thread - no per-thread address arithmetic, bounds tests or
+// cp.async instructions for the 16 x (seglen + 3) records (~8 % of the kernel's instructions at 24 cells per segment).
+template <int THREADS, int MINB, bool BULK>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
-               int seglen, int nseg) {
-  extern __shared__ __align__(16) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state
+               int seglen, int nseg, const double *__restrict__ nvs) {
+  extern __shared__ __align__(128) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state, then (BULK) the mbarrier
   const int TLEN = seglen + 3;
   double *tile = smem3;
   double *state = smem3 + (size_t)16 * TLEN * 4;
@@ -117,9 +152,19 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
   int p = pbeg + tid;
   int ip = p < pend ? order[p] : -1;
   int ipn = p + THREADS < pend ? order[p + THREADS] : -1;
+  const unsigned bar = smem_addr(state + (size_t)PSTATE_SLOTS * THREADS);
+  if (BULK) {
+    if (tid == 0) {
+      const unsigned row_bytes = (unsigned)TLEN * 32u;
+      mbar_init(bar, 1); mbar_fence_init();
+      mbar_arrive_expect_tx(bar, 16u * row_bytes);
+#pragma unroll 1
+      for (int r = 0; r < 16; r++) bulk_g2s(smem_addr(tile) + (unsigned)r * row_bytes, nvs + nvd_index(g, i0 + (r >> 2), j0 + (r & 3), kbeg) * 4, row_bytes, bar);
+    }
+  }
   // node tile: 16 rows, contiguous along k in global memory
   const double4 *__restrict__ src0 = tp.doublemapping ? g.nv : g.nvu;
-  for (int e = tid; e < 16 * TLEN; e += THREADS) {
+  if (!BULK) for (int e = tid; e < 16 * TLEN; e += THREADS) {
     const int row = e / TLEN, t = e - row * TLEN;
     const int ni = i0 + (row >> 2), nj = j0 + (row & 3), nk = kbeg + t;
     double *d = tile + (size_t)e * 4;
@@ -133,6 +178,7 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
+  if (BULK) mbar_wait(bar, 0); // (the barrier above made the initialised mbarrier visible)
 
   const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
   const double h = g.h, ih = g.inv_cellsize;
@@ -196,7 +242,7 @@ struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads 
 
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
 inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
-                              const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
+                              const CellLists &cl, cudaStream_t st, const GatherTune &tune, const double *nvs = nullptr) { // nvs: padded node records -> bulk-copied stress tile
   if (sp.axisymmetric || sp.temp || !cl.valid) return -1;
   // G2P: segments of (almost) equal length.  Stress: segments of EXACTLY seg_stress cells (the last one shorter) - measured at 100 M
   // particles: 24 cells 10.6 ms, 15 cells 11.0, 20 cells 12.0, 30 cells (the equalised split of 210 planes) 12.4, 12 cells 13.4; a short
@@ -207,7 +253,7 @@ inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, 
   const long long nblocks = (long long)g.n[0] * g.n[1] * nseg;
   if (nblocks >= (1ll << 31)) return -1;
   const size_t tile = sizeof(double) * 16 * (size_t)(seglen + 3) * (stress ? 4 : 6);
-  const size_t smem = tile + (stress ? sizeof(double) * PSTATE_SLOTS * (size_t)tune.threads : 0);
+  const size_t smem = tile + (stress ? sizeof(double) * PSTATE_SLOTS * (size_t)tune.threads + 16 : 0);
 #define KML_GATHER_LAUNCH(KERN, THREADS, ...)                                                                                       \
   do {                                                                                                                             \
     auto kern = KERN;                                                                                                              \
@@ -215,8 +261,13 @@ inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, 
     kern<<<(unsigned)nblocks, THREADS, smem, st>>>(__VA_ARGS__);                                                                   \
   } while (0)
   if (stress) {
-    if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
-    else KML_GATHER_LAUNCH((k_stress_cell<128, 3>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
+    if (nvs) {
+      if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6, true>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
+      else KML_GATHER_LAUNCH((k_stress_cell<128, 3, true>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
+    } else {
+      if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6, false>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
+      else KML_GATHER_LAUNCH((k_stress_cell<128, 3, false>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
+    }
   } else {
     if (tune.g2p_threads == 64) KML_GATHER_LAUNCH((k_g2p_cell<64, 8>), 64, s, g, sp, cl.start, cl.order, seglen, nseg);
     else KML_GATHER_LAUNCH((k_g2p_cell<128, 4>), 128, s, g, sp, cl.start, cl.order, seglen, nseg);

@@ -19,37 +19,16 @@
 
 namespace kml {
 
-// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) ------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "KML_MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra KML_MBAR_DONE;\n"
-      "bra KML_MBAR_WAIT;\n"
-      "KML_MBAR_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (1-D TMA); bytes a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// Packed gather records.  nvd is indexed on a PADDED grid (n1 + 3) x (n2 + NVD_PADK) with zero planes behind every axis, so a tile row
-// (i, j, kbeg .. kbeg + seglen + 2) is always one in-bounds contiguous range, zero where no node exists.
-constexpr int NVD_PADK = KML_NVD_PADK; // the longest segment (96 cells) + the stencil span + slack
-static_assert(NVD_PADK >= 96 + 3, "tile rows of the longest segment must stay inside the padded grid");
-__host__ __device__ __forceinline__ long long nvd_index(const GridDev &g, int i, int j, int k) { return ((long long)i * (g.n[1] + 3) + j) * (g.n[2] + NVD_PADK) + k; }
-inline size_t nvd_doubles(const GridDev &g) { return (size_t)(g.n[0] + 3) * (g.n[1] + 3) * (g.n[2] + NVD_PADK) * 6; }
-
 #ifdef KML_MISC_KERNELS
+// fallback copy of the node records {v, mass} onto the padded grid of the bulk-copied stress tile (normally written by k_grid_update)
+__global__ void k_grid_pack_v(GridDev g, const double4 *__restrict__ src, double *nvs) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= g.nn) return;
+  const int k = (int)(n % g.n[2]); const long long t = n / g.n[2]; const int j = (int)(t % g.n[1]), i = (int)(t / g.n[1]);
+  const double4 v = src[n];
+  double *d = nvs + nvd_index(g, i, j, k) * 4;
+  *(double2 *)d = make_double2(v.x, v.y); *(double2 *)(d + 2) = make_double2(v.z, v.w);
+}
 __global__ void k_grid_pack_g2p(GridDev g, double *nvd) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= g.nn) return;
@@ -168,6 +147,92 @@ k_g2p_cell_tma(SolidDev s, GridDev g, StepParams sp, const double *__restrict__ 
     if ((tid & 31) == 0) mbar_arrive(bars + 16 + 8u * b);
     m++;
   }
+}
+
+// One block per column segment like k_g2p_cell, but the tile arrives as 16 bulk copies (TMA, SASS UBLKCP) of the packed records onto one
+// mbarrier.  k_g2p_cell fills its tile through registers in a loop ptxas unrolls by two (4 LDG -> 3 STS per pair of records): 9 records
+// per thread are 4-5 serialised L2 round trips before the block's barrier, and ncu's samples put ~40 % of that kernel's warp time in the
+// prologue.  Here the fill is one latency, in parallel with the start[] -> order[] -> x chain of the first particle; no second buffer, so
+// the occupancy (8 blocks of 64 threads) is that of k_g2p_cell.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_g2p_cell_bulk(SolidDev s, GridDev g, StepParams sp, const double *__restrict__ nvd, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
+  extern __shared__ __align__(128) unsigned char smem_g4[]; // [16][TLEN] records of 48 B, then the mbarrier
+  const int TLEN = seglen + 3;
+  const unsigned row_bytes = (unsigned)TLEN * 48u, tile_bytes = 16u * row_bytes;
+  const unsigned smem0 = smem_addr(smem_g4), bar = smem0 + tile_bytes;
+  const int tid = threadIdx.x;
+  const long long col = blockIdx.x / nseg; const int seg = (int)(blockIdx.x % nseg);
+  const int i0 = (int)(col / g.n[1]), j0 = (int)(col % g.n[1]);
+  const int kbeg = seg * seglen, kend = min(kbeg + seglen, g.n[2]);
+  const long long cellbase = col * g.n[2];
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  const int pbeg = start[cellbase + kbeg], pend = start[cellbase + kend];
+  if (pbeg == pend) return; // block-uniform
+  if (tid == 0) { // the tile does not depend on the particles: request it before anything else waits
+    mbar_arrive_expect_tx(bar, tile_bytes);
+#pragma unroll 1
+    for (int r = 0; r < 16; r++) bulk_g2s(smem0 + (unsigned)r * row_bytes, nvd + nvd_index(g, i0 + (r >> 2), j0 + (r & 3), kbeg) * 6, row_bytes, bar);
+  }
+  int p = pbeg + tid;
+  int ip = p < pend ? order[p] : -1;
+  int ipn = p + THREADS < pend ? order[p + THREADS] : -1;
+  double px = 0, py = 0, pz = 0;
+  if (ip >= 0) { px = s.x[0][ip]; py = s.x[1][ip]; pz = s.x[2][ip]; }
+  __syncthreads(); // the barrier object is initialised for every thread that is about to wait on it
+  mbar_wait(bar, 0);
+
+  const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
+  const double h = g.h, ih = g.inv_cellsize;
+  unsigned tile_s = smem0;
+  asm volatile("" : "+r"(tile_s));
+  while (ip >= 0) {
+    const int pn = p + THREADS;
+    const int ipnn = pn + THREADS < pend ? order[pn + THREADS] : -1;
+    double nx = 0, ny = 0, nz = 0;
+    if (ipn >= 0) { nx = s.x[0][ipn]; ny = s.x[1][ipn]; nz = s.x[2][ipn]; }
+    double vold[3];
+    vold[0] = s.v[0][ip]; vold[1] = s.v[1][ip]; vold[2] = s.v[2][ip];
+    const int k0 = cell_axis(pz, g.lo[2], ih, g.n[2], 0);
+    const int koff = k0 - kbeg;
+    double wx[4], wy[4], wz[4], dw_[4];
+    cubic_axis4(px, g.lo[0], h, ih, i0, g.n[0], g.goff0, g.gn0, int_x, wx, dw_);
+    cubic_axis4(py, g.lo[1], h, ih, j0, g.n[1], 0, g.n[1], int_y, wy, dw_);
+    cubic_axis4(pz, g.lo[2], h, ih, k0, g.n[2], 0, g.n[2], cubic_interior(k0, g.n[2], 0, g.n[2]), wz, dw_);
+    double vu[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int bb = 0; bb < 4; bb++) {
+        const double gxy = wx[a] * wy[bb];
+        const unsigned row = tile_s + (unsigned)(((a * 4 + bb) * TLEN + koff) * 48);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const double2 r01 = lds_d2(row + 48 * c), r23 = lds_d2(row + 48 * c + 16), r45 = lds_d2(row + 48 * c + 32);
+          const double wf = gxy * wz[c];
+          vu[0] = fma(wf, r01.x, vu[0]); vu[1] = fma(wf, r01.y, vu[1]); vu[2] = fma(wf, r23.x, vu[2]);
+          acc[0] = fma(wf, r23.y, acc[0]); acc[1] = fma(wf, r45.x, acc[1]); acc[2] = fma(wf, r45.y, acc[2]);
+        }
+      }
+    particle_advance<false, false>(s, sp, ip, vu, acc, 0.0, vold);
+    p = pn; ip = ipn; ipn = ipnn; px = nx; py = ny; pz = nz;
+  }
+}
+
+inline int cell_g2p_bulk_launch(const SolidDev &s, const GridDev &g, const StepParams &sp, const double *nvd, const CellLists &cl, cudaStream_t st, int seg_target, int threads) {
+  int seglen, nseg; cell_segments(g.n[2], seg_target, &seglen, &nseg);
+  const long long nblocks = (long long)g.n[0] * g.n[1] * nseg;
+  if (nblocks >= (1ll << 31)) return 1;
+  const size_t smem = (size_t)16 * (seglen + 3) * 48 + 16;
+#define KML_G4_LAUNCH(T, B)                                                                                                              \
+  do {                                                                                                                                   \
+    auto kern = k_g2p_cell_bulk<T, B>;                                                                                                   \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+    kern<<<(unsigned)nblocks, T, smem, st>>>(s, g, sp, nvd, cl.start, cl.order, seglen, nseg);                                           \
+  } while (0)
+  if (threads == 64) KML_G4_LAUNCH(64, 8); else KML_G4_LAUNCH(128, 4);
+#undef KML_G4_LAUNCH
+  return cudaGetLastError() != cudaSuccess;
 }
 
 // returns 0 = launched, 1 = CUDA error

@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
 // normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
 // Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
 // nvd (optional): packed gather records {v_update, v_update - v} on the zero-padded grid of kml_gather_cell3.cuh, written in the same pass
-__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware, double *nvd) {
+// nvs (optional): copy of the (normalised) node record {v, mass} on the same padded grid, 32 B per node: the bulk-copied tile of the stress kernel
+__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware, double *nvd, double *nvs) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
   double4 rec = g.nv[i];
@@ -199,6 +200,11 @@ __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, i
     for (int d = 0; d < 3; d++) v[d] = (m > 0) ? v[d] / m : 0.0;
     rec.x = v[0]; rec.y = v[1]; rec.z = v[2];
     g.nv[i] = rec;
+  }
+  if (nvs) {
+    const int k = (int)(i % g.n[2]); const long long t = i / g.n[2]; const int j = (int)(t % g.n[1]), ii = (int)(t / g.n[1]);
+    double *d = nvs + (((long long)ii * (g.n[1] + 3) + j) * (g.n[2] + KML_NVD_PADK) + k) * 4;
+    *(double2 *)d = make_double2(rec.x, rec.y); *(double2 *)(d + 2) = make_double2(rec.z, rec.w);
   }
   double T = 0;
   if (temp) { T = g.T[i]; if (normalize_T) { T = (m > 0) ? T / m : 0.0; g.T[i] = T; } }
@@ -661,7 +667,9 @@ __global__ void k_fix_body_force(GridDev g, int groupbit, int set_mask, double f
 // FixForceNodes, src/fix_force_nodes.cpp:96-193: count the massive nodes of the group, then share the force among them
 __global__ void k_fix_force_count(GridDev g, int groupbit, int *count) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = i < g.nn && g.nv[i].w > 0 && (g.mask[i] & groupbit);
+  // a decomposed grid counts every node once: on the rank that owns its plane (the counts are then summed over the ranks)
+  const int plane = (int)(min(i, g.nn - 1) / ((long long)g.n[1] * g.n[2]));
+  const bool in = i < g.nn && plane >= g.own_lo && plane < g.own_hi && g.nv[i].w > 0 && (g.mask[i] & groupbit);
   const unsigned b = __ballot_sync(0xffffffffu, in);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
 }

@@ -81,6 +81,9 @@ def step(args):
         m = 4
         script += ("region(rlow, block, INF, INF, INF, %g, INF, INF)\ngroup(gn, nodes, region, rlow, solid, blk)\n"
                    "fix(bc, velocity_nodes, gn, NULL, 0, NULL)\n" % (m + 1.5))
+    elif args.variant == "force_nodes":  # a total force spread over the nodes of a group that spans the slab cuts: the node count is a global sum
+        script += ("region(rmid, block, INF, INF, %g, INF, INF, INF)\ngroup(gf, nodes, region, rmid, solid, blk)\n"
+                   "fix(ff, force_nodes, gf, 0.004, NULL, -0.002)\n" % 6.5)
     elif args.variant == "thermal":  # thermo-mechanical: temperature and heat-source node fields join the halo sums
         script = script.replace("method(ulmpm, FLIP, %s, 0.99)" % args.shape, "method(ulmpm, FLIP, %s, 0.99, thermo-mechanical)" % args.shape)
         script = script.replace("material(m, eos-strength, e, s)", "temperature(tpw, plastic_work, 0.9, 50, 2, 0, 0, 500)\nmaterial(m, eos-strength, e, s, tpw)")
@@ -133,7 +136,7 @@ if __name__ == "__main__":
     ap.add_argument("--drift", type=float, default=0.0)
     ap.add_argument("--method", default="", help="arguments of method(ulmpm, ...) replacing the block's FLIP cubic-spline default")
     ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
-    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal"])
+    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal", "force_nodes"])
     a = ap.parse_args()
     try:
         {"partition": partition, "step": step}[a.mode](a)

@@ -70,6 +70,51 @@ template <int ILP, int NI, int NL> void run_mixed(int nsm, int threads, int bloc
   cudaFree(out); cudaFree(clk);
 }
 
+// Three REGISTER operands per DFMA, as in the kernels' accumulate loops (acc[i] += b[j] * c[k], 28 accumulators, 4 + 4 multiplicands): the
+// chains above feed two of the three operands from a uniform register and a reuse cache, which costs the register file one read per DFMA
+// instead of three.  NL: LDS.128 per 28 DFMAs whose results replace the multiplicands (as the record loads of P2G do).
+template <int NL>
+__global__ void k_dfma3(double *out, const double *in, int iters, long long *clocks) {
+  __shared__ __align__(16) double sh[512];
+  sh[threadIdx.x & 511] = in[threadIdx.x & 63]; sh[(threadIdx.x + 256) & 511] = in[(threadIdx.x + 7) & 63];
+  __syncthreads();
+  double a[28], b[4], c[4];
+#pragma unroll
+  for (int i = 0; i < 28; i++) a[i] = i + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { b[i] = in[i] + 1e-9 * threadIdx.x; c[i] = in[4 + i]; }
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sh) + 16u * (threadIdx.x & 7);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) a[i] = fma(b[i & 3], c[(i >> 2) & 3], a[i]);
+#pragma unroll
+    for (int j = 0; j < NL; j++) { // the loaded values become multiplicands of the next iteration
+      double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 128u * j));
+      if (j & 1) { c[(j >> 1) & 3] = v.x; b[(j >> 1) & 3] = v.y; } else { b[(j >> 1) & 3] = v.x; c[(j >> 1) & 3] = v.y; }
+    }
+  }
+  long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 28; i++) s += a[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+}
+template <int NL> void run_dfma3(int nsm, int threads, int blocks_per_sm, int iters) {
+  const int nb = nsm * blocks_per_sm;
+  double *out, *in; long long *clk; cudaMalloc(&out, sizeof(double) * nb * threads); cudaMalloc(&clk, sizeof(long long) * nb); cudaMalloc(&in, 64 * sizeof(double));
+  double h[64]; for (int i = 0; i < 64; i++) h[i] = 1.0 + 1e-7 * i; cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma3<NL><<<nb, threads>>>(out, in, iters / 8, clk); cudaDeviceSynchronize();
+  cudaEventRecord(e0); k_dfma3<NL><<<nb, threads>>>(out, in, iters, clk); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  const double dfma = (double)nb * threads * 28 * iters;
+  printf("3 register operands per DFMA, 28 accumulators, %d LDS.128 per 28 DFMA, %d warps/sub-partition: %.2f T DFMA/s (%.3f ms)\n", NL, threads * blocks_per_sm / 128,
+         dfma / (ms * 1e-3) * 1e-12, ms);
+  cudaFree(out); cudaFree(clk); cudaFree(in);
+}
+
 template <int ILP> void run(int nsm, int threads, int blocks_per_sm, int iters) {
   const int nb = nsm * blocks_per_sm;
   double *out; long long *clk; cudaMalloc(&out, sizeof(double) * nb * threads); cudaMalloc(&clk, sizeof(long long) * nb);
@@ -101,5 +146,10 @@ int main() {
   run_mixed<8, 0, 2>(nsm, 128, 3, iters);
   run_mixed<8, 1, 2>(nsm, 128, 3, iters);
   run_mixed<8, 1, 0>(nsm, 128, 4, iters);
+  run_dfma3<0>(nsm, 128, 1, iters / 4);
+  run_dfma3<0>(nsm, 128, 3, iters / 4);
+  run_dfma3<4>(nsm, 128, 3, iters / 4);
+  run_dfma3<8>(nsm, 128, 3, iters / 4);
+  run_dfma3<8>(nsm, 128, 4, iters / 4);
   return 0;
 }

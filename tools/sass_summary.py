@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "karamelo_b200", "lib", "libkml.so")
-WANT = ["k_p2g_cell3", "k_g2p_cell", "k_stress_cell", "k_g2p_cell_tma", "k_cell_count", "k_cell_fill", "k_permute", "k_grid_update", "k_lattice_fill", "k_set_particles_expr"]
+WANT = ["k_p2g_cell3", "k_g2p_cell", "k_stress_cell", "k_g2p_cell_tma", "k_g2p_cell_bulk", "k_cell_count", "k_cell_fill", "k_permute", "k_grid_update", "k_lattice_fill", "k_set_particles_expr"]
 KEY = ["UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "REDG", "ATOMG", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "BAR", "MUFU", "HMMA", "UTC"]
 
 
