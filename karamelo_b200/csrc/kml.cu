@@ -31,7 +31,6 @@ struct Grid {
   // packed gather records {v_update, v_update - v} on a zero-padded grid for the TMA-fed G2P kernel (kml_gather_cell3.cuh); valid = they
   // reflect the current nv / nvu (written by k_grid_update, invalidated by everything else that touches node velocities)
   double *nvd = nullptr; bool nvd_valid = false;
-  double *nvs = nullptr; bool nvs_valid = false; // padded copy of the node records {v, mass} for the bulk-copied stress tile; valid = it holds the current nv
 };
 struct Solid {
   kml_solid_desc d; SolidDev s; double *buf = nullptr; long long *lbuf = nullptr; int *ibuf = nullptr; long long cap = 0;
@@ -70,8 +69,8 @@ struct kml_ctx {
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
   bool permute_want = false, permute_go = false, dt_collective = false; // decomposed runs: a rank's wish travels with the dt all-reduce and all ranks re-order in the same step (no rank waits for another's permute)
   double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
-  int g2p_tma = 4, stress_bulk = 1; int nsm = 148; // KML_G2P_TMA: 0 = tile through registers, 1 / 3 = persistent TMA-fed kernel, 4 = one block per segment with a bulk-copied tile (default); KML_STRESS_BULK
-  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2, p2g_pipe = 1; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
+  int g2p_tma = 4; int nsm = 148; // KML_G2P_TMA: 0 = tile through registers, 1 / 3 = persistent TMA-fed kernel, 4 = one block per segment with a bulk-copied tile (default)
+  bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
   Comm comm;
   // profiling
   // Per-stage device time: event pairs are recorded around every stage and only READ in kml_stage_times (one synchronisation for the
@@ -204,12 +203,11 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   if (e && !strcmp(e, "atomic")) c->use_cell_p2g = false;
   auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; };
   c->p2g_nb = env_int("KML_P2G_NB", 1) == 2 ? 2 : 1;
-  c->p2g_pipe = env_int("KML_P2G_PIPE", 1);
   c->cell_mask = env_int("KML_CELL_MASK", 7);
   { const char *v = getenv("KML_PERMUTE_FRAC"); if (v && *v) c->permute_frac = atof(v); }
   c->permute_min_steps = env_int("KML_PERMUTE_MIN_STEPS", 2);
   c->permute_every = env_int("KML_PERMUTE_EVERY", 0);
-  c->g2p_tma = env_int("KML_G2P_TMA", 4); c->stress_bulk = env_int("KML_STRESS_BULK", 1);
+  c->g2p_tma = env_int("KML_G2P_TMA", 4);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, c->dev) == cudaSuccess) c->nsm = pr.multiProcessorCount; }
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
@@ -225,7 +223,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
 int kml_destroy(kml_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
-  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); cudaFree(g->nvs); delete g; }
+  for (auto g : c->grids) { cudaFree(g->buf); cudaFree(g->ibuf); cudaFree(g->nvd); delete g; }
   for (auto s : c->solids) { cudaFree(s->cpbuf); cudaFree(s->cpibuf); cudaFree(s->buf); cudaFree(s->lbuf); cudaFree(s->ibuf); cudaFree(s->accbuf); cudaFree(s->buf2); cudaFree(s->lbuf2); cudaFree(s->ibuf2); s->cl.release();
     for (int a = 0; a < 2; a++) { for (int b = 0; b < 2; b++) if (s->ev_s[a][b]) cudaEventDestroy(s->ev_s[a][b]); if (s->ev_p[a]) cudaEventDestroy(s->ev_p[a]); }
     delete s; }
@@ -280,15 +278,9 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
 }
 int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.nn; return 0; }
 
-static int grid_normalize_if_needed(kml_ctx *c, Grid *G, bool want_nvs = false) {
+static int grid_normalize_if_needed(kml_ctx *c, Grid *G) {
   if (!G->v_is_momentum && !G->T_is_weighted) return 0;
-  double *nvs = nullptr;
-  if (want_nvs) {
-    if (!G->nvs) { const size_t nb = sizeof(double) * nvd_doubles(G->g) / 6 * 4; CU(cudaMalloc(&G->nvs, nb)); CU(cudaMemsetAsync(G->nvs, 0, nb, c->stream)); }
-    nvs = G->nvs;
-  }
-  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, 0.0 /* dt is not used without the update */, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr, nvs);
-  G->nvs_valid = nvs != nullptr;
+  k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, 0.0 /* dt is not used without the update */, G->v_is_momentum, 0, c->c.temp, G->T_is_weighted, 0, nullptr);
   G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = false; c->launches[KML_STAGE_GRID]++;
   return check_launch("k_grid_update(normalize)");
 }
@@ -321,7 +313,7 @@ int kml_grid_upload(kml_ctx *c, int gid, int field, const void *src) {
   if (ic) { CU(cudaMemcpyAsync(ic, src, sizeof(int) * nn, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream)); return 0; }
   if (field == KML_N_V) G->v_is_momentum = false;
   if (field == KML_N_T) G->T_is_weighted = false;
-  G->nvd_valid = false; G->nvs_valid = false;
+  G->nvd_valid = false;
   const double *s = (const double *)src;
   for (int k = 0; k < nc; k++) { // strided 2-D copy: host column k of [nn][nc] -> device component
     CU(cudaMemcpy2DAsync(comp[k], sizeof(double) * stride, s + k, sizeof(double) * nc, sizeof(double), nn, cudaMemcpyHostToDevice, c->stream));
@@ -904,7 +896,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (!TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 1) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function) && !sp.axisymmetric &&
         !(what & (P2G_TEMP | P2G_HEAT))) {
       int nl = 0;
-      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl, c->p2g_pipe != 0); // -1: combination not covered -> atomic kernel
+      const int rc = cell_p2g3_launch(S->s, g, S->cl, what, c->p2g_nb, c->v2g_nb, c->gtune.seg_target, c->stream, &nl); // -1: combination not covered -> atomic kernel
       if (rc > 0) return fail("cell p2g launch failed");
       if (rc == 0) { c->launches[stage] += nl; done = true; }
     }
@@ -920,7 +912,7 @@ static int p2g_launch(kml_ctx *c, int what_in, int stage) {
     if (check_launch("k_p2g")) return 1;
     if (what & P2G_MOM) G->v_is_momentum = true;
     if (what & P2G_TEMP) G->T_is_weighted = true;
-    G->nvd_valid = false; G->nvs_valid = false;
+    G->nvd_valid = false;
   }
   if (TL && (what_in & P2G_MASS)) c->tl_mass_done = true;
   t.stop();
@@ -952,8 +944,8 @@ int kml_update_grid_state(kml_ctx *c) {
       if (!G->nvd) { const size_t nb = sizeof(double) * nvd_doubles(G->g); CU(cudaMalloc(&G->nvd, nb)); CU(cudaMemsetAsync(G->nvd, 0, nb, c->stream)); }
       nvd = G->nvd;
     }
-    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid, nvd, nullptr);
-    G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = nvd != nullptr; G->nvs_valid = false; c->launches[KML_STAGE_GRID]++;
+    k_grid_update<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, c->dt, G->v_is_momentum, 1, c->c.temp, G->T_is_weighted, c->has_rigid, nvd);
+    G->v_is_momentum = false; G->T_is_weighted = false; G->nvd_valid = nvd != nullptr; c->launches[KML_STAGE_GRID]++;
     if (check_launch("k_grid_update")) return 1;
   }
   return 0;
@@ -1038,9 +1030,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
   StepParams sp = step_params(c);
   for (Solid *S : c->solids) {
     Grid *G = c->grids[S->d.grid];
-    const bool cell_stress = !c->c.is_TL && !c->apic && !c->c.ge && !c->has_rigid && c->use_cell_p2g && (c->cell_mask & 4) && S->cl.valid && cell_p2g_supported(c->c.dimension, c->c.shape_function);
-    const bool bulk = cell_stress && c->stress_bulk && c->pending_grad == 1 && !sp.axisymmetric && !sp.temp; // the MUSL gradient reads nv: the normalisation pass also writes its padded copy
-    if (grid_normalize_if_needed(c, G, bulk)) return 1;
+    if (grid_normalize_if_needed(c, G)) return 1;
     if (S->rigid) continue; // src/solid.cpp:799,862,1157,1248: the gradient, F and stress updates return at once for a rigid material
     sp.inv_tav = S->d.mat.signal_velocity / (1000 * G->d.cellsize);
     StressParams tp; tp.doublemapping = c->pending_grad; tp.moved = c->grad_moved; tp.max_wave = S->red; tp.min_h_ratio = S->red + 1;
@@ -1051,11 +1041,7 @@ int kml_update_stress(kml_ctx *c, int doublemapping) {
       const int k = S->ev_s_next; S->ev_s_next ^= 1; // timed every step for the permute policy (kml_compute_grid_weight_...)
       if (!S->ev_s[k][0]) { CU(cudaEventCreate(&S->ev_s[k][0])); CU(cudaEventCreate(&S->ev_s[k][1])); }
       CU(cudaEventRecord(S->ev_s[k][0], c->stream));
-      if (bulk && !G->nvs_valid) { // nv was normalised by an earlier call: copy it
-        if (!G->nvs) { const size_t nb = sizeof(double) * nvd_doubles(G->g) / 6 * 4; CU(cudaMalloc(&G->nvs, nb)); CU(cudaMemsetAsync(G->nvs, 0, nb, c->stream)); }
-        k_grid_pack_v<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, G->g.nv, G->nvs); G->nvs_valid = true; c->launches[KML_STAGE_STRESS]++;
-      }
-      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, S->cl, c->stream, c->gtune, bulk ? G->nvs : nullptr);
+      rc = cell_gather_launch(true, S->s, G->g, sp, tp, S->d.mat, S->cl, c->stream, c->gtune);
       if (rc > 0) return fail("cell stress launch failed");
       if (rc == 0) { CU(cudaEventRecord(S->ev_s[k][1], c->stream)); S->ev_s_valid[k] = true; S->ev_s_step[k] = c->steps_started; }
     }
@@ -1200,7 +1186,7 @@ int kml_fix_velocity_nodes(kml_ctx *c, int solid, int groupbit, int set_mask, co
   if (solid == -1) gs = active_grids(c); else gs.push_back(c->grids[c->solids[solid]->d.grid]);
   for (Grid *G : gs) {
     if (grid_normalize_if_needed(c, G)) return 1;
-    G->nvd_valid = false; G->nvs_valid = false;
+    G->nvd_valid = false;
     k_fix_velocity_nodes<<<nblocks(G->g.nn, 256), 256, 0, c->stream>>>(G->g, groupbit, set_mask, v[0], v[1], v[2], vprev ? vprev[0] : 0, vprev ? vprev[1] : 0,
                                                                         vprev ? vprev[2] : 0, which, 1.0 / c->dt, c->d_scratch);
     c->launches[KML_STAGE_GRID]++;

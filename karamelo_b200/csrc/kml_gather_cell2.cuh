@@ -130,14 +130,11 @@ k_g2p_cell(SolidDev s, GridDev g, StepParams sp, const int *__restrict__ start, 
 // private shared-memory slot (8-byte cp.async) while it runs the constitutive update of the current one.  The register file only holds
 // the weights, the gather accumulators and the constitutive update, so the kernel fits 168 registers (3 x 128 or
 // 6 x 64 threads per SM); prefetching the state into registers instead costs 60 more and halves the occupancy.
-// BULK: the tile arrives as 16 bulk copies (TMA, SASS UBLKCP) of rows of the padded copy `nvs` of the node records (written by the
-// normalisation pass of k_grid_update) onto an mbarrier, requested by one thread - no per-thread address arithmetic, bounds tests or
-// cp.async instructions for the 16 x (seglen + 3) records (~8 % of the kernel's instructions at 24 cells per segment).
-template <int THREADS, int MINB, bool BULK>
+template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_material mat, const int *__restrict__ start, const int *__restrict__ order,
-               int seglen, int nseg, const double *__restrict__ nvs) {
-  extern __shared__ __align__(128) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state, then (BULK) the mbarrier
+               int seglen, int nseg) {
+  extern __shared__ __align__(16) double smem3[]; // [16][TLEN] double4 node tile, then [PSTATE_SLOTS][THREADS] particle state
   const int TLEN = seglen + 3;
   double *tile = smem3;
   double *state = smem3 + (size_t)16 * TLEN * 4;
@@ -152,19 +149,9 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
   int p = pbeg + tid;
   int ip = p < pend ? order[p] : -1;
   int ipn = p + THREADS < pend ? order[p + THREADS] : -1;
-  const unsigned bar = smem_addr(state + (size_t)PSTATE_SLOTS * THREADS);
-  if (BULK) {
-    if (tid == 0) {
-      const unsigned row_bytes = (unsigned)TLEN * 32u;
-      mbar_init(bar, 1); mbar_fence_init();
-      mbar_arrive_expect_tx(bar, 16u * row_bytes);
-#pragma unroll 1
-      for (int r = 0; r < 16; r++) bulk_g2s(smem_addr(tile) + (unsigned)r * row_bytes, nvs + nvd_index(g, i0 + (r >> 2), j0 + (r & 3), kbeg) * 4, row_bytes, bar);
-    }
-  }
   // node tile: 16 rows, contiguous along k in global memory
   const double4 *__restrict__ src0 = tp.doublemapping ? g.nv : g.nvu;
-  if (!BULK) for (int e = tid; e < 16 * TLEN; e += THREADS) {
+  for (int e = tid; e < 16 * TLEN; e += THREADS) {
     const int row = e / TLEN, t = e - row * TLEN;
     const int ni = i0 + (row >> 2), nj = j0 + (row & 3), nk = kbeg + t;
     double *d = tile + (size_t)e * 4;
@@ -178,7 +165,6 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  if (BULK) mbar_wait(bar, 0); // (the barrier above made the initialised mbarrier visible)
 
   const bool int_x = cubic_interior(i0, g.n[0], g.goff0, g.gn0), int_y = cubic_interior(j0, g.n[1], 0, g.n[1]);
   const double h = g.h, ih = g.inv_cellsize;
@@ -242,7 +228,7 @@ struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads 
 
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
 inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
-                              const CellLists &cl, cudaStream_t st, const GatherTune &tune, const double *nvs = nullptr) { // nvs: padded node records -> bulk-copied stress tile
+                              const CellLists &cl, cudaStream_t st, const GatherTune &tune) {
   if (sp.axisymmetric || sp.temp || !cl.valid) return -1;
   // G2P: segments of (almost) equal length.  Stress: segments of EXACTLY seg_stress cells (the last one shorter) - measured at 100 M
   // particles: 24 cells 10.6 ms, 15 cells 11.0, 20 cells 12.0, 30 cells (the equalised split of 210 planes) 12.4, 12 cells 13.4; a short
@@ -253,7 +239,7 @@ inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, 
   const long long nblocks = (long long)g.n[0] * g.n[1] * nseg;
   if (nblocks >= (1ll << 31)) return -1;
   const size_t tile = sizeof(double) * 16 * (size_t)(seglen + 3) * (stress ? 4 : 6);
-  const size_t smem = tile + (stress ? sizeof(double) * PSTATE_SLOTS * (size_t)tune.threads + 16 : 0);
+  const size_t smem = tile + (stress ? sizeof(double) * PSTATE_SLOTS * (size_t)tune.threads : 0);
 #define KML_GATHER_LAUNCH(KERN, THREADS, ...)                                                                                       \
   do {                                                                                                                             \
     auto kern = KERN;                                                                                                              \
@@ -261,13 +247,8 @@ inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, 
     kern<<<(unsigned)nblocks, THREADS, smem, st>>>(__VA_ARGS__);                                                                   \
   } while (0)
   if (stress) {
-    if (nvs) {
-      if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6, true>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
-      else KML_GATHER_LAUNCH((k_stress_cell<128, 3, true>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
-    } else {
-      if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6, false>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
-      else KML_GATHER_LAUNCH((k_stress_cell<128, 3, false>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg, nvs);
-    }
+    if (tune.threads == 64) KML_GATHER_LAUNCH((k_stress_cell<64, 6>), 64, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
+    else KML_GATHER_LAUNCH((k_stress_cell<128, 3>), 128, s, g, sp, tp, mat, cl.start, cl.order, seglen, nseg);
   } else {
     if (tune.g2p_threads == 64) KML_GATHER_LAUNCH((k_g2p_cell<64, 8>), 64, s, g, sp, cl.start, cl.order, seglen, nseg);
     else KML_GATHER_LAUNCH((k_g2p_cell<128, 4>), 128, s, g, sp, cl.start, cl.order, seglen, nseg);

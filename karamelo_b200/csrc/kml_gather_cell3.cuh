@@ -20,15 +20,6 @@
 namespace kml {
 
 #ifdef KML_MISC_KERNELS
-// fallback copy of the node records {v, mass} onto the padded grid of the bulk-copied stress tile (normally written by k_grid_update)
-__global__ void k_grid_pack_v(GridDev g, const double4 *__restrict__ src, double *nvs) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= g.nn) return;
-  const int k = (int)(n % g.n[2]); const long long t = n / g.n[2]; const int j = (int)(t % g.n[1]), i = (int)(t / g.n[1]);
-  const double4 v = src[n];
-  double *d = nvs + nvd_index(g, i, j, k) * 4;
-  *(double2 *)d = make_double2(v.x, v.y); *(double2 *)(d + 2) = make_double2(v.z, v.w);
-}
 __global__ void k_grid_pack_g2p(GridDev g, double *nvd) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= g.nn) return;

@@ -187,8 +187,7 @@ __global__ void __launch_bounds__(128) k_p2g(SolidDev s, GridDev g, StepParams s
 // normalise momentum -> velocity (the "/ grid->mass[in]" of src/solid.cpp:378, :2761) and
 // Grid::update_grid_velocities / update_grid_temperature (src/grid.cpp:448-466, :1354-1362)
 // nvd (optional): packed gather records {v_update, v_update - v} on the zero-padded grid of kml_gather_cell3.cuh, written in the same pass
-// nvs (optional): copy of the (normalised) node record {v, mass} on the same padded grid, 32 B per node: the bulk-copied tile of the stress kernel
-__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware, double *nvd, double *nvs) {
+__global__ void k_grid_update(GridDev g, double dt, int normalize, int update, int temp, int normalize_T, int rigid_aware, double *nvd) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.nn) return;
   double4 rec = g.nv[i];
@@ -200,11 +199,6 @@ __global__ void k_grid_update(GridDev g, double dt, int normalize, int update, i
     for (int d = 0; d < 3; d++) v[d] = (m > 0) ? v[d] / m : 0.0;
     rec.x = v[0]; rec.y = v[1]; rec.z = v[2];
     g.nv[i] = rec;
-  }
-  if (nvs) {
-    const int k = (int)(i % g.n[2]); const long long t = i / g.n[2]; const int j = (int)(t % g.n[1]), ii = (int)(t / g.n[1]);
-    double *d = nvs + (((long long)ii * (g.n[1] + 3) + j) * (g.n[2] + KML_NVD_PADK) + k) * 4;
-    *(double2 *)d = make_double2(rec.x, rec.y); *(double2 *)(d + 2) = make_double2(rec.z, rec.w);
   }
   double T = 0;
   if (temp) { T = g.T[i]; if (normalize_T) { T = (m > 0) ? T / m : 0.0; g.T[i] = T; } }

@@ -76,7 +76,7 @@ __device__ __forceinline__ bool cubic_interior(int i0, int n, int goff, int gn) 
 // 42 % of peak in the momentum pass with a 128-byte stride; the padding took that pass from 0.54 to 0.42 ms at 7 M particles).
 template <bool FULL> struct Rec3 { static constexpr int N = FULL ? 38 : 18; static constexpr int K = FULL ? 34 : 15; };
 
-template <bool FULL, bool MASS, int NB, bool PIPE>
+template <bool FULL, bool MASS, int NB>
 __global__ void __launch_bounds__(128, FULL ? (NB == 2 ? 2 : 3) : (NB == 4 ? 3 : 4))
 k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__restrict__ order, int seglen, int nseg) {
   constexpr int Q = FULL ? 7 : 3;
@@ -84,7 +84,7 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
   constexpr int GPB = 128 / GL;        // groups per block
   constexpr int REC = Rec3<FULL>::N;
   constexpr int GSTRIDE = GL * REC + (NB == 1 ? 8 : (NB == 2 ? 4 : 2)); // the groups of one warp start at different bank offsets (64 / 32 / 16 B apart)
-  __shared__ __align__(16) double stage[GPB * GSTRIDE + REC]; // + one record: the pipelined loop reads one record past the round's last particle
+  __shared__ __align__(16) double stage[GPB * GSTRIDE];
 
   const int lg = threadIdx.x % GL;
   int a = lg / (4 / NB), b0 = (lg % (4 / NB)) * NB;
@@ -235,58 +235,6 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
     }
   };
 
-  // Software-pipelined variant (PIPE): the record of particle q + 1 is loaded INTO THE SAME REGISTERS while particle q is accumulated - the lane
-  // weights and particle quantities as soon as the head products are formed, the z weights plane pair by plane pair as the FMA stream is
-  // done with them.  ncu on the unpipelined loop (profiles/r2b): 11 LDS.128 then a DMUL that waits for them, 27 % of the warp's time per
-  // particle with no FP64 instruction in flight.  r: shared-space byte address of the NEXT record.
-  auto rec_accumulate_pipe = [&](RecR &R, unsigned r) {
-    if (FULL) {
-      double mm[NB], M0[NB], M1[NB], M2[NB], P0[NB], P1[NB], P2[NB], Q0[NB], Q1[NB], Q2[NB];
-#pragma unroll
-      for (int e = 0; e < NB; e++) {
-        const double gxy = R.X.x * R.Y[e].x, gx = R.X.y * R.Y[e].x, gy = R.X.x * R.Y[e].y;
-        mm[e] = gxy * R.MM.x; M0[e] = gxy * R.MM.y; M1[e] = gxy * R.MV.x; M2[e] = gxy * R.MV.y;
-        P0[e] = -(R.A01.x * gx + R.A23.y * gy); P1[e] = -(R.A23.y * gx + R.A01.y * gy); P2[e] = -(R.A45.x * gx + R.A45.y * gy);
-        Q0[e] = -(R.A45.x * gxy); Q1[e] = -(R.A45.y * gxy); Q2[e] = -(R.A23.x * gxy);
-      }
-      R.X = lds_d2(r + offx);
-#pragma unroll
-      for (int e = 0; e < NB; e++) R.Y[e] = lds_d2(r + offy + 16u * e);
-      R.MM = lds_d2(r + 192); R.MV = lds_d2(r + 208);
-      R.A01 = lds_d2(r + 224); R.A23 = lds_d2(r + 240); R.A45 = lds_d2(r + 256);
-      auto plane = [&](int c, double wz, double dwz) {
-#pragma unroll
-        for (int e = 0; e < NB; e++) {
-          double *ac = acc[e][c];
-          ac[0] += mm[e] * wz;
-          ac[1] += M0[e] * wz; ac[2] += M1[e] * wz; ac[3] += M2[e] * wz;
-          ac[4] = fma(Q0[e], dwz, fma(P0[e], wz, ac[4]));
-          ac[5] = fma(Q1[e], dwz, fma(P1[e], wz, ac[5])); ac[6] = fma(Q2[e], dwz, fma(P2[e], wz, ac[6]));
-        }
-      };
-      plane(0, R.Z01.x, R.D01.x); plane(1, R.Z01.y, R.D01.y);
-      R.Z01 = lds_d2(r + 128); R.D01 = lds_d2(r + 160);
-      plane(2, R.Z23.x, R.D23.x); plane(3, R.Z23.y, R.D23.y);
-      R.Z23 = lds_d2(r + 144); R.D23 = lds_d2(r + 176);
-    } else {
-      double M0[NB], M1[NB], M2[NB];
-#pragma unroll
-      for (int e = 0; e < NB; e++) { const double gxy = R.X.x * R.Y[e].x; M0[e] = gxy * R.MM.x; M1[e] = gxy * R.MM.y; M2[e] = gxy * R.MV.x; }
-      R.X.x = lds_d1(r + offx);
-#pragma unroll
-      for (int e = 0; e < NB; e++) R.Y[e].x = lds_d1(r + offy + 8u * e);
-      R.MM = lds_d2(r + 96); R.MV.x = lds_d1(r + 112);
-      auto plane = [&](int c, double wz) {
-#pragma unroll
-        for (int e = 0; e < NB; e++) { double *ac = acc[e][c]; ac[0] += M0[e] * wz; ac[1] += M1[e] * wz; ac[2] += M2[e] * wz; }
-      };
-      plane(0, R.Z01.x); plane(1, R.Z01.y);
-      R.Z01 = lds_d2(r + 64);
-      plane(2, R.Z23.x); plane(3, R.Z23.y);
-      R.Z23 = lds_d2(r + 80);
-    }
-  };
-
   const int gshift = (threadIdx.x & 31) / GL * GL;
   int kcur = kbeg, dirty = 0;
   int p = pbeg;
@@ -314,15 +262,9 @@ k_p2g_cell3(SolidDev s, GridDev g, const int *__restrict__ start, const int *__r
       }
       dirty = 0xF;
     };
-    if (PIPE) {
-      RecR cur; rec_load(cur, rec0s);
-      unsigned rnext = rec0s + (unsigned)(REC * 8);
-      for (int q = 0; q < n; q++, rnext += (unsigned)(REC * 8)) { boundary(q); rec_accumulate_pipe(cur, rnext); }
-    } else {
-      for (int q = 0; q < n; q++) {
-        RecR cur; rec_load(cur, rec0s + (unsigned)(q * REC * 8));
-        boundary(q); rec_accumulate(cur);
-      }
+    for (int q = 0; q < n; q++) {
+      RecR cur; rec_load(cur, rec0s + (unsigned)(q * REC * 8));
+      boundary(q); rec_accumulate(cur);
     }
     __syncwarp(gmask);
     p = pn;
@@ -338,19 +280,19 @@ inline void cell_segments(int n2, int target, int *seglen, int *nseg) {
 }
 
 // returns 0 = launched, -1 = combination not covered (caller uses the atomic kernel), 1 = CUDA error
-template <bool FULL, bool MASS, int NB, bool PIPE>
+template <bool FULL, bool MASS, int NB>
 inline int cell_p2g3_launch_one(const SolidDev &s, const GridDev &g, const CellLists &cl, int seg_target, cudaStream_t st) {
   constexpr int GL = 16 / NB;
   int seglen, nseg; cell_segments(g.n[2], seg_target, &seglen, &nseg);
   const long long ngroups = (long long)g.n[0] * g.n[1] * nseg;
   const long long nb = (ngroups * GL + 127) / 128;
   if (nb >= (1ll << 31)) return -1;
-  k_p2g_cell3<FULL, MASS, NB, PIPE><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
+  k_p2g_cell3<FULL, MASS, NB><<<(unsigned)nb, 128, 0, st>>>(s, g, cl.start, cl.order, seglen, nseg);
   return cudaGetLastError() != cudaSuccess;
 }
 
-// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4); pipe: software-pipelined record loads
-inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int seg_target, cudaStream_t st, int *nlaunch, bool pipe = true) {
+// nb_full / nb_mom: node columns per lane for the full pass (1 | 2) and the momentum-only pass (1 | 2 | 4)
+inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists &cl, int what, int nb_full, int nb_mom, int seg_target, cudaStream_t st, int *nlaunch) {
   *nlaunch = 0;
   const bool full = (what & P2G_FORCE) != 0;
   if (what & (P2G_MB | P2G_TEMP | P2G_HEAT)) return -1;
@@ -358,7 +300,7 @@ inline int cell_p2g3_launch(const SolidDev &s, const GridDev &g, const CellLists
   if (!full && (what & P2G_MASS)) return -1; // mass-only / mass+momentum passes (USF) use the atomic kernel
   if (!full && !(what & P2G_MOM)) return -1;
   int rc;
-#define KML_P2G3(F, M, N) (pipe ? cell_p2g3_launch_one<F, M, N, true>(s, g, cl, seg_target, st) : cell_p2g3_launch_one<F, M, N, false>(s, g, cl, seg_target, st))
+#define KML_P2G3(F, M, N) cell_p2g3_launch_one<F, M, N>(s, g, cl, seg_target, st)
   if (full) {
     if (what & P2G_MASS) rc = nb_full == 2 ? KML_P2G3(true, true, 2) : KML_P2G3(true, true, 1);
     else rc = nb_full == 2 ? KML_P2G3(true, false, 2) : KML_P2G3(true, false, 1);
