@@ -117,8 +117,15 @@ def step(args):
         strict = {k: rel(got[k], ref[k]) for k in fields if k != "PTAG"}
         worst = {k: rel_either(got[k], ref[k], keep[k]) for k in fields if k != "PTAG"}
         branch = max(rel(keep[k], ref[k]) for k in fields if k != "PTAG")
-        bad = {k: v for k, v in worst.items() if v > 1e-10}
+        # 1e-10 of the field magnitude, with one allowance: the CUDA run takes its OWN coin flips on `wf != 0` (a particle position that differs
+        # from the oracle's in the last bit), also where the oracle run has none.  One flip moves F by at most |v| dw dt = 4e-13, which this
+        # block (bulk modulus 833, yield stress 3) shows as 1.2e-10 of max|sigma|: the stress of drifting cases is held to 1e-10 + that bound.
+        tol = {k: 1e-10 for k in worst}
+        if args.drift:
+            tol["SIGMA"] = 2.5e-10
+        bad = {k: v for k, v in worst.items() if v > tol[k]}
         assert not bad, (bad, worst, strict)
+        assert worst["FDEF"] <= 1e-12 and worst["X"] <= 1e-13, worst  # the quantities the flip acts on stay far inside the tolerance
         assert abs(st["dt"] - st_ref["dt"]) <= 1e-10 * st_ref["dt"] and st["ntimestep"] == st_ref["ntimestep"]
         if args.drift:
             assert any(a != b for a, b in moved), "no particle migrated: the test does not exercise exchange_particles"
