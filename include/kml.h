@@ -324,6 +324,9 @@ int kml_error_flags(kml_ctx *ctx, unsigned *flags); /* on a decomposed run: coll
 /* 128-byte NCCL unique id created on rank 0 and passed to every rank. */
 int kml_comm_unique_id(void *id128);
 int kml_comm_init(kml_ctx *ctx, const void *id128);
+/* In-place sum over the ranks of n <= 16 host doubles (the MPI_Allreduce(SUM) of the reference's set-up commands, e.g.
+ * src/delete_particles.cpp:76-78, src/solid.cpp:2302-2310); collective; a no-op on one rank. */
+int kml_comm_sum(kml_ctx *ctx, double *vals, int n);
 
 /* ---- measurement ------------------------------------------------------------------------- */
 /* Per-stage device time (ms) accumulated with CUDA events on the context's stream since the last

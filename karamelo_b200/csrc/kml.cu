@@ -589,7 +589,6 @@ int kml_solid_delete_particles(kml_ctx *c, int sid, const int *dlist) {
   CU(cudaSetDevice(c->dev));
   Solid *S = c->solids[sid]; const long long np = S->s.np;
   if (c->c.is_CPDI) return fail("kml: delete_particles with CPDI is not supported (the reference does not move the particle domains either, src/solid.cpp:1590-1610)");
-  if (c->c.nranks > 1) return fail("kml: delete_particles is a single-GPU set-up command in the CUDA engine");
   if (!c->c.is_TL && S->moved) { for (int k = 0; k < 3; k++) std::swap(S->s.x[k], S->s.xn[k]); S->moved = false; }
   const std::vector<int> src = delete_order(dlist, np); const long long n = (long long)src.size();
   if (n == np) return 0;
@@ -1346,6 +1345,18 @@ int kml_comm_init(kml_ctx *c, const void *id128) {
   c->comm.rank = c->c.rank; c->comm.nranks = c->c.nranks;
   CU(cudaMalloc(&c->comm.mig_cnt, 8 * sizeof(int)));
   CU(cudaMallocHost(&c->comm.h_cnt, 8 * sizeof(int)));
+  return 0;
+}
+
+int kml_comm_sum(kml_ctx *c, double *vals, int n) { // set-up commands only: one blocking round trip
+  if (c->comm.nranks <= 1 || n <= 0) return 0;
+  if (n > 16) return fail("kml_comm_sum: at most 16 values");
+  CU(cudaSetDevice(c->dev));
+  double *d = c->d_scratch + 40;
+  CU(cudaMemcpyAsync(d, vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  NC(nccl().AllReduce(d, d, n, ncclDouble, ncclSum, c->comm.comm, c->stream));
+  CU(cudaMemcpyAsync(vals, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

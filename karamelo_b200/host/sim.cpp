@@ -190,11 +190,14 @@ void Sim::register_commands() {
       while (k < n) {
         if (dl[k]) { S.x0[k] = S.x0[n - 1]; S.mask[k] = S.mask[n - 1]; S.ptag[k] = S.ptag[n - 1]; dl[k] = dl[n - 1]; n--; } else k++;
       }
-      np_total = n; // sic: the reference stores this solid's remaining count (domain->np_total = np_local_reduced, src/delete_particles.cpp:78)
       S.np = n; S.x0.resize(n); S.mask.resize(n); S.ptag.resize(n); mirrors_current(S);
       std::vector<double> vol(n), mass(n);
       check(kml_solid_download(ctx, S.dev, KML_P_VOL, vol.data())); check(kml_solid_download(ctx, S.dev, KML_P_MASS, mass.data()));
       S.vtot = S.mtot = 0; for (int64_t i = 0; i < n; i++) { S.vtot += vol[i]; S.mtot += mass[i]; }
+      double red[3] = {(double)n, S.vtot, S.mtot}; // decomposed run: every rank deleted its own particles; the totals are sums over the slabs
+      check(kml_comm_sum(ctx, red, 3));
+      np_total = (int64_t)red[0]; // sic: the reference stores this solid's remaining count (domain->np_total = np_local_reduced, src/delete_particles.cpp:78)
+      S.vtot = red[1]; S.mtot = red[2];
       if (!quiet) std::cout << "Solid " << S.id << " new total volume = " << S.vtot << std::endl;
     }
     return Var(0);

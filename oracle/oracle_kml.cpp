@@ -1370,6 +1370,7 @@ int kml_compute_strain_energy(kml_ctx *c, int solid, int groupbit, double *es) {
 int kml_error_flags(kml_ctx *c, unsigned *flags) { *flags = c->flags; return 0; }
 int kml_comm_unique_id(void *) { return fail("oracle: single rank"); }
 int kml_comm_init(kml_ctx *, const void *) { return fail("oracle: single rank"); }
+int kml_comm_sum(kml_ctx *, double *, int) { return 0; } // one rank: the sum is the value
 int kml_profile(kml_ctx *, int) { return 0; }
 static double g_t0;
 static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }

@@ -84,6 +84,8 @@ def step(args):
     elif args.variant == "force_nodes":  # a total force spread over the nodes of a group that spans the slab cuts: the node count is a global sum
         script += ("region(rmid, block, INF, INF, %g, INF, INF, INF)\ngroup(gf, nodes, region, rmid, solid, blk)\n"
                    "fix(ff, force_nodes, gf, 0.004, NULL, -0.002)\n" % 6.5)
+    elif args.variant == "delete_particles":  # a set-up command that edits the particle set: every rank deletes its own part of the region
+        script += "region(rdel, block, %g, %g, INF, 6.1, INF, INF)\ndelete_particles(blk, region, rdel)\n" % (4 + cells[0] / 2 - 1.6, 4 + cells[0] / 2 + 2.1)
     elif args.variant == "thermal":  # thermo-mechanical: temperature and heat-source node fields join the halo sums
         script = script.replace("method(ulmpm, FLIP, %s, 0.99)" % args.shape, "method(ulmpm, FLIP, %s, 0.99, thermo-mechanical)" % args.shape)
         script = script.replace("material(m, eos-strength, e, s)", "temperature(tpw, plastic_work, 0.9, 50, 2, 0, 0, 500)\nmaterial(m, eos-strength, e, s, tpw)")
@@ -143,7 +145,7 @@ if __name__ == "__main__":
     ap.add_argument("--drift", type=float, default=0.0)
     ap.add_argument("--method", default="", help="arguments of method(ulmpm, ...) replacing the block's FLIP cubic-spline default")
     ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
-    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal", "force_nodes"])
+    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal", "force_nodes", "delete_particles"])
     a = ap.parse_args()
     try:
         {"partition": partition, "step": step}[a.mode](a)

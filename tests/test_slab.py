@@ -75,7 +75,7 @@ def test_two_slabs_affine_transfer(oracle_lib, method):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["velocity_nodes", "thermal", "force_nodes"])
+@pytest.mark.parametrize("variant", ["velocity_nodes", "thermal", "force_nodes", "delete_particles"])
 def test_two_slabs_node_fix_and_thermal_fields(oracle_lib, variant):
     """fix velocity_nodes on a node group that spans both slabs (reaction force all-reduced) and a thermo-mechanical block (T, Qext,
     Qint in the halo sums), with particles migrating."""
