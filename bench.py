@@ -344,7 +344,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_stage[dom]["algo_GBps"], "peak": peak, "unit": "GB/s", "frac": per_stage[dom]["frac"],
                 "traffic": (tr["dram_bytes_per_particle"] * np_max if tr else None), "traffic_source": (tr or {}).get("source"),
                 "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "particles_per_launch": np_max,
-                "second_roof": "FP64 pipe (64 DFMA/clk/SM nominal = 18.6 T DFMA/s at 1965 MHz; tools/fp64_peak.cu measures 18.1 T, profiles/r1l_fp64_peak_microbenchmark.txt): "
+                "second_roof": "FP64 pipe (64 DFMA/clk/SM nominal = 18.6 T DFMA/s at 1965 MHz; tools/fp64_peak.cu measures 18.3 T, profiles/r2_fp64_peak_microbenchmark.txt): "
                                "fp64_frac = minimal FP64 instructions / (time x nominal pipe rate), DESIGN.md section 3",
                 "per_stage": per_stage,
                 "stage_protocol": "CUDA event pairs around every stage INSIDE the timed region, read after the final synchronisation; per stage the max over ranks",

@@ -416,7 +416,6 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   CU(cudaSetDevice(c->dev));
   const bool rigid_ = d->mat.rigid || d->mat.type == KML_MAT_RIGID;
   if (rigid_ && c->c.is_CPDI) return fail("kml: rigid solids with CPDI are not implemented in the CUDA engine");
-  if (rigid_ && c->c.nranks > 1) return fail("kml: rigid solids are single-GPU in the CUDA engine (Grid::reduce_rigid_ghost_nodes is not reproduced)");
   if (c->apic && c->c.shape_function == KML_SHAPE_LINEAR && d->np_per_cell != 0 && d->np_per_cell != 1 && d->np_per_cell != 2)
     return fail("Number of particle per cell not supported with linear shape functions and APIC."); // src/solid.cpp:1453-1460
   Solid *S = new Solid(); S->d = *d; S->rigid = rigid_; if (rigid_) c->has_rigid = true; SolidDev &s = S->s;
@@ -731,6 +730,10 @@ int kml_set_dt(kml_ctx *c, double dt) { if (resolve_dt(c)) return 1; c->dt = dt;
 int kml_get_dt(kml_ctx *c, double *dt) { if (resolve_dt(c)) return 1; *dt = c->dt; return 0; }
 
 // ---- stages -----------------------------------------------------------------------------------
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + nccl().GetErrorString(r_)); } while (0)
+static int halo_or_rigid(kml_ctx *c, Grid *G, int stage);
+static std::vector<Grid *> active_grids(kml_ctx *c);
+
 int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
   CU(cudaSetDevice(c->dev));
   c->steps_started++;
@@ -769,6 +772,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
       c->launches[KML_STAGE_REBIN]++;
       if (check_launch("k_p2g(mark rigid)")) return 1;
     }
+    if (c->comm.nranks > 1) for (Grid *G : active_grids(c)) if (halo_or_rigid(c, G, KML_STAGE_REBIN)) return 1;
     if (c->c.is_TL) c->tl_wf_done = true;
   }
   if (!c->c.is_TL) {
@@ -835,7 +839,6 @@ static std::vector<Grid *> active_grids(kml_ctx *c) {
   return r;
 }
 
-#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(std::string(#call) + ": " + nccl().GetErrorString(r_)); } while (0)
 
 // Sum of the node planes shared with the slab neighbours (see kml_comm.cuh).  Local planes [0, nsh) are shared
 // with the left neighbour, [n0 - nsh, n0) with the right one, nsh = stencil span - 1.
@@ -866,6 +869,26 @@ static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
   k_halo_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top, rl, rr, left, right);
   c->launches[stage] += 2;
   return check_launch("halo_sum");
+}
+
+// Grid::reduce_rigid_ghost_nodes (src/grid.cpp:746-879): OR of the rigid flags on the planes shared with the slab neighbours
+static int halo_or_rigid(kml_ctx *c, Grid *G, int stage) {
+  Comm &cm = c->comm; GridDev &g = G->g;
+  const int nsh = (c->c.shape_function == KML_SHAPE_LINEAR ? 2 : 4) - 1;
+  const long long plane = (long long)g.n[1] * g.n[2], cnt = plane * nsh;
+  const size_t need = (size_t)cnt * 4 * sizeof(int);
+  if (need > cm.halo_bytes) { cudaFree(cm.halo_buf); cm.halo_buf = nullptr; CU(cudaMalloc(&cm.halo_buf, need)); cm.halo_bytes = need; }
+  const int left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+  int *sl = (int *)cm.halo_buf, *sr = sl + cnt, *rl = sr + cnt, *rr = rl + cnt;
+  const long long top = (long long)(g.n[0] - nsh) * plane;
+  k_halo_pack_flag<<<nblocks(cnt, 256), 256, 0, c->stream>>>(g.rigid, cnt, top, sl, sr, left, right);
+  NC(nccl().GroupStart());
+  if (left) { NC(nccl().Send(sl, cnt, ncclInt, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(rl, cnt, ncclInt, cm.rank - 1, cm.comm, c->stream)); }
+  if (right) { NC(nccl().Send(sr, cnt, ncclInt, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(rr, cnt, ncclInt, cm.rank + 1, cm.comm, c->stream)); }
+  NC(nccl().GroupEnd());
+  k_halo_or_flag<<<nblocks(cnt, 256), 256, 0, c->stream>>>(g.rigid, cnt, top, rl, rr, left, right);
+  c->launches[stage] += 2;
+  return check_launch("halo_or_rigid");
 }
 
 static int p2g_launch(kml_ctx *c, int what_in, int stage) {

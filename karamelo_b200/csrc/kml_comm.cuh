@@ -59,6 +59,21 @@ __global__ void k_halo_add(HaloFields hf, long long cnt, long long top_off_nodes
   }
 }
 
+// Grid::reduce_rigid_ghost_nodes (src/grid.cpp:746-879): a node is rigid if ANY rank's rigid particle reaches it - the flags of the shared
+// planes are OR-ed with the neighbours' (same message layout as the sums, one int per node)
+__global__ void k_halo_pack_flag(const int *a, long long cnt, long long top_off_nodes, int *outL, int *outR, int left, int right) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  if (left) outL[i] = a[i];
+  if (right) outR[i] = a[top_off_nodes + i];
+}
+__global__ void k_halo_or_flag(int *a, long long cnt, long long top_off_nodes, const int *inL, const int *inR, int left, int right) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  if (left) a[i] |= inL[i];
+  if (right) a[top_off_nodes + i] |= inR[i];
+}
+
 // ---- migration ---------------------------------------------------------------------------------
 // dest of every particle from the GLOBAL stencil base of its (new) position; leavers are appended to a list
 __global__ void k_mig_mark(const double *x0, long long np, double lo, double ih, int shape_linear, int base_lo, int base_hi, int rank, int nranks,

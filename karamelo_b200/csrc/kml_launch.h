@@ -2,6 +2,7 @@
 // so that the library builds in parallel (see karamelo_b200/Makefile).
 #pragma once
 #include "kml_kernels.cuh"
+#include <algorithm>
 
 namespace kml {
 #define KML_DECL_LAUNCHERS(D, T)                                                                                                     \
@@ -13,7 +14,8 @@ KML_DECL_LAUNCHERS(1, 0) KML_DECL_LAUNCHERS(2, 0) KML_DECL_LAUNCHERS(3, 0)
 KML_DECL_LAUNCHERS(1, 1) KML_DECL_LAUNCHERS(2, 1) KML_DECL_LAUNCHERS(3, 1)
 #undef KML_DECL_LAUNCHERS
 
-inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+// at least one block: a solid may hold no particle on a rank of a decomposed run (every kernel checks its index against the count)
+inline unsigned nblocks(long long n, int bs) { return (unsigned)((std::max<long long>(n, 1) + bs - 1) / bs); }
 } // namespace kml
 
 // expands to launch_<family>_d<KML_DIM>_tl<KML_TL>

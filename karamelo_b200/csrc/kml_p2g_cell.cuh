@@ -79,7 +79,7 @@ inline int CellLists::build(const SolidDev &s, const GridDev &g, long long capac
     memset(h_disorder, 0, sizeof(int) * 32 * DISORDER_SLOTS);
   }
   if (cudaMemsetAsync(start, 0, sizeof(int) * (ncells + 1), st) || cudaMemsetAsync(disorder, 0, sizeof(int) * 32 * DISORDER_SLOTS, st)) return 1;
-  const unsigned nb = (unsigned)((s.np + 255) / 256);
+  const unsigned nb = (unsigned)((std::max<long long>(s.np, 1) + 255) / 256);
   k_cell_count<<<nb, 256, 0, st>>>(s, g, cell_of, rank, start);
   if (cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, start, start, (int)(ncells + 1), st)) return 1;
   k_cell_fill<<<nb, 256, 0, st>>>(s.np, cell_of, rank, start, order, disorder);

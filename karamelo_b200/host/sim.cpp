@@ -809,6 +809,12 @@ Var Sim::cmd_solid(std::vector<std::string> &a) {
   return Var(0);
 }
 
+// Room for the particles that migrate in: a solid of up to 4 M particles may end up entirely on one slab (a body crossing the box), a large one
+// is balanced by construction and keeps 1/8 of head room.
+static int64_t slab_capacity(int64_t np_local, int64_t np_global) {
+  return np_global <= 4000000 ? np_global + 4096 : np_local + np_local / 8 + 4096;
+}
+
 void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   int iregion = find_region(a[2]);
   if (iregion == -1) fatal("Error: region ID " + a[2] + " not does not exist.\n");
@@ -897,9 +903,9 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
       for (int b = 0; b < nbins; b++) { if (b < base_lo) tag_offset += hist[b]; else if (b < base_hi) np_local += hist[b]; }
       L.base_lo = base_lo; L.base_hi = base_hi;
     } else np_local = np_global;
-    if (np_local == 0) fatal("Error: solid does not have any particles.\n");
+    if (np_global == 0) fatal("Error: solid does not have any particles.\n"); // a slab of a decomposed run may hold none of them (yet)
     s.np = np_local; s.np_created = np_global; s.mirror_gen = 0; s.x0.clear(); s.mask.clear(); s.ptag.clear();
-    kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
+    kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? slab_capacity(s.np, np_global) : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
     check(kml_solid_create(ctx, &d, &s.dev));
     check(kml_solid_populate(ctx, s.dev, &L, &kreg, tag_offset));
     np_total += np_global; np_global_last = np_global; tag_offset_last = tag_offset;
@@ -948,7 +954,7 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
     np_global = (int64_t)s.x0.size();
   }
   s.np = (int64_t)s.x0.size(); s.np_created = np_global;
-  if (s.np == 0) fatal("Error: solid does not have any particles.\n");
+  if (np_global == 0) fatal("Error: solid does not have any particles.\n"); // a slab of a decomposed run may hold none of them (yet)
   s.mask.assign(s.np, 1);
   s.ptag.resize(s.np);
   std::vector<double> mass(s.np), vol(s.np), T(s.np, s.T0);
@@ -961,7 +967,7 @@ void Sim::populate(SolidH &s, std::vector<std::string> &a) {
   np_global_last = np_global; tag_offset_last = tag_offset;
 
   // upload; everything not set here starts at the values of src/solid.cpp:2283-2321 (F = R = I, J = 1, mask = 1, rest 0)
-  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? s.np + s.np / 8 + 4096 : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
+  kml_solid_desc d; memset(&d, 0, sizeof d); d.np = s.np; d.capacity = nranks > 1 ? slab_capacity(s.np, np_global) : s.np; d.grid = s.grid->id; d.np_per_cell = s.np_per_cell; d.mat = mat;
   check(kml_solid_create(ctx, &d, &s.dev));
   check(kml_solid_upload(ctx, s.dev, KML_P_PTAG, s.ptag.data()));
   check(kml_solid_upload(ctx, s.dev, KML_P_X, s.x0.data()));

@@ -49,11 +49,11 @@ def make_engine(lib=None, quiet=True, with_comm=True):
     return Engine(lib, quiet=quiet or rank != 0, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
 
 
-def gather_snapshot(engine, fields):
-    """All ranks' particles (solid 0) concatenated and sorted by tag, on every rank."""
+def gather_snapshot(engine, fields, solid=0):
+    """All ranks' particles of one solid concatenated and sorted by tag, on every rank."""
     from .api import P
     _, world, _, dist = init_distributed()
-    d = {f: engine.download(0, getattr(P, f)) for f in fields}
+    d = {f: engine.download(solid, getattr(P, f)) for f in fields}
     if world > 1:
         parts = [None] * world
         dist.all_gather_object(parts, d)

@@ -87,7 +87,7 @@ def rel_either(got, ref_a, ref_b):
     return float(np.max(np.minimum(np.abs(g - a), np.abs(g - b)))) / scale
 
 
-def oracle_both_memberships(lib, script, steps, fields):
+def oracle_both_memberships(lib, script, steps, fields, all_solids=False):
     """The oracle run twice: reference semantics (nodes whose weight rounds to 0 are dropped, src/ulmpm.cpp:252-263) and with those nodes kept."""
     out = []
     for keep in (False, True):
@@ -96,7 +96,8 @@ def oracle_both_memberships(lib, script, steps, fields):
         try:
             e = Engine(lib)
             e.script(script + "\nrun(%d)\n" % steps)
-            out.append((e.snapshot(fields)[0], e.state()))
+            snaps = e.snapshot(fields)
+            out.append((snaps if all_solids else snaps[0], e.state()))
             e.close()
         finally:
             os.environ.pop("KML_ORACLE_KEEP_ZERO_WEIGHT", None)

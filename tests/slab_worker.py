@@ -86,6 +86,13 @@ def step(args):
                    "fix(ff, force_nodes, gf, 0.004, NULL, -0.002)\n" % 6.5)
     elif args.variant == "delete_particles":  # a set-up command that edits the particle set: every rank deletes its own part of the region
         script += "region(rdel, block, %g, %g, INF, 6.1, INF, INF)\ndelete_particles(blk, region, rdel)\n" % (4 + cells[0] / 2 - 1.6, 4 + cells[0] / 2 + 2.1)
+    elif args.variant in ("two_solids", "rigid_tool"):  # a second solid on the same decomposed grid (some slabs hold none of its particles); rigid: Grid::reduce_rigid_ghost_nodes
+        mat2 = "material(m2, rigid, rho)" if args.variant == "rigid_tool" else "material(m2, eos-strength, e, s)"
+        assert "material(m, eos-strength, e, s)\n" in script
+        script = script.replace("material(m, eos-strength, e, s)\n", "material(m, eos-strength, e, s)\n" + mat2 + "\n")  # both materials before the first solid (src/material.cpp:293-298)
+        x0 = 4 + cells[0] / 2 - 1.5  # straddles the middle slab cut; the outer slabs of a 4-rank run hold none of it
+        script += ("region(rtool, block, %g, %g, %g, %g, 5, %g)\nsolid(tool, region, rtool, 2, m2, h, 0)\ngroup(gtool, particles, region, rtool, solid, tool)\n"
+                   "fix(vtool, initial_velocity_particles, gtool, %g, -0.02, 0)\n" % (x0, x0 + 3, 4 + cells[1] + 0.5, 4 + cells[1] + 2.5, 4 + cells[2] - 1, args.drift))
     elif args.variant == "thermal":  # thermo-mechanical: temperature and heat-source node fields join the halo sums
         script = script.replace("method(ulmpm, FLIP, %s, 0.99)" % args.shape, "method(ulmpm, FLIP, %s, 0.99, thermo-mechanical)" % args.shape)
         script = script.replace("material(m, eos-strength, e, s)", "temperature(tpw, plastic_work, 0.9, 50, 2, 0, 0, 500)\nmaterial(m, eos-strength, e, s, tpw)")
@@ -103,7 +110,7 @@ def step(args):
     eng.line("run(%d)" % args.steps)
     np1 = eng.solid_info(0)["np"]
     st = eng.state()
-    got = slab.gather_snapshot(eng, fields)
+    gots = [slab.gather_snapshot(eng, fields, i) for i in range(eng.nsolids())]
     moved = [None] * world
     dist.all_gather_object(moved, (np0, np1))
     flags = eng.error_flags()
@@ -113,12 +120,18 @@ def step(args):
         # the oracle with the reference's `wf != 0` neighbour test and without it: where a case contains a marginal membership event
         # (tests/test_weight_zero_skip.py) an element may follow either branch; without such an event the two runs are identical and this
         # is the plain 1e-10 comparison
-        (ref, st_ref), (keep, _) = oracle_both_memberships(load_host_library(ORACLE_HOST_LIB), script, args.steps, fields)
-        assert flags == 0
-        assert (got["PTAG"] == ref["PTAG"]).all(), "particle tags differ"
-        strict = {k: rel(got[k], ref[k]) for k in fields if k != "PTAG"}
-        worst = {k: rel_either(got[k], ref[k], keep[k]) for k in fields if k != "PTAG"}
-        branch = max(rel(keep[k], ref[k]) for k in fields if k != "PTAG")
+        refs = oracle_both_memberships(load_host_library(ORACLE_HOST_LIB), script, args.steps, fields, all_solids=True)
+        (ref_all, st_ref), (keep_all, _) = refs
+        assert flags == 0 and len(gots) == len(ref_all)
+        strict, worst, branch = {}, {}, 0.0
+        for got, ref, keep in zip(gots, ref_all, keep_all):  # every solid of the run
+            assert (got["PTAG"] == ref["PTAG"]).all(), "particle tags differ"
+            for k in fields:
+                if k == "PTAG":
+                    continue
+                strict[k] = max(strict.get(k, 0.0), rel(got[k], ref[k]))
+                worst[k] = max(worst.get(k, 0.0), rel_either(got[k], ref[k], keep[k]))
+                branch = max(branch, rel(keep[k], ref[k]))
         # 1e-10 of the field magnitude, with one allowance: the CUDA run takes its OWN coin flips on `wf != 0` (a particle position that differs
         # from the oracle's in the last bit), also where the oracle run has none.  One flip moves F by at most |v| dw dt = 4e-13, which this
         # block (bulk modulus 833, yield stress 3) shows as 1.2e-10 of max|sigma|: the stress of drifting cases is held to 1e-10 + that bound.
@@ -145,7 +158,7 @@ if __name__ == "__main__":
     ap.add_argument("--drift", type=float, default=0.0)
     ap.add_argument("--method", default="", help="arguments of method(ulmpm, ...) replacing the block's FLIP cubic-spline default")
     ap.add_argument("--a", type=float, default=2.5e-4, help="squeeze rate (SURVEY 8d: 2.5e-4)")
-    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal", "force_nodes", "delete_particles"])
+    ap.add_argument("--variant", default="", choices=["", "velocity_nodes", "thermal", "force_nodes", "delete_particles", "two_solids", "rigid_tool"])
     a = ap.parse_args()
     try:
         {"partition": partition, "step": step}[a.mode](a)

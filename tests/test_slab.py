@@ -85,6 +85,18 @@ def test_two_slabs_node_fix_and_thermal_fields(oracle_lib, variant):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,cells", [(2, "12"), (4, "24")])
+@pytest.mark.parametrize("variant", ["two_solids", "rigid_tool"])
+def test_slabs_second_solid(oracle_lib, world, cells, variant):
+    """A second solid on the same decomposed grid, compared solid by solid: a deformable plate pressed onto the drifting block, and the same
+    plate made rigid (Grid::rigid flags OR-ed over the shared planes, Grid::reduce_rigid_ghost_nodes src/grid.cpp:746-879).  On 4 slabs the
+    outer two hold no particle of the plate."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    print(launch(world, ["step", "--cells", cells, "6", "6", "--scheme", "musl", "--drift", "0.03", "--steps", "100", "--a", "2.5e-3", "--variant", variant]))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("a", ["2.5e-4", "2.5e-3"])
 def test_four_slabs_match_single_rank_oracle(oracle_lib, a):
     """2.5e-4 is the benchmark's own squeeze rate; 2.5e-3 is ten times that (round 1 measured the stress of this block at
