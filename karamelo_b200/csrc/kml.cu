@@ -67,7 +67,7 @@ struct kml_ctx {
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   double *d_red = nullptr, *h_red = nullptr; cudaEvent_t ev_dt = nullptr; bool dt_pending = false; double dt_factor = 1.0; // deferred adjust_dt (resolve_dt)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
-  bool permute_want = false, permute_go = false, dt_collective = false; // decomposed runs: a rank's wish travels with the dt all-reduce and all ranks re-order in the same step (no rank waits for another's permute)
+  bool permute_want = false, permute_go = false, dt_collective = false; long long last_collective_permute = -10; // decomposed runs: a rank's wish travels with the dt all-reduce and all ranks re-order in the same step (no rank waits for another's permute)
   double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   int g2p_tma = 4; int nsm = 148; // KML_G2P_TMA: 0 = tile through registers, 1 / 3 = persistent TMA-fed kernel, 4 = one block per segment with a bulk-copied tile (default)
   bool use_cell_p2g = true; int cell_mask = 7; int p2g_nb = 1, v2g_nb = 2; GatherTune gtune; // cell_mask (KML_CELL_MASK): 1 = P2G, 2 = G2P, 4 = stress use the cell kernels // measurement switches: KML_P2G=atomic, KML_P2G_NB, KML_V2G_NB, KML_SEGLEN, KML_GATHER_THREADS
@@ -229,6 +229,7 @@ int kml_destroy(kml_ctx *c) {
     delete s; }
   if (c->comm.comm) {
     nccl().CommDestroy(c->comm.comm);
+    if (c->comm.zone_left) cudaIpcCloseMemHandle(c->comm.zone_left); if (c->comm.zone_right) cudaIpcCloseMemHandle(c->comm.zone_right); cudaFree(c->comm.zone); cudaFree(c->comm.push_done);
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
     cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
   }
@@ -387,7 +388,9 @@ __global__ void k_permute(const double *__restrict__ src, double *__restrict__ d
 }
 __global__ void k_iota(int *a, long long n) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = (int)i; }
 
-static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
+// the second buffer of the double-buffered permute, allocated at the FIRST re-bin (a 26-52 GB cudaMalloc takes tens of milliseconds once peer
+// access is enabled; it must not land in the middle of a run)
+static int permute_reserve(kml_ctx *c, Solid *S) {
   if (S->no_permute || S->accbuf || S->cpbuf) return 0;
   if (!S->buf2) {
     const size_t bytes = sizeof(double) * S->cap * S->nd;
@@ -397,6 +400,11 @@ static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
     }
     CU(cudaMemsetAsync(S->buf2, 0, bytes, c->stream));
   }
+  return 0;
+}
+static int permute_solid(kml_ctx *c, Solid *S, Grid *G) {
+  if (permute_reserve(c, S)) return 1;
+  if (S->no_permute || S->accbuf || S->cpbuf || !S->buf2) return 0;
   const long long np = S->s.np;
   const int xslot = (int)((S->s.x[0] - S->buf) / S->cap); // 0, or 3 after an odd number of x <-> xn swaps
   if (xslot != 0 && xslot != 3) return fail("permute_solid: unexpected position slot");
@@ -778,6 +786,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
   if (!c->c.is_TL) {
     if (c->use_cell_p2g && !c->apic && !c->c.ge && !c->has_rigid && cell_p2g_supported(c->c.dimension, c->c.shape_function)) {
       StageTimer t(c, KML_STAGE_REBIN);
+      const bool go_now = c->permute_go; // decomposed runs: the ranks agreed (through the dt all-reduce) to re-order in this step
       for (Solid *S : c->solids) {
         Grid *G = c->grids[S->d.grid];
         int nl = 0;
@@ -786,7 +795,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
         // physical re-ordering when too many particles sit far from their cell-sorted position (the count of the PREVIOUS re-bin, read
         // without a synchronisation; the first re-bin waits for its own)
         if (c->permute_frac >= 0 && S->cl.valid) {
-          if (c->steps_started == 1) { CU(cudaStreamSynchronize(c->stream)); }
+          if (c->steps_started == 1) { if (permute_reserve(c, S)) return 1; CU(cudaStreamSynchronize(c->stream)); }
           const long long far = S->cl.far_count();
           // measurements of earlier steps, read without waiting (an event that has not completed yet is looked at next step)
           float t = 0;
@@ -806,8 +815,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
           if (c->permute_every > 0) due = c->steps_started - S->last_permute_step >= c->permute_every && far > 0; // KML_PERMUTE_EVERY: fixed period (measurements)
           if (c->comm.nranks > 1 && c->dt_collective && c->permute_every <= 0) { // collective decision (one step late): ask now, act when the all-reduce said so
             if (due && c->steps_started - S->last_permute_step >= c->permute_min_steps && c->steps_started > 1) c->permute_want = true;
-            due = c->permute_go || (c->steps_started == 1 && due);
-            if (due) c->permute_go = false;
+            due = go_now || (c->steps_started == 1 && due);
           }
           if (due && c->steps_started - S->last_permute_step >= (c->comm.nranks > 1 && c->dt_collective ? 0 : c->permute_min_steps)) {
             if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] step %lld: physical permute, %lld of %lld particles far from their cell-sorted slot (stress %.3f ms clean, %.3f ms lost since, permute %.3f ms)\n",
@@ -817,6 +825,7 @@ int kml_compute_grid_weight_functions_and_gradients(kml_ctx *c) {
           }
         }
       }
+      if (go_now) { c->permute_go = false; c->permute_want = false; c->last_collective_permute = c->steps_started; }
     }
   }
   return 0;
@@ -840,6 +849,48 @@ static std::vector<Grid *> active_grids(kml_ctx *c) {
 }
 
 
+// One-time, collective: every rank allocates its landing zone, the neighbours trade CUDA IPC handles (64-byte blobs through ncclSend/Recv) and map
+// each other's zones; the peer path is used only if EVERY rank succeeded (KML_HALO=nccl forces the send/recv path).
+static int halo_peer_setup(kml_ctx *c, size_t slot_bytes) {
+  Comm &cm = c->comm; cm.peer_state = -1;
+  const char *mode = getenv("KML_HALO");
+  const bool want = !(mode && !strcmp(mode, "nccl"));
+  const int left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  bool ok = want;
+  cudaIpcMemHandle_t mine, hl, hr; memset(&mine, 0, sizeof mine); memset(&hl, 0, sizeof hl); memset(&hr, 0, sizeof hr);
+  if (ok) ok = cudaMalloc(&cm.zone, HALO_ZONE_HDR + 4 * slot_bytes) == cudaSuccess && cudaMemsetAsync(cm.zone, 0, HALO_ZONE_HDR, c->stream) == cudaSuccess &&
+               cudaMalloc(&cm.push_done, sizeof(unsigned)) == cudaSuccess && cudaMemsetAsync(cm.push_done, 0, sizeof(unsigned), c->stream) == cudaSuccess &&
+               cudaIpcGetMemHandle(&mine, cm.zone) == cudaSuccess;
+  cudaGetLastError();
+  unsigned char *d_h = nullptr; // [mine | from left | from right]
+  CU(cudaMalloc(&d_h, 3 * sizeof mine));
+  CU(cudaMemcpyAsync(d_h, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  NC(nccl().GroupStart());
+  if (left) { NC(nccl().Send(d_h, sizeof mine, ncclChar, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(d_h + sizeof mine, sizeof mine, ncclChar, cm.rank - 1, cm.comm, c->stream)); }
+  if (right) { NC(nccl().Send(d_h, sizeof mine, ncclChar, cm.rank + 1, cm.comm, c->stream)); NC(nccl().Recv(d_h + 2 * sizeof mine, sizeof mine, ncclChar, cm.rank + 1, cm.comm, c->stream)); }
+  NC(nccl().GroupEnd());
+  CU(cudaMemcpyAsync(&hl, d_h + sizeof mine, sizeof mine, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&hr, d_h + 2 * sizeof mine, sizeof mine, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_h);
+  if (ok && left) ok = cudaIpcOpenMemHandle((void **)&cm.zone_left, hl, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  if (ok && right) ok = cudaIpcOpenMemHandle((void **)&cm.zone_right, hr, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  cudaGetLastError();
+  double *flag = c->d_scratch + 40; const double mine_ok = ok ? 1.0 : 0.0;
+  CU(cudaMemcpyAsync(flag, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NC(nccl().AllReduce(flag, flag, 1, ncclDouble, ncclMin, c->comm.comm, c->stream));
+  double all_ok = 0; CU(cudaMemcpyAsync(&all_ok, flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (all_ok == 1.0) { cm.peer_state = 1; cm.zone_slot = slot_bytes; cm.seq = 0; }
+  else {
+    if (cm.zone_left) cudaIpcCloseMemHandle(cm.zone_left); if (cm.zone_right) cudaIpcCloseMemHandle(cm.zone_right);
+    cudaFree(cm.zone); cm.zone = cm.zone_left = cm.zone_right = nullptr; cudaGetLastError();
+  }
+  if (getenv("KML_DEBUG")) fprintf(stderr, "[kml rank %d] halo exchange: %s\n", cm.rank, cm.peer_state == 1 ? "NVLink peer memory (CUDA IPC)" : "NCCL send/recv");
+  return 0;
+}
+
 // Sum of the node planes shared with the slab neighbours (see kml_comm.cuh).  Local planes [0, nsh) are shared
 // with the left neighbour, [n0 - nsh, n0) with the right one, nsh = stencil span - 1.
 static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
@@ -856,9 +907,22 @@ static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
   if (what & P2G_HEAT) { add(g.Qext, 1, 0); add(g.Qint, 1, 0); }
   if (hf.n == 0) return 0;
   size_t total = 0; for (int f = 0; f < hf.n; f++) total += (size_t)cnt * hf.width[f];
+  const int left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
+  if (cm.peer_state == 0 && halo_peer_setup(c, sizeof(double) * (size_t)cnt * 13)) return 1; // 13 doubles per node: every field a pass can exchange
+  if (cm.peer_state == 1 && total * sizeof(double) <= cm.zone_slot) { // pack straight into the neighbours' memory over NVLink, add from ours
+    const unsigned long long seq = ++cm.seq; const size_t b = seq & 1, sl = cm.zone_slot;
+    double *remL = left ? (double *)(cm.zone_left + HALO_ZONE_HDR + (2 + b) * sl) : nullptr;  // the left neighbour's "from the right" buffer
+    double *remR = right ? (double *)(cm.zone_right + HALO_ZONE_HDR + (0 + b) * sl) : nullptr; // the right neighbour's "from the left" buffer
+    unsigned long long *fL = left ? (unsigned long long *)(cm.zone_left + 128) : nullptr, *fR = right ? (unsigned long long *)(cm.zone_right + 0) : nullptr;
+    const long long top_ = (long long)(g.n[0] - nsh) * plane;
+    k_halo_push<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top_, remL, remR, fL, fR, seq, cm.push_done);
+    const double *inL = left ? (const double *)(cm.zone + HALO_ZONE_HDR + (0 + b) * sl) : nullptr, *inR = right ? (const double *)(cm.zone + HALO_ZONE_HDR + (2 + b) * sl) : nullptr;
+    k_halo_wait_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top_, inL, inR, (const unsigned long long *)(cm.zone + 0), (const unsigned long long *)(cm.zone + 128), seq);
+    c->launches[stage] += 2;
+    return check_launch("halo_sum (peer memory)");
+  }
   const size_t need = total * 4 * sizeof(double);
   if (need > cm.halo_bytes) { cudaFree(cm.halo_buf); cm.halo_buf = nullptr; CU(cudaMalloc(&cm.halo_buf, need)); cm.halo_bytes = need; }
-  const int left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
   double *sl = cm.halo_buf, *sr = sl + total, *rl = sr + total, *rr = rl + total;
   const long long top = (long long)(g.n[0] - nsh) * plane;
   k_halo_pack<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top, sl, sr, left, right);
@@ -1091,7 +1155,9 @@ static int resolve_dt(kml_ctx *c) {
   CU(cudaEventSynchronize(c->ev_dt));
   const int ns = (int)c->solids.size();
   unsigned flags = 0; for (int b = 0; b < 8; b++) if (c->h_red[KML_RED_BITS + b] != 0.0) flags |= 1u << b;
-  if (c->comm.nranks > 1 && c->h_red[KML_RED_BITS + 8] != 0.0) c->permute_go = true; // some rank asked: every rank re-orders at its next re-bin
+  // some rank asked: every rank re-orders at its next re-bin.  A request that was made before the permute of this or the previous step is stale
+  // (the ranks around the threshold ask one after the other; the all-reduce delivers each request one step late).
+  if (c->comm.nranks > 1 && c->h_red[KML_RED_BITS + 8] != 0.0 && c->steps_started - c->last_collective_permute > 1) c->permute_go = true;
   if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow, 32: particle migration bookkeeping)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
