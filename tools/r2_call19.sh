@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call 14 (8 GPUs): the 8-slab stepping test + the new decomposed variants, strong-scaling bench at N = 8 (twice: with the parity check, then without)
+# round 2, call 19 (4 GPUs): the whole slab suite on the final tree (peer-memory halo), strong-scaling bench at N = 4 and N = 2 with the parity check
 cd "$(dirname "$0")/.."
-TAG=${1:-r2n}
+TAG=${1:-r2s}
 mkdir -p gpurun_out; rm -f gpurun_out/slab_results.log
-python -m pytest tests/test_slab.py -m gpu -q --timeout 900 -k "eight" > gpurun_out/pytest_slab_$TAG.log 2>&1; tail -4 gpurun_out/pytest_slab_$TAG.log; cut -c1-300 gpurun_out/slab_results.log; grep -o "against-the-reference.*" gpurun_out/slab_results.log | cut -c1-400
+python -m pytest tests/test_slab.py -m gpu -q --timeout 900 > gpurun_out/pytest_slab_$TAG.log 2>&1; tail -3 gpurun_out/pytest_slab_$TAG.log; grep -E "SLAB-FAIL" gpurun_out/pytest_slab_$TAG.log | head -5 | cut -c1-500
 runN() { n=$1; shift; echo "== N=$n $*"; env "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $n --steps 20 --warmup 5 --no-e2e 2> gpurun_out/n${n}_stderr_$TAG.log > gpurun_out/bench_n${n}_$TAG.log; grep '^{' gpurun_out/bench_n${n}_$TAG.log | tail -1 | python -c "
 import sys,json
 try:
@@ -11,6 +11,7 @@ try:
     for k,v in r.get('per_rank_stage_ms',{}).items(): print('   ', k, v)
 except Exception as e: print('FAILED', e)"; }
 {
-runN 8 KML_DEBUG=1
+runN 4 KML_X=0
+runN 2 KML_X=0
 } > gpurun_out/ab_$TAG.log 2>&1
-cat gpurun_out/ab_$TAG.log; grep "halo exchange\|physical permute" gpurun_out/n8_stderr_$TAG.log | cut -c1-160 | head -12
+cat gpurun_out/ab_$TAG.log
