@@ -133,14 +133,16 @@ def step(args):
                 worst[k] = max(worst.get(k, 0.0), rel_either(got[k], ref[k], keep[k]))
                 branch = max(branch, rel(keep[k], ref[k]))
         # 1e-10 of the field magnitude, with one allowance: the CUDA run takes its OWN coin flips on `wf != 0` (a particle position that differs
-        # from the oracle's in the last bit), also where the oracle run has none.  One flip moves F by at most |v| dw dt = 4e-13, which this
-        # block (bulk modulus 833, yield stress 3) shows as 1.2e-10 of max|sigma|: the stress of drifting cases is held to 1e-10 + that bound.
+        # from the oracle's in the last bit), also where the oracle run has none.  The weight can round to zero up to 2 - r = 1.3e-5, where the
+        # dropped gradient is 9e-11 / h: one flip moves F by at most |v| dw dt = 0.06 x 9e-11 x 0.42 = 2.3e-12, which this block (bulk modulus
+        # 833, yield stress 3) shows as up to 6e-10 of max|sigma| (the flips observed so far: 3e-13 in F, 1.0-1.7e-10 in the stress).  The stress of
+        # drifting cases is held to 1e-10 + that bound; F and x, on which the flip acts directly, stay far inside 1e-10.
         tol = {k: 1e-10 for k in worst}
         if args.drift:
-            tol["SIGMA"] = 2.5e-10
+            tol["SIGMA"] = 7e-10
         bad = {k: v for k, v in worst.items() if v > tol[k]}
         assert not bad, (bad, worst, strict)
-        assert worst["FDEF"] <= 1e-12 and worst["X"] <= 1e-13, worst  # the quantities the flip acts on stay far inside the tolerance
+        assert worst["FDEF"] <= 5e-12 and worst["X"] <= 1e-13, worst
         assert abs(st["dt"] - st_ref["dt"]) <= 1e-10 * st_ref["dt"] and st["ntimestep"] == st_ref["ntimestep"]
         if args.drift:
             assert any(a != b for a, b in moved), "no particle migrated: the test does not exercise exchange_particles"
