@@ -1205,18 +1205,26 @@ int kml_exchange_particles(kml_ctx *c) {
     if (S->moved) { for (int k = 0; k < 3; k++) std::swap(s.x[k], s.xn[k]); S->moved = false; }
     const int xs = (int)((s.x[0] - S->buf) / S->cap); // buffer slot of the current positions (0 or 3), see k_mig_pack
     const int narr = SOLID_NDBL_UL + (s.Lst[0] ? 9 : 0); // the stored velocity gradient of the APIC family / gradient-enhanced projection follows the UL block
-    const int cap_mig = (int)std::min<long long>(std::max<long long>(s.np / 8, 1024), 1 << 24);
-    if (cap_mig > cm.mig_cap) {
+    auto reserve = [&](long long want) -> int { // migration scratch for `want` particles per direction (never shrinks)
+      const int cap_mig = (int)std::min<long long>(want, 1 << 26);
+      if (cap_mig <= cm.mig_cap && (size_t)(narr + 2) * 2 * cm.mig_cap * sizeof(double) <= cm.mig_bytes) return 0;
+      const int cap_new = std::max(cap_mig, cm.mig_cap);
       cudaFree(cm.mig_list); cudaFree(cm.mig_send); cudaFree(cm.mig_recv); cudaFree(cm.mig_flag);
-      CU(cudaMalloc(&cm.mig_list, sizeof(int) * 6 * (size_t)cap_mig)); // leavers left | right (cap each), holes, fillers (2 cap each: up to nL + nR entries)
-      CU(cudaMalloc(&cm.mig_flag, sizeof(int) * 2 * (size_t)cap_mig));
-      cm.mig_bytes = sizeof(double) * (size_t)(narr + 2) * 2 * cap_mig;
+      CU(cudaMalloc(&cm.mig_list, sizeof(int) * 6 * (size_t)cap_new)); // leavers left | right (cap each), holes, fillers (2 cap each: up to nL + nR entries)
+      CU(cudaMalloc(&cm.mig_flag, sizeof(int) * 2 * (size_t)cap_new));
+      cm.mig_bytes = sizeof(double) * (size_t)(narr + 2) * 2 * cap_new;
       CU(cudaMalloc(&cm.mig_send, cm.mig_bytes)); CU(cudaMalloc(&cm.mig_recv, cm.mig_bytes));
-      cm.mig_cap = cap_mig;
-    }
-    CU(cudaMemsetAsync(cm.mig_cnt, 0, 8 * sizeof(int), c->stream));
-    k_mig_mark<<<nblocks(s.np, 256), 256, 0, c->stream>>>(s.x[0], s.np, G->g.lo[0], G->g.inv_cellsize, c->c.shape_function == KML_SHAPE_LINEAR,
-                                                          G->d.base_lo, G->d.base_hi, cm.rank, cm.nranks, cm.mig_cnt, cm.mig_list, cm.mig_cap);
+      cm.mig_cap = cap_new;
+      return 0;
+    };
+    auto mark = [&]() -> int {
+      CU(cudaMemsetAsync(cm.mig_cnt, 0, 8 * sizeof(int), c->stream));
+      k_mig_mark<<<nblocks(s.np, 256), 256, 0, c->stream>>>(s.x[0], s.np, G->g.lo[0], G->g.inv_cellsize, c->c.shape_function == KML_SHAPE_LINEAR,
+                                                            G->d.base_lo, G->d.base_hi, cm.rank, cm.nranks, cm.mig_cnt, cm.mig_list, cm.mig_cap);
+      return 0;
+    };
+    { const char *e = getenv("KML_MIG_CAP"); if (reserve(e && *e ? atoll(e) : std::max<long long>(s.np / 8, 1024))) return 1; } // KML_MIG_CAP: test knob (forces the growth path)
+    if (mark()) return 1;
     const bool left = cm.rank > 0, right = cm.rank < cm.nranks - 1;
     NC(nccl().GroupStart());
     if (left) { NC(nccl().Send(cm.mig_cnt + 0, 1, ncclInt, cm.rank - 1, cm.comm, c->stream)); NC(nccl().Recv(cm.mig_cnt + 2, 1, ncclInt, cm.rank - 1, cm.comm, c->stream)); }
@@ -1226,7 +1234,14 @@ int kml_exchange_particles(kml_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     const int nL = cm.h_cnt[0], nR = cm.h_cnt[1], rL = cm.h_cnt[2], rR = cm.h_cnt[3];
     c->launches[KML_STAGE_MIGRATE]++;
-    if (nL > cm.mig_cap || nR > cm.mig_cap || rL > cm.mig_cap || rR > cm.mig_cap) return fail("particle migration buffer overflow");
+    if (nL > cm.mig_cap || nR > cm.mig_cap || rL > cm.mig_cap || rR > cm.mig_cap) {
+      // more migrants than the scratch holds (a body entering a slab): grow it and, if this rank's own lists were cut off, mark again.  Every rank
+      // decides from counts it already has; the payload exchange below is sized by those counts, so no rank waits for another's decision.
+      const bool relist = nL > cm.mig_cap || nR > cm.mig_cap;
+      const long long need = std::max(std::max(nL, nR), std::max(rL, rR));
+      if (reserve(need + need / 2 + 1024)) return 1;
+      if (relist && mark()) return 1; // same particles, same counts; only the lists were truncated
+    }
     if (nL + nR + rL + rR == 0) continue;
     const long long np_new = s.np - nL - nR;
     if (np_new + rL + rR > S->cap) return fail("particle capacity exceeded by migration");

@@ -25,9 +25,12 @@ def free_port():
 
 
 def launch(world, args, timeout=600):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), WORKER] + args
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    for attempt in range(3):  # the probed port can be taken again before the rendezvous binds it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", str(free_port()), WORKER] + args
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        if not (p.returncode != 0 and "EADDRINUSE" in p.stderr):
+            break
     if not (p.returncode == 0 and "SLAB-OK" in p.stdout):
         fails = [ln for ln in p.stdout.splitlines() if ln.startswith("SLAB-FAIL")]
         raise AssertionError("worker failed (rc %d)\n%s\n%s" % (p.returncode, "\n".join(fails) or p.stdout[-1500:], p.stderr[-1500:]))
