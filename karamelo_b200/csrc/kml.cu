@@ -67,6 +67,7 @@ struct kml_ctx {
   bool keep_acc = false; long long steps_started = 0; // kml_keep_particle_acceleration
   double *d_red = nullptr, *h_red = nullptr; cudaEvent_t ev_dt = nullptr; bool dt_pending = false; double dt_factor = 1.0; // deferred adjust_dt (resolve_dt)
   bool pending_g2p = false; int pending_grad = -1; bool pending_F = false; bool grad_moved = false;
+  struct ContactScratch { int *start = nullptr, *cell_of = nullptr, *rank = nullptr, *order = nullptr; void *scan_tmp = nullptr; size_t scan_bytes = 0; long long nbins_cap = 0, np_cap = 0; } contact; // bins of the cell-list contact kernel
   bool permute_want = false, permute_go = false, dt_collective = false; long long last_collective_permute = -10; // decomposed runs: a rank's wish travels with the dt all-reduce and all ranks re-order in the same step (no rank waits for another's permute)
   double permute_frac = 0.05; int permute_min_steps = 2, permute_every = 0; // KML_PERMUTE_FRAC (negative: never), KML_PERMUTE_MIN_STEPS
   int g2p_tma = 4; int nsm = 148; // KML_G2P_TMA: 0 = tile through registers, 1 / 3 = persistent TMA-fed kernel, 4 = one block per segment with a bulk-copied tile (default)
@@ -233,6 +234,7 @@ int kml_destroy(kml_ctx *c) {
     cudaFree(c->comm.halo_buf); cudaFree(c->comm.mig_cnt); cudaFree(c->comm.mig_list); cudaFree(c->comm.mig_flag);
     cudaFree(c->comm.mig_send); cudaFree(c->comm.mig_recv); cudaFreeHost(c->comm.h_cnt);
   }
+  cudaFree(c->contact.start); cudaFree(c->contact.cell_of); cudaFree(c->contact.rank); cudaFree(c->contact.order); cudaFree(c->contact.scan_tmp);
   cudaFree(c->d_flags); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned); cudaFree(c->d_stage); cudaFree(c->d_red); cudaFreeHost(c->h_red); if (c->ev_dt) cudaEventDestroy(c->ev_dt);
   for (auto &p : c->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1393,8 +1395,35 @@ static int contact(kml_ctx *c, int s1, int s2, int hertz, double mu, double ftot
   CU(cudaMemsetAsync(c->d_scratch, 0, 3 * sizeof(double), c->stream));
   // contact uses the current positions: for UL these are the step-start positions (x)
   SolidDev a = A->s, b = B->s;
-  k_contact<<<nblocks(a.np, 128), 128, 0, c->stream>>>(a, b, cp, c->d_scratch);
-  c->launches[KML_STAGE_CONTACT]++;
+  // large bodies: bin solid 2 by the reference's first screen and visit 3^dim bins per particle (kml_kernels.cuh k_contact_bins); KML_CONTACT=bins | pairs forces a path
+  const char *mode = getenv("KML_CONTACT");
+  bool bins = mode ? !strcmp(mode, "bins") : (double)a.np * (double)b.np > 5.0e7;
+  ContactBins cb; long long nbins = 1;
+  if (bins) {
+    cb.inv = 1.0 / cp.max_cellsize; cb.dim3 = c->c.dimension == 3;
+    for (int d = 0; d < 3; d++) {
+      cb.lo[d] = c->c.boxlo[d];
+      cb.n[d] = (d == 2 && !cb.dim3) ? 1 : std::max(1, (int)std::ceil((c->c.boxhi[d] - c->c.boxlo[d]) * cb.inv) + 1);
+      nbins *= cb.n[d];
+    }
+    if (nbins > (1ll << 27) || b.np >= (1ll << 31)) bins = false; // too fine a box for a dense bin table: the all-pairs sweep stays correct
+  }
+  if (bins) {
+    kml_ctx::ContactScratch &w = c->contact;
+    if (nbins + 1 > w.nbins_cap) { cudaFree(w.start); CU(cudaMalloc(&w.start, sizeof(int) * (nbins + 1))); w.nbins_cap = nbins + 1; cudaFree(w.scan_tmp); w.scan_tmp = nullptr; w.scan_bytes = 0; }
+    if (b.np > w.np_cap) { cudaFree(w.cell_of); cudaFree(w.rank); cudaFree(w.order); const long long cap = b.np + b.np / 8 + 1024;
+      CU(cudaMalloc(&w.cell_of, sizeof(int) * cap)); CU(cudaMalloc(&w.rank, sizeof(int) * cap)); CU(cudaMalloc(&w.order, sizeof(int) * cap)); w.np_cap = cap; }
+    if (!w.scan_tmp) { cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, w.start, w.start, (int)(nbins + 1), c->stream); CU(cudaMalloc(&w.scan_tmp, w.scan_bytes)); }
+    CU(cudaMemsetAsync(w.start, 0, sizeof(int) * (nbins + 1), c->stream));
+    k_contact_bin_count<<<nblocks(b.np, 256), 256, 0, c->stream>>>(b, cb, w.cell_of, w.rank, w.start);
+    if (cub::DeviceScan::ExclusiveSum(w.scan_tmp, w.scan_bytes, w.start, w.start, (int)(nbins + 1), c->stream) != cudaSuccess) return fail("contact bins: scan failed");
+    k_contact_bin_fill<<<nblocks(b.np, 256), 256, 0, c->stream>>>(b.np, w.cell_of, w.rank, w.start, w.order);
+    k_contact_bins<<<nblocks(a.np, 128), 128, 0, c->stream>>>(a, b, cp, cb, w.start, w.order, c->d_scratch);
+    c->launches[KML_STAGE_CONTACT] += 4;
+  } else {
+    k_contact<<<nblocks(a.np, 128), 128, 0, c->stream>>>(a, b, cp, c->d_scratch);
+    c->launches[KML_STAGE_CONTACT]++;
+  }
   if (check_launch("k_contact")) return 1;
   A->mbp_nonzero = B->mbp_nonzero = true;
   if (ftot) return read_scratch3(c, ftot);

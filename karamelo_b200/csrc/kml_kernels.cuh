@@ -692,74 +692,62 @@ __global__ void k_fix_force_apply(GridDev g, int groupbit, int set_mask, double 
 // reference are applied in order so the pair set is identical.
 struct ContactParams { int dim, hertz, axisymmetric, temp; double Estar, max_cellsize, mu, dt, alpha, invcp1, invcp2; };
 
-__global__ void __launch_bounds__(128) k_contact(SolidDev s1, SolidDev s2, ContactParams cp, double *ftot) {
-  __shared__ double sx[128], sy[128], sz[128], svol[128], sm[128], svx[128], svy[128], svz[128];
-  const long long i1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool act = i1 < s1.np;
-  double x1 = 0, y1 = 0, z1 = 0, vol1 = 1, m1 = 1, vx1 = 0, vy1 = 0, vz1 = 0;
-  if (act) { x1 = s1.x[0][i1]; y1 = s1.x[1][i1]; z1 = s1.x[2][i1]; vol1 = s1.vol[i1]; m1 = s1.mass[i1]; vx1 = s1.v[0][i1]; vy1 = s1.v[1][i1]; vz1 = s1.v[2][i1]; }
-  double Rp1;
-  if (cp.dim == 2) Rp1 = 0.5 * sqrt(cp.axisymmetric && !cp.hertz ? vol1 / x1 : vol1);
-  else Rp1 = cp.hertz ? 0.5 * pow(vol1, 0.333333333) : 0.5 * cbrt(vol1);
-  double f1[3] = {0, 0, 0}, g1 = 0, ft[3] = {0, 0, 0};
+// One particle pair of the contact fixes (src/fix_contact_hertz.cpp:105-192, src/fix_contact_min_penetration.cpp:112-252): the reference's three
+// screens in its order, then the force.  Particle 1's share is accumulated in registers (f1, g1), particle 2's goes out as atomics.
+struct ContactP1 { double x, y, z, vol, m, vx, vy, vz, Rp; long long i; };
+__device__ __forceinline__ double contact_radius(const ContactParams &cp, double vol, double x) {
+  if (cp.dim == 2) return 0.5 * sqrt(cp.axisymmetric && !cp.hertz ? vol / x : vol);
+  return cp.hertz ? 0.5 * pow(vol, 0.333333333) : 0.5 * cbrt(vol);
+}
+__device__ __forceinline__ void contact_pair(const SolidDev &s1, const SolidDev &s2, const ContactParams &cp, const ContactP1 &p1, long long j, double x2, double y2, double z2,
+                                             double vol2, double m2, double vx2, double vy2, double vz2, double (&f1)[3], double &g1, double (&ft)[3]) {
   const double mc = cp.max_cellsize;
-  for (long long base = 0; base < s2.np; base += 128) {
-    const long long j = base + threadIdx.x;
-    __syncthreads();
-    if (j < s2.np) { sx[threadIdx.x] = s2.x[0][j]; sy[threadIdx.x] = s2.x[1][j]; sz[threadIdx.x] = s2.x[2][j]; svol[threadIdx.x] = s2.vol[j]; sm[threadIdx.x] = s2.mass[j];
-      svx[threadIdx.x] = s2.v[0][j]; svy[threadIdx.x] = s2.v[1][j]; svz[threadIdx.x] = s2.v[2][j]; }
-    __syncthreads();
-    const int cnt = (int)min((long long)128, s2.np - base);
-    if (!act) continue;
-    for (int t = 0; t < cnt; t++) {
-      const double dx = sx[t] - x1, dy = sy[t] - y1, dz = sz[t] - z1;
-      bool near = dx < mc && dy < mc && dx > -mc && dy > -mc;
-      if (cp.dim == 3 || cp.hertz) near = near && dz < mc && dz > -mc;
-      if (!near) continue;
-      double Rp2;
-      if (cp.dim == 2) Rp2 = 0.5 * sqrt(cp.axisymmetric && !cp.hertz ? svol[t] / sx[t] : svol[t]);
-      else Rp2 = cp.hertz ? 0.5 * pow(svol[t], 0.333333333) : 0.5 * cbrt(svol[t]);
-      const double Rp = Rp1 + Rp2;
-      bool near2 = dx < Rp && dy < Rp && dx > -Rp && dy > -Rp;
-      if (cp.dim == 3 || cp.hertz) near2 = near2 && dz < Rp && dz > -Rp;
-      if (!near2) continue;
-      const double r = sqrt(dx * dx + dy * dy + dz * dz);
-      if (!(r < Rp)) continue;
-      double f[3], g2 = 0;
-      if (cp.hertz) {
-        const double p = Rp - r;
-        const double fmag = (cp.dim == 2 ? 0.25 * M_PI : 1.333333333) * cp.Estar * sqrt(Rp1 * Rp2 / (Rp1 + Rp2) * p * p * p);
-        f[0] = fmag * dx / r; f[1] = fmag * dy / r; f[2] = fmag * dz / r;
-        // s1 -= f ; s2 += f
-        f1[0] -= f[0]; f1[1] -= f[1]; f1[2] -= f[2];
-        atomicAdd(&s2.mbp[0][base + t], f[0]); atomicAdd(&s2.mbp[1][base + t], f[1]); atomicAdd(&s2.mbp[2][base + t], f[2]);
-      } else {
-        const double inv_r = 1.0 / r;
-        const double m2 = sm[t];
-        const double fmag = m1 * m2 / ((m1 + m2) * cp.dt * cp.dt) * (1 - Rp * inv_r);
-        f[0] = fmag * dx; f[1] = fmag * dy; f[2] = fmag * dz;
-        if (cp.mu != 0) {
-          const double dvx = svx[t] - vx1, dvy = svy[t] - vy1, dvz = svz[t] - vz1;
-          const double dd = (dvx * dx + dvy * dy + dvz * dz) * inv_r * inv_r;
-          double vt[3] = {dvx - dd * dx, dvy - dd * dy, dvz - dd * dz};
-          const double vtn = sqrt(vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2]);
-          if (vtn != 0) {
-            const double ffric = cp.mu * fmag * r;
-            f[0] -= ffric * (vt[0] / vtn); f[1] -= ffric * (vt[1] / vtn); f[2] -= ffric * (vt[2] / vtn);
-            if (cp.temp) {
-              if (cp.dim == 2) { const double gm = ffric * vtn * cp.dt; g1 += cp.alpha * s1.vol0[i1] * cp.invcp1 * gm; g2 = (1.0 - cp.alpha) * s2.vol0[base + t] * cp.invcp2 * gm; }
-              else { const double gm = cp.alpha * ffric * vtn * cp.dt; g1 += s1.vol0[i1] * cp.invcp1 * gm; g2 = s2.vol0[base + t] * cp.invcp2 * gm; }
-            }
-          }
+  const double dx = x2 - p1.x, dy = y2 - p1.y, dz = z2 - p1.z;
+  bool near = dx < mc && dy < mc && dx > -mc && dy > -mc;
+  if (cp.dim == 3 || cp.hertz) near = near && dz < mc && dz > -mc;
+  if (!near) return;
+  const double Rp1 = p1.Rp, Rp2 = contact_radius(cp, vol2, x2);
+  const double Rp = Rp1 + Rp2;
+  bool near2 = dx < Rp && dy < Rp && dx > -Rp && dy > -Rp;
+  if (cp.dim == 3 || cp.hertz) near2 = near2 && dz < Rp && dz > -Rp;
+  if (!near2) return;
+  const double r = sqrt(dx * dx + dy * dy + dz * dz);
+  if (!(r < Rp)) return;
+  double f[3], g2 = 0;
+  if (cp.hertz) {
+    const double p = Rp - r;
+    const double fmag = (cp.dim == 2 ? 0.25 * M_PI : 1.333333333) * cp.Estar * sqrt(Rp1 * Rp2 / (Rp1 + Rp2) * p * p * p);
+    f[0] = fmag * dx / r; f[1] = fmag * dy / r; f[2] = fmag * dz / r;
+    // s1 -= f ; s2 += f
+    f1[0] -= f[0]; f1[1] -= f[1]; f1[2] -= f[2];
+    atomicAdd(&s2.mbp[0][j], f[0]); atomicAdd(&s2.mbp[1][j], f[1]); atomicAdd(&s2.mbp[2][j], f[2]);
+  } else {
+    const double inv_r = 1.0 / r;
+    const double m1 = p1.m;
+    const double fmag = m1 * m2 / ((m1 + m2) * cp.dt * cp.dt) * (1 - Rp * inv_r);
+    f[0] = fmag * dx; f[1] = fmag * dy; f[2] = fmag * dz;
+    if (cp.mu != 0) {
+      const double dvx = vx2 - p1.vx, dvy = vy2 - p1.vy, dvz = vz2 - p1.vz;
+      const double dd = (dvx * dx + dvy * dy + dvz * dz) * inv_r * inv_r;
+      double vt[3] = {dvx - dd * dx, dvy - dd * dy, dvz - dd * dz};
+      const double vtn = sqrt(vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2]);
+      if (vtn != 0) {
+        const double ffric = cp.mu * fmag * r;
+        f[0] -= ffric * (vt[0] / vtn); f[1] -= ffric * (vt[1] / vtn); f[2] -= ffric * (vt[2] / vtn);
+        if (cp.temp) {
+          if (cp.dim == 2) { const double gm = ffric * vtn * cp.dt; g1 += cp.alpha * s1.vol0[p1.i] * cp.invcp1 * gm; g2 = (1.0 - cp.alpha) * s2.vol0[j] * cp.invcp2 * gm; }
+          else { const double gm = cp.alpha * ffric * vtn * cp.dt; g1 += s1.vol0[p1.i] * cp.invcp1 * gm; g2 = s2.vol0[j] * cp.invcp2 * gm; }
         }
-        // s1 += f ; s2 -= f
-        f1[0] += f[0]; f1[1] += f[1]; f1[2] += f[2];
-        atomicAdd(&s2.mbp[0][base + t], -f[0]); atomicAdd(&s2.mbp[1][base + t], -f[1]); atomicAdd(&s2.mbp[2][base + t], -f[2]);
-        if (g2 != 0) atomicAdd(&s2.gamma[base + t], g2);
       }
-      ft[0] += f[0]; ft[1] += f[1]; ft[2] += f[2];
     }
+    // s1 += f ; s2 -= f
+    f1[0] += f[0]; f1[1] += f[1]; f1[2] += f[2];
+    atomicAdd(&s2.mbp[0][j], -f[0]); atomicAdd(&s2.mbp[1][j], -f[1]); atomicAdd(&s2.mbp[2][j], -f[2]);
+    if (g2 != 0) atomicAdd(&s2.gamma[j], g2);
   }
+  ft[0] += f[0]; ft[1] += f[1]; ft[2] += f[2];
+}
+__device__ __forceinline__ void contact_finish(const SolidDev &s1, long long i1, bool act, const double (&f1)[3], double g1, const double (&ft)[3], double *ftot) {
   if (act) {
     if (f1[0] != 0 || f1[1] != 0 || f1[2] != 0) { s1.mbp[0][i1] += f1[0]; s1.mbp[1][i1] += f1[1]; s1.mbp[2][i1] += f1[2]; }
     if (g1 != 0) s1.gamma[i1] += g1;
@@ -771,6 +759,69 @@ __global__ void __launch_bounds__(128) k_contact(SolidDev s1, SolidDev s2, Conta
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&ftot[d], x);
   }
+}
+
+// all pairs like the reference, tiled through shared memory (small bodies: C4 has 812 x 812)
+__global__ void __launch_bounds__(128) k_contact(SolidDev s1, SolidDev s2, ContactParams cp, double *ftot) {
+  __shared__ double sx[128], sy[128], sz[128], svol[128], sm[128], svx[128], svy[128], svz[128];
+  const long long i1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i1 < s1.np;
+  ContactP1 p1{0, 0, 0, 1, 1, 0, 0, 0, 0, i1};
+  if (act) { p1.x = s1.x[0][i1]; p1.y = s1.x[1][i1]; p1.z = s1.x[2][i1]; p1.vol = s1.vol[i1]; p1.m = s1.mass[i1]; p1.vx = s1.v[0][i1]; p1.vy = s1.v[1][i1]; p1.vz = s1.v[2][i1]; }
+  p1.Rp = contact_radius(cp, p1.vol, p1.x);
+  double f1[3] = {0, 0, 0}, g1 = 0, ft[3] = {0, 0, 0};
+  for (long long base = 0; base < s2.np; base += 128) {
+    const long long j = base + threadIdx.x;
+    __syncthreads();
+    if (j < s2.np) { sx[threadIdx.x] = s2.x[0][j]; sy[threadIdx.x] = s2.x[1][j]; sz[threadIdx.x] = s2.x[2][j]; svol[threadIdx.x] = s2.vol[j]; sm[threadIdx.x] = s2.mass[j];
+      svx[threadIdx.x] = s2.v[0][j]; svy[threadIdx.x] = s2.v[1][j]; svz[threadIdx.x] = s2.v[2][j]; }
+    __syncthreads();
+    const int cnt = (int)min((long long)128, s2.np - base);
+    if (!act) continue;
+    for (int t = 0; t < cnt; t++) contact_pair(s1, s2, cp, p1, base + t, sx[t], sy[t], sz[t], svol[t], sm[t], svx[t], svy[t], svz[t], f1, g1, ft);
+  }
+  contact_finish(s1, i1, act, f1, g1, ft, ftot);
+}
+
+// Large bodies: the first screen of the reference (|dx_i| < max_cellsize) confines a particle's partners to the 3^dim bins of edge max_cellsize
+// around its own, so solid 2 is binned (count, scan, fill - like the cell lists of the MPM kernels) and every particle of solid 1 visits those
+// bins only: O(N1 x particles per bin neighbourhood) pair tests instead of the reference's O(N1 x N2) sweep, same screens, same pair set.
+struct ContactBins { double lo[3]; double inv; int n[3]; int dim3; }; // dim3: bin along z as well (3-D, and Hertz which screens z in 2-D too)
+__device__ __forceinline__ int contact_bin_axis(double x, double lo, double inv, int n) { const int b = (int)floor((x - lo) * inv); return min(max(b, 0), n - 1); }
+__global__ void k_contact_bin_count(SolidDev s2, ContactBins cb, int *cell_of, int *rank, int *count) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= s2.np) return;
+  const int bx = contact_bin_axis(s2.x[0][j], cb.lo[0], cb.inv, cb.n[0]), by = contact_bin_axis(s2.x[1][j], cb.lo[1], cb.inv, cb.n[1]);
+  const int bz = cb.dim3 ? contact_bin_axis(s2.x[2][j], cb.lo[2], cb.inv, cb.n[2]) : 0;
+  const int key = (bx * cb.n[1] + by) * cb.n[2] + bz;
+  cell_of[j] = key; rank[j] = atomicAdd(&count[key], 1);
+}
+__global__ void k_contact_bin_fill(long long np, const int *cell_of, const int *rank, const int *start, int *order) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < np) order[start[cell_of[j]] + rank[j]] = (int)j;
+}
+__global__ void __launch_bounds__(128) k_contact_bins(SolidDev s1, SolidDev s2, ContactParams cp, ContactBins cb, const int *__restrict__ start, const int *__restrict__ order, double *ftot) {
+  const long long i1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i1 < s1.np;
+  ContactP1 p1{0, 0, 0, 1, 1, 0, 0, 0, 0, i1};
+  double f1[3] = {0, 0, 0}, g1 = 0, ft[3] = {0, 0, 0};
+  if (act) {
+    p1.x = s1.x[0][i1]; p1.y = s1.x[1][i1]; p1.z = s1.x[2][i1]; p1.vol = s1.vol[i1]; p1.m = s1.mass[i1]; p1.vx = s1.v[0][i1]; p1.vy = s1.v[1][i1]; p1.vz = s1.v[2][i1];
+    p1.Rp = contact_radius(cp, p1.vol, p1.x);
+    // partners lie within one bin edge of particle 1's bin (positions outside the box are clamped into the edge bins on both sides)
+    const int bx = contact_bin_axis(p1.x, cb.lo[0], cb.inv, cb.n[0]), by = contact_bin_axis(p1.y, cb.lo[1], cb.inv, cb.n[1]), bz = cb.dim3 ? contact_bin_axis(p1.z, cb.lo[2], cb.inv, cb.n[2]) : 0;
+    for (int ix = max(bx - 1, 0); ix <= min(bx + 1, cb.n[0] - 1); ix++)
+      for (int iy = max(by - 1, 0); iy <= min(by + 1, cb.n[1] - 1); iy++) {
+        const int z0 = cb.dim3 ? max(bz - 1, 0) : 0, z1 = cb.dim3 ? min(bz + 1, cb.n[2] - 1) : 0;
+        if (z0 > z1) continue;
+        const int k0 = (ix * cb.n[1] + iy) * cb.n[2];
+        for (int q = start[k0 + z0]; q < start[k0 + z1 + 1]; q++) { // the bins of a z column are contiguous
+          const int j = order[q];
+          contact_pair(s1, s2, cp, p1, j, s2.x[0][j], s2.x[1][j], s2.x[2][j], s2.vol[j], s2.mass[j], s2.v[0][j], s2.v[1][j], s2.v[2][j], f1, g1, ft);
+        }
+      }
+  }
+  contact_finish(s1, i1, act, f1, g1, ft, ftot);
 }
 
 // ---- reductions for computes -----------------------------------------------------------------
