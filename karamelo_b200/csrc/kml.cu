@@ -213,7 +213,7 @@ int kml_create(const kml_config *cfg, kml_ctx **out) {
   { const int v = env_int("KML_V2G_NB", 2); c->v2g_nb = (v == 1 || v == 4) ? v : 2; }
   // cells per column segment, per kernel family (measured at 100 M particles: the stress kernel wants shorter segments than the other three)
   auto seg_env = [&](const char *name, int dflt) { return std::min(std::max(env_int(name, env_int("KML_SEGLEN", dflt)), 8), 96); };
-  c->gtune.seg_target = seg_env("KML_SEGLEN_P2G", 32);
+  c->gtune.seg_target = seg_env("KML_SEGLEN_P2G", 64); // 64 (and 96) against 32 at 100 M particles: P2G 11.64 vs 12.01 ms, re-projection 4.91 vs 5.04 (gpurun_out/ab_r2w.log)
   c->gtune.seg_g2p = seg_env("KML_SEGLEN_G2P", 32);
   c->gtune.seg_stress = seg_env("KML_SEGLEN_STRESS", 24);
   c->gtune.threads = env_int("KML_GATHER_THREADS", 64) == 128 ? 128 : 64;

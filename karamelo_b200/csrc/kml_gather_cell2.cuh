@@ -224,7 +224,7 @@ k_stress_cell(SolidDev s, GridDev g, StepParams sp, StressParams tp, kml_materia
 }
 
 // measurement knobs (environment, see kml.cu): cells per segment and threads per block
-struct GatherTune { int seg_target = 32, seg_g2p = 32, seg_stress = 24, threads = 64, g2p_threads = 64; }; // seg_target: P2G / re-projection
+struct GatherTune { int seg_target = 64, seg_g2p = 32, seg_stress = 24, threads = 64, g2p_threads = 64; }; // seg_target: P2G / re-projection
 
 // returns 0 = launched, -1 = not covered, 1 = CUDA error
 inline int cell_gather_launch(bool stress, const SolidDev &s, const GridDev &g, const StepParams &sp, const StressParams &tp, const kml_material &mat,
