@@ -316,7 +316,8 @@ int kml_compute_strain_energy(kml_ctx *ctx, int solid, int groupbit, double *es)
 
 /* Device error word, the invariants of SURVEY section 4: bit0 particle left the domain
  * (src/solid.cpp:617-627), bit1 J <= 0 (src/solid.cpp:1208-1215), bit2 dtCFL NaN/0
- * (src/ulmpm.cpp:535-544), bit3 polar decomposition failed (src/solid.cpp:1229-1236). */
+ * (src/ulmpm.cpp:535-544), bit3 polar decomposition failed (src/solid.cpp:1229-1236); engine-side conditions: bit4 CPDI neighbour list
+ * overflow, bit5 particle migration bookkeeping, bit6 halo exchange timed out (a neighbour rank never delivered its shared planes). */
 int kml_error_flags(kml_ctx *ctx, unsigned *flags); /* on a decomposed run: collective (call on every rank), returns the union */
 
 /* ---- slab decomposition over several GPUs (replaces Grid::reduce_ghost_nodes

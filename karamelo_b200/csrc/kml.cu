@@ -919,7 +919,7 @@ static int halo_sum(kml_ctx *c, Grid *G, int what, int stage) {
     const long long top_ = (long long)(g.n[0] - nsh) * plane;
     k_halo_push<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top_, remL, remR, fL, fR, seq, cm.push_done);
     const double *inL = left ? (const double *)(cm.zone + HALO_ZONE_HDR + (0 + b) * sl) : nullptr, *inR = right ? (const double *)(cm.zone + HALO_ZONE_HDR + (2 + b) * sl) : nullptr;
-    k_halo_wait_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top_, inL, inR, (const unsigned long long *)(cm.zone + 0), (const unsigned long long *)(cm.zone + 128), seq);
+    k_halo_wait_add<<<nblocks(cnt, 256), 256, 0, c->stream>>>(hf, cnt, top_, inL, inR, (const unsigned long long *)(cm.zone + 0), (const unsigned long long *)(cm.zone + 128), seq, c->d_flags);
     c->launches[stage] += 2;
     return check_launch("halo_sum (peer memory)");
   }
@@ -1160,7 +1160,7 @@ static int resolve_dt(kml_ctx *c) {
   // some rank asked: every rank re-orders at its next re-bin.  A request that was made before the permute of this or the previous step is stale
   // (the ranks around the threshold ask one after the other; the all-reduce delivers each request one step late).
   if (c->comm.nranks > 1 && c->h_red[KML_RED_BITS + 8] != 0.0 && c->steps_started - c->last_collective_permute > 1) c->permute_go = true;
-  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow, 32: particle migration bookkeeping)");
+  if (flags) return fail("device error flags " + std::to_string(flags) + " (1: particle left the domain, 2: J<=0, 4: NaN wave speed, 8: polar decomposition failed, 16: CPDI neighbour list overflow, 32: particle migration bookkeeping, 64: halo exchange timed out - a neighbour rank never delivered its planes)");
   double dtCFL = 1.0e22;
   for (int i = 0; i < ns; i++) { // src/solid.cpp:1429 then src/ulmpm.cpp:525-551
     Solid *S = c->solids[i]; Grid *G = c->grids[S->d.grid];

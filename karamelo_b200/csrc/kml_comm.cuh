@@ -103,11 +103,14 @@ __global__ void k_halo_push(HaloFields hf, long long cnt, long long top_off_node
     }
   }
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+constexpr unsigned long long HALO_TIMEOUT_NS = 30ull * 1000 * 1000 * 1000; // a neighbour that has not delivered after 30 s is gone: raise bit 6 of the error word instead of spinning for ever
 __global__ void k_halo_wait_add(HaloFields hf, long long cnt, long long top_off_nodes, const double *inL, const double *inR, const unsigned long long *flagL,
-                                const unsigned long long *flagR, unsigned long long seq) { // inL: my landing buffer "from the left" (null: no neighbour)
+                                const unsigned long long *flagR, unsigned long long seq, unsigned *err) { // inL: my landing buffer "from the left" (null: no neighbour)
   if (threadIdx.x == 0) {
-    if (inL) while (ld_volatile_u64(flagL) < seq) __nanosleep(100);
-    if (inR) while (ld_volatile_u64(flagR) < seq) __nanosleep(100);
+    const unsigned long long t0 = global_timer_ns();
+    if (inL) while (ld_volatile_u64(flagL) < seq) { __nanosleep(100); if (global_timer_ns() - t0 > HALO_TIMEOUT_NS) { atomicOr(err, 64u); break; } }
+    if (inR) while (ld_volatile_u64(flagR) < seq) { __nanosleep(100); if (global_timer_ns() - t0 > HALO_TIMEOUT_NS) { atomicOr(err, 64u); break; } }
     __threadfence_system();
   }
   __syncthreads();
