@@ -21,7 +21,6 @@ static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }
 enum { KML_RED_BITS = 64, KML_RED_N = KML_RED_BITS + 16 }; // d_red: [2 i] max wave speed, [2 i + 1] min_h_ratio of solid i; [KML_RED_BITS + b] bit b of the error word; [KML_RED_BITS + 8] a rank asks for a physical permute
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
-#define CUV(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); } } while (0)
 
 struct kml_ctx;
 extern "C" { static int resolve_dt(kml_ctx *c); }
@@ -250,6 +249,7 @@ static const int GRID_NDBL = 4 + 4 + 3 + 3 + 3 + 3; // nv(4) nvu(4) f mb T Qext 
 int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
   CU(cudaSetDevice(c->dev));
   Grid *G = new Grid(); G->d = *d; GridDev &g = G->g;
+  struct Guard { Grid *G; bool keep = false; ~Guard() { if (!keep) { cudaFree(G->buf); cudaFree(G->ibuf); delete G; } } } guard{G}; // a failed CU(...) below returns early
   for (int k = 0; k < 3; k++) { g.lo[k] = d->lo[k]; g.n[k] = d->n[k]; }
   g.h = d->h; g.cellsize = d->cellsize; g.inv_cellsize = 1.0 / d->cellsize;
   g.goff0 = d->goff; g.gn0 = d->gn > 0 ? d->gn : d->n[0];
@@ -277,6 +277,7 @@ int kml_grid_create(kml_ctx *c, const kml_grid_desc *d, int *gid) {
     CU(cudaMemcpyAsync(g.x[k], xs.data(), sizeof(double) * nn, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
+  guard.keep = true;
   c->grids.push_back(G); *gid = (int)c->grids.size() - 1; return 0;
 }
 int kml_grid_nnodes(kml_ctx *c, int gid, int64_t *nn) { *nn = c->grids[gid]->g.nn; return 0; }
@@ -429,6 +430,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   if (c->apic && c->c.shape_function == KML_SHAPE_LINEAR && d->np_per_cell != 0 && d->np_per_cell != 1 && d->np_per_cell != 2)
     return fail("Number of particle per cell not supported with linear shape functions and APIC."); // src/solid.cpp:1453-1460
   Solid *S = new Solid(); S->d = *d; S->rigid = rigid_; if (rigid_) c->has_rigid = true; SolidDev &s = S->s;
+  struct Guard { Solid *S; bool keep = false; ~Guard() { if (!keep) { cudaFree(S->buf); cudaFree(S->lbuf); cudaFree(S->ibuf); cudaFree(S->cpbuf); cudaFree(S->cpibuf); delete S; } } } guard{S}; // a failed CU(...) below returns early
   for (int k = 0; k < 3; k++) { s.acc[k] = nullptr; s.vup[k] = nullptr; }
   s.np = d->np; S->cap = std::max<long long>(d->capacity, d->np);
   long long cap = (S->cap + 31) / 32 * 32;
@@ -457,6 +459,7 @@ int kml_solid_create(kml_ctx *c, const kml_solid_desc *d, int *sid) {
   }
   if (c->keep_acc && alloc_acc(c, S)) return 1;
   CU(cudaStreamSynchronize(c->stream));
+  guard.keep = true;
   c->solids.push_back(S); *sid = (int)c->solids.size() - 1; return 0;
 }
 int kml_solid_np(kml_ctx *c, int sid, int64_t *np) { *np = c->solids[sid]->s.np; return 0; }

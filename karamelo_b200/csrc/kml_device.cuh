@@ -259,7 +259,10 @@ __device__ inline bool poldec3(const double *M, double *R) {
 }
 
 // min |Re(lambda_i)| of a general real 3x3 matrix (TL time-step limiter, src/solid.cpp:1400-1408;
-// the reference uses Eigen::EigenSolver).  Householder-Hessenberg + shifted QR (EISPACK hqr scheme).
+// the reference uses Eigen::EigenSolver).  Reduction to Hessenberg form followed by the implicit double-shift QR iteration for the
+// eigenvalues only, i.e. the algorithm of EISPACK's `hqr` (Martin, Peters & Wilkinson, "The QR algorithm for real Hessenberg matrices",
+// Numer. Math. 14, 219-231 (1970); Handbook for Automatic Computation II, contribution II/14; the same routine appears as `hqr` in
+// Numerical Recipes in C, section 11.6), restated here for a fixed 3 x 3 size - third-party algorithm, not reference code.
 __device__ inline bool eig3_min_abs_real(const double *M, double &out) {
   const int n = 3;
   double a[3][3];
