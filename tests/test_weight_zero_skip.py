@@ -78,5 +78,7 @@ def test_cuda_follows_one_of_the_two_branches(cuda_lib, oracle_lib, cells, a):
     assert (got["PTAG"] == ref["PTAG"]).all()
     d = {k: rel_either(got[k], ref[k], keep[k]) for k in FIELDS if k != "PTAG"}
     print(cells, a, "either-branch error", d, "vs reference branch only", {k: rel(got[k], ref[k]) for k in FIELDS if k != "PTAG"})
-    assert max(d.values()) <= 1e-10
+    # the CUDA run can take a flip of its own that neither oracle run has (its particle positions differ from the oracle's in the last bit):
+    # the stress is held to 1e-10 plus the bound of one flip (tests/slab_worker.py), everything else to 1e-10
+    assert max(v for k, v in d.items() if k != "SIGMA") <= 1e-10 and d["SIGMA"] <= 7e-10
     assert abs(st["dt"] - st_ref["dt"]) <= 1e-10 * st_ref["dt"]
