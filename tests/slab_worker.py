@@ -29,8 +29,40 @@ def partition(args):
     lib = load_host_library(ORACLE_HOST_LIB)
     cells = tuple(args.cells)
     script = block(cells, "musl", args.shape)
+    if args.variant == "two_solids":  # a second, small solid on the same decomposed grid: slabs that hold none of its particles
+        script = script.replace("material(m, eos-strength, e, s)\n", "material(m, eos-strength, e, s)\nmaterial(m2, eos-strength, e, s)\n")
+        x0 = 4 + cells[0] / 2 - 1.5
+        script += ("region(rtool, block, %g, %g, %g, %g, 5, %g)\nsolid(tool, region, rtool, 2, m2, h, 0)\n" % (x0, x0 + 3, 4 + cells[1] + 0.5, 4 + cells[1] + 2.5, 4 + cells[2] - 1))
     eng = slab.make_engine(lib, with_comm=False)
     eng.script(script)
+    if args.variant == "two_solids":
+        tool = {f: eng.download(1, getattr(P, f)) for f in ("PTAG", "X", "MASS")}
+        tools = [None] * world
+        dist.all_gather_object(tools, tool)
+        if rank == 0:
+            ref2 = Engine(lib)
+            ref2.script(script)
+            snaps = ref2.snapshot(("PTAG", "X", "MASS"))
+            n_first = len(snaps[0]["PTAG"])
+            counts2 = [len(t["PTAG"]) for t in tools]
+            assert sum(counts2) == len(snaps[1]["PTAG"]) and min(counts2) == 0, counts2  # some slab holds none of the second solid's particles
+            cat2 = {k: np.concatenate([t[k] for t in tools]) for k in tool}
+            order2 = np.argsort(cat2["PTAG"], kind="stable")
+            assert cat2["PTAG"].min() == n_first + 1  # tags continue after the first solid's GLOBAL count (domain->np_total, src/solid.cpp:2322)
+            for k in cat2:
+                assert (cat2[k][order2] == snaps[1][k]).all(), k
+            print("SLAB-OK second solid world=%d counts=%s" % (world, counts2))
+        first = {f: eng.download(0, getattr(P, f)) for f in ("PTAG", "X", "MASS")}
+        firsts = [None] * world
+        dist.all_gather_object(firsts, first)
+        if rank == 0:  # the first solid is unaffected by the presence of the second (slab_info describes the LAST solid created, so the checks below do not apply)
+            cat1 = {k: np.concatenate([t[k] for t in firsts]) for k in first}
+            order1 = np.argsort(cat1["PTAG"], kind="stable")
+            for k in cat1:
+                assert (cat1[k][order1] == snaps[0][k]).all(), k
+            ref2.close()
+        dist.barrier()
+        return
     info = eng.slab_info(0)
     mine = {f: eng.download(0, getattr(P, f)) for f in ("PTAG", "X", "V", "MASS")}
     parts = [None] * world
@@ -39,6 +71,7 @@ def partition(args):
         ref = Engine(lib)
         ref.script(script)
         full = ref.snapshot(("PTAG", "X", "V", "MASS"))[0]
+        ref.close()
         n_total = len(full["PTAG"])
         infos = [p[0] for p in parts]
         span = 2 if args.shape == "linear" else 4

@@ -46,6 +46,13 @@ def test_partition_cpu(oracle_lib, world, shape):
     launch(world, ["partition", "--cells", "12", "5", "4", "--shape", shape])
 
 
+def test_partition_second_solid_cpu(oracle_lib):
+    """Several solids on one decomposed grid: the second solid is split by the first solid's cuts, a slab may hold none of its particles, tags
+    continue after the first solid's global count."""
+    out = launch(3, ["partition", "--cells", "24", "5", "4", "--variant", "two_solids"])
+    assert "SLAB-OK second solid" in out
+
+
 def test_thin_slab_is_rejected(oracle_lib):
     """A slab thinner than the stencil overlap cannot own its shared planes: the host driver refuses the run."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
