@@ -113,6 +113,7 @@ def load_host_library(path=None):
         "kml_grid_upload": (i32, [vp, i32, i32, vp]),
         "kml_grid_nnodes": (i32, [vp, i32, PL]),
         "kml_solid_np": (i32, [vp, i32, PL]),
+        "kml_solid_generation": (i32, [vp, i32, C.POINTER(C.c_uint64)]),
         "kml_synchronize": (i32, [vp]),
         "kml_profile": (i32, [vp, i32]),
         "kml_stage_times": (i32, [vp, PD, PL, i32]),
@@ -223,6 +224,12 @@ class Engine:
         cur = C.c_int64()
         self._ckk(self.lib.kml_solid_np(self.ctx, sid.value, C.byref(cur)))
         return {"np": cur.value, "solid": sid.value, "grid": gid.value, "n": tuple(n)}
+
+    def solid_generation(self, i):
+        """Bumped whenever the solid's particle set or storage order changed (migration, physical permute, delete_particles)."""
+        g = C.c_uint64()
+        self._ckk(self.lib.kml_solid_generation(self.ctx, self.solid_info(i)["solid"], C.byref(g)))
+        return g.value
 
     def state(self):
         nt, t, dt = C.c_int64(), C.c_double(), C.c_double()
